@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/zl_b200.h declares, and fails loudly (no CPU fallback) when no CUDA device exists."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "zl_b200.h")).read()
+    return sorted(set(re.findall(r"ZL_API\s+[\w\s\*]+?\b(zl_\w+)\s*\(", hdr)))
+
+
+def test_header_declares_expected_surface():
+    syms = _declared_symbols()
+    for must in ("zl_engine_create", "zl_engine_submit", "zl_engine_set_callback", "zl_infer_batch",
+                 "zl_preprocess", "zl_forward_raw", "zl_decode_nms", "zl_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    import zlb200
+    syms = _declared_symbols()
+    assert sorted(zlb200.EXPORTS) == syms, "python binding and header disagree"
+    for s in syms:
+        assert hasattr(built_lib, s), f"{s} missing from libzl_b200.so"
+
+
+def test_error_codes_match_reference_values():
+    # src/common/result.h:14-48
+    hdr = open(os.path.join(ROOT, "include", "zl_b200.h")).read()
+    want = {"ZL_OK": 0, "ZL_INVALID_ARGUMENT": 2, "ZL_NOT_INITIALIZED": 3, "ZL_INFERENCE_ERROR": 200,
+            "ZL_MODEL_NOT_FOUND": 201, "ZL_MODEL_LOAD_FAILED": 202, "ZL_INVALID_INPUT": 203,
+            "ZL_SYSTEM_ERROR": 300, "ZL_INSUFFICIENT_RESOURCES": 303}
+    for k, v in want.items():
+        assert re.search(rf"\b{k}\s*=\s*{v}\b", hdr), k
+
+
+def test_det_layout_is_prefix_of_reference_detection():
+    import zlb200
+    # Detection = {BoundingBox(4 x f32), confidence f32, class_id i32, track_id u32, pad, timestamp u64} = 40 B
+    # (src/common/types.h:16-26); the device record is its first 24 bytes.
+    assert zlb200.DET_DTYPE.itemsize == 24
+    assert [zlb200.DET_DTYPE.fields[n][1] for n in ("x", "y", "w", "h", "confidence", "class_id")] == [0, 4, 8, 12, 16, 20]
+
+
+def test_no_cpu_fallback_without_device(built_lib):
+    import zlb200
+    if built_lib.zl_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(zlb200.ZlError) as ei:
+        zlb200.Engine(416, 416, 4, "n")
+    assert ei.value.code == zlb200.INSUFFICIENT_RESOURCES
+    assert "no CPU fallback" in ei.value.message
+    with pytest.raises(zlb200.ZlError):
+        zlb200.test_conv([[[[0.0] * 16]]], [[[[0.0] * 16]]] * 16, [0.0] * 16)
+
+
+def test_null_handle_is_an_error_not_a_crash(built_lib):
+    assert built_lib.zl_engine_warmup(None, 1) == 2
+    assert built_lib.zl_engine_submit(None, 0, 0, 0, 1, 1, None, 3, 0) == 2
+    assert built_lib.zl_engine_queue_size(None) == 0
+    assert built_lib.zl_engine_destroy(None) == 0
+    assert b"zl_b200" in built_lib.zl_version()

@@ -1,0 +1,191 @@
+"""GPU parity tests of the individual kernels, through the C-ABI, against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_c, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib, model_n4):
+    import zlb200
+    e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP32, max_batch=2, max_frame=(1920, 1080))
+    yield e
+    e.close()
+
+
+# ---------------------------------------------------------------- P1: bit-exact
+@pytest.mark.parametrize("w,h", [(416, 416), (800, 600), (1920, 1080), (37, 53), (415, 417), (1, 1), (640, 360)])
+def test_preprocess_bit_exact(eng, w, h):
+    img = synth.frames_noise(1, h, w, seed=w * 7 + h)[0]
+    code, ref = oracle_c.preprocess(img, w, h, 416, 416)
+    assert code == 0
+    out = eng.preprocess(img, w, h)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def test_preprocess_wrong_length_is_invalid_input(eng):
+    import zlb200
+    with pytest.raises(zlb200.ZlError) as ei:
+        eng.preprocess(np.zeros(100, np.uint8), 10, 10)
+    assert ei.value.code == zlb200.INVALID_INPUT
+    assert "expected 300, got 100" in ei.value.message
+
+
+def test_preprocess_other_model_size(built_lib):
+    import zlb200
+    e = zlb200.Engine(640, 384, 4, "n", precision=zlb200.BF16, max_batch=1, max_frame=(800, 600))
+    img = synth.frames_structured(1, 600, 800)[0]
+    _, ref = oracle_c.preprocess(img, 800, 600, 640, 384)
+    assert np.array_equal(e.preprocess(img, 800, 600), ref)
+    e.close()
+
+
+# ---------------------------------------------------------------- convs
+def _torch_conv(x, w, b, stride, act, res):
+    xt = torch.tensor(x).permute(0, 3, 1, 2)
+    wt = torch.tensor(w).permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(xt, wt, torch.tensor(b), stride=stride, padding=w.shape[1] // 2)
+    if act:
+        y = torch.nn.functional.silu(y)
+    y = y.permute(0, 2, 3, 1).numpy()
+    if res is not None:
+        y = y + res
+    return y
+
+
+def _bf(a):
+    return torch.tensor(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, stride, act, res
+    (1, 13, 13, 64, 64, 3, 1, True, False),
+    (2, 26, 26, 32, 32, 3, 1, True, True),
+    (1, 20, 20, 16, 16, 3, 1, True, True),
+    (1, 40, 40, 16, 32, 3, 2, True, False),
+    (2, 27, 31, 64, 128, 3, 2, True, False),
+    (1, 13, 13, 128, 256, 1, 1, True, False),
+    (1, 52, 52, 48, 32, 1, 1, True, False),
+    (2, 13, 13, 384, 256, 1, 1, True, False),
+    (1, 26, 26, 64, 4, 1, 1, False, False),
+    (1, 26, 26, 64, 80, 1, 1, False, False),
+    (1, 10, 10, 256, 64, 3, 1, True, False),
+    (1, 9, 9, 192, 576, 1, 1, True, False),
+    (3, 16, 16, 96, 48, 3, 1, True, True),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fp32_simt(built_lib, case):
+    import zlb200
+    n, h, w, cin, cout, k, s, act, use_res = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = rng.normal(size=(n, h, w, cin)).astype(np.float32)
+    wt = (rng.normal(size=(cout, k, k, cin)) / np.sqrt(cin * k * k)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    res = rng.normal(size=(n, ho, wo, cout)).astype(np.float32) if use_res else None
+    y = zlb200.test_conv(x, wt, b, stride=s, act=act, res=res, impl=0)
+    ref = _torch_conv(x, wt, b, s, act, res)
+    assert np.abs(y - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tcgen05(built_lib, case, impl):
+    import zlb200
+    n, h, w, cin, cout, k, s, act, use_res = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = _bf(rng.normal(size=(n, h, w, cin)).astype(np.float32))
+    wt = _bf((rng.normal(size=(cout, k, k, cin)) / np.sqrt(cin * k * k)).astype(np.float32))
+    b = rng.normal(size=cout).astype(np.float32)
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    res = _bf(rng.normal(size=(n, ho, wo, cout)).astype(np.float32)) if use_res else None
+    ref = _torch_conv(x, wt, b, s, act, res)
+    # fp32 output: only accumulation order differs (fp32 accumulate in TMEM)
+    y32 = zlb200.test_conv(x, wt, b, stride=s, act=act, res=res, impl=impl, out_f32=True)
+    assert np.abs(y32 - ref).max() < 2e-3 * max(1.0, np.abs(ref).max()), "fp32-out mismatch"
+    # bf16 output: one rounding on top
+    y16 = zlb200.test_conv(x, wt, b, stride=s, act=act, res=res, impl=impl, out_f32=False)
+    assert np.abs(y16 - ref).max() < 1.2e-2 * max(1.0, np.abs(ref).max()), "bf16-out mismatch"
+
+
+@pytest.mark.parametrize("hint", [16, 32, 64])
+def test_conv_tcgen05_n_split(built_lib, hint):
+    import zlb200
+    rng = np.random.default_rng(hint)
+    x = _bf(rng.normal(size=(1, 13, 13, 128)).astype(np.float32))
+    wt = _bf((rng.normal(size=(128, 3, 3, 128)) / 34).astype(np.float32))
+    b = rng.normal(size=128).astype(np.float32)
+    res = _bf(rng.normal(size=(1, 13, 13, 128)).astype(np.float32))
+    ref = _torch_conv(x, wt, b, 1, True, res)
+    y = zlb200.test_conv(x, wt, b, stride=1, act=True, res=res, impl=1, out_f32=True, ntile_hint=hint)
+    assert np.abs(y - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
+# ---------------------------------------------------------------- F1 + N1: bit-exact
+def _check_post(eng, raw, img_w, img_h, conf, iou):
+    got = eng.decode_nms(raw, img_w, img_h, conf, iou)
+    for f in range(raw.shape[0]):
+        ref, _ = oracle_c.postprocess(raw[f], img_w, img_h, conf, iou)
+        assert len(got[f]) == len(ref), f"frame {f}: kept {len(got[f])} vs oracle {len(ref)}"
+        assert np.array_equal(got[f].view(np.uint8), ref.view(np.uint8)), f"frame {f}: detections differ bitwise"
+
+
+def test_post_small_random(eng):
+    _check_post(eng, synth.stress_head(4, 4, 3549, seed=1, img=416), 416, 416, 0.25, 0.45)
+
+
+def test_post_reference_defaults_nc80(eng):
+    _check_post(eng, synth.stress_head(3, 80, 8400, seed=2), 640, 640, 0.5, 0.45)
+
+
+def test_post_stress_low_threshold(eng):
+    # cfg5 shape at a batch the oracle finishes quickly: nearly every anchor is a candidate
+    _check_post(eng, synth.stress_head(6, 80, 8400, seed=42), 640, 640, 0.01, 0.45)
+
+
+def test_post_adversarial_ties_and_clusters(eng):
+    _check_post(eng, synth.stress_head_adversarial(3, 80, 8400, seed=43), 640, 640, 0.01, 0.45)
+    _check_post(eng, synth.stress_head_adversarial(2, 4, 3549, seed=44, img=416), 800, 600, 0.3, 0.5)
+
+
+def test_post_empty_single_and_odd_sizes(eng):
+    raw = np.zeros((3, 6, 77), np.float32)                      # nothing passes
+    raw[1, 0:4, 5] = [10, 10, 4, 4]; raw[1, 4 + 1, 5] = 0.9     # exactly one candidate in frame 1
+    raw[2, 0:4, :] = np.array([[20.0], [20.0], [8.0], [8.0]]); raw[2, 4, :] = 0.8   # 77 identical boxes -> one survivor
+    got = eng.decode_nms(raw, 100, 100, 0.5, 0.45)
+    assert [len(g) for g in got] == [0, 1, 1]
+    _check_post(eng, raw, 100, 100, 0.5, 0.45)
+
+
+def test_post_threshold_edges(eng):
+    raw = np.zeros((1, 7, 64), np.float32)
+    raw[0, 0] = np.arange(64) * 3 + 10; raw[0, 1] = 50; raw[0, 2] = 12; raw[0, 3] = 12
+    raw[0, 4] = 0.5                       # == threshold -> kept
+    raw[0, 5, ::2] = 0.5                  # tie with class 0 -> class 0 wins
+    raw[0, 6, 1::4] = np.nextafter(np.float32(0.5), np.float32(1))
+    for iou in (0.1, 0.45, 0.6):
+        _check_post(eng, raw, 640, 480, 0.5, iou)
+
+
+def test_post_full_cfg5_batch128(eng):
+    # BASELINE.json config 5 at full size: A=8400, nc=80, conf 0.01, batch 128
+    raw = synth.stress_head(128, 80, 8400, seed=42)
+    got = eng.decode_nms(raw, 640, 640, 0.01, 0.45)
+    ref, counts = oracle_c.postprocess_batch(raw, 640, 640, 0.01, 0.45)
+    assert [len(g) for g in got] == list(counts)
+    assert np.array_equal(np.concatenate(got).view(np.uint8), ref.view(np.uint8))
+    # size-independent property: NMS is idempotent — survivors fed back (as one-hot heads) all survive
+    f = 0
+    k = got[f]
+    raw2 = np.zeros((1, 84, len(k)), np.float32)
+    raw2[0, 0] = k["x"] * 640; raw2[0, 1] = k["y"] * 640; raw2[0, 2] = k["w"] * 640; raw2[0, 3] = k["h"] * 640
+    raw2[0, 4 + k["class_id"], np.arange(len(k))] = k["confidence"]
+    again = eng.decode_nms(raw2, 640, 640, 0.01, 0.45)[0]
+    assert len(again) == len(k)

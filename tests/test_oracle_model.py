@@ -1,0 +1,66 @@
+"""Pins the YOLOv8 restatement (oracle/yolov8_ref.py) to the published totals and checks the Detect tail."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolov8_ref as yr
+from oracle import zlw
+
+
+@pytest.mark.parametrize("scale,gflops,mparams", [("n", 8.7, 3.2), ("s", 28.6, 11.2), ("m", 78.9, 25.9)])
+def test_published_flops_and_params(scale, gflops, mparams):
+    # ultralytics' model table at 640x640, nc=80: GFLOPs = 2*MAC, params incl. BN/DFL
+    specs = zlw.conv_specs(scale, 80)
+    shapes = yr.trace_shapes(scale, 80, 640, 640)
+    fl = sum(2 * s["cin"] * s["cout"] * s["k"] ** 2 * h * w for s, (h, w) in zip(specs, shapes)) / 1e9
+    par = sum(s["cin"] * s["cout"] * s["k"] ** 2 + s["cout"] for s in specs) / 1e6
+    assert abs(fl - gflops) / gflops < 0.01
+    assert abs(par - mparams) / mparams < 0.02
+
+
+def test_survey_table_exact():
+    # v8n 416 nc=4 = 3.4159 GFLOP, 63 convs, A=3549 ; v8m has 83 convs
+    specs = zlw.conv_specs("n", 4)
+    shapes = yr.trace_shapes("n", 4, 416, 416)
+    fl = sum(2 * s["cin"] * s["cout"] * s["k"] ** 2 * h * w for s, (h, w) in zip(specs, shapes))
+    assert len(specs) == 63 and round(fl / 1e9, 4) == 3.4159
+    assert yr.num_anchors(416, 416) == 3549 and yr.num_anchors(640, 640) == 8400
+    assert len(zlw.conv_specs("m", 80)) == 83
+
+
+def test_dfl_decode_against_manual():
+    rng = np.random.default_rng(3)
+    B, nc = 2, 3
+    boxes = [torch.tensor(rng.normal(size=(B, 64, h, h)).astype(np.float32)) for h in (4, 2, 1)]
+    clss = [torch.tensor(rng.normal(size=(B, nc, h, h)).astype(np.float32)) for h in (4, 2, 1)]
+    out = yr.dfl_decode(boxes, clss).numpy()
+    assert out.shape == (B, 4 + nc, 21)
+    # anchor 5 of level 0 = (y=1, x=1), stride 8
+    logits = boxes[0][1, :, 1, 1].numpy().reshape(4, 16).astype(np.float64)
+    p = np.exp(logits - logits.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+    l, t, r, b = (p * np.arange(16)).sum(1)
+    ax = ay = 1.5
+    exp = np.array([(ax - l + ax + r) / 2, (ay - t + ay + b) / 2, l + r, t + b]) * 8
+    assert np.allclose(out[1, :4, 5], exp, atol=1e-4)
+    z = clss[0][1, :, 1, 1].numpy().astype(np.float64)
+    assert np.allclose(out[1, 4:, 5], 1 / (1 + np.exp(-z)), atol=1e-6)
+    # level order: stride-8 map row-major, then 16, then 32
+    z2 = clss[2][0, :, 0, 0].numpy().astype(np.float64)
+    assert np.allclose(out[0, 4:, 20], 1 / (1 + np.exp(-z2)), atol=1e-6)
+
+
+def test_forward_shapes_and_determinism(model_n4):
+    tensors, blob = model_n4
+    x = np.random.default_rng(0).uniform(0, 1, (1, 3, 64, 64)).astype(np.float32)
+    a = yr.forward_raw(tensors, "n", 4, x)
+    b = yr.forward_raw(zlw.loads(blob)[0], "n", 4, x)
+    assert a.shape == (1, 8, 84) and np.array_equal(a, b)
+    assert np.all(a[:, 4:] >= 0) and np.all(a[:, 4:] <= 1)
+
+
+def test_container_roundtrip(model_n4):
+    tensors, blob = model_n4
+    back, scale, nc = zlw.loads(blob)
+    assert scale == "n" and nc == 4 and list(back) == list(tensors)
+    for k in tensors:
+        assert np.array_equal(back[k], tensors[k])

@@ -1,0 +1,335 @@
+// capi.cpp — the extern "C" surface declared in include/zl_b200.h.
+// No exception may cross this boundary (the reference wraps every engine call in
+// try/catch and returns Result::error, onnx_engine.cpp:165-169,621-645).
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <vector>
+
+#include "engine.h"
+
+struct zl_engine {
+    zl::Engine* impl;
+};
+
+using zl::Engine;
+
+#define ZL_GUARD_BEGIN try {
+#define ZL_GUARD_END                                                        \
+    } catch (const std::bad_alloc&) {                                       \
+        zl::set_error("out of host memory");                                \
+        return ZL_INSUFFICIENT_RESOURCES;                                   \
+    } catch (const std::exception& ex) {                                    \
+        zl::set_error(std::string("exception: ") + ex.what());              \
+        return ZL_UNKNOWN_ERROR;                                            \
+    } catch (...) {                                                         \
+        zl::set_error("unknown exception");                                 \
+        return ZL_UNKNOWN_ERROR;                                            \
+    }
+
+#define ZL_CHECK_ENGINE(e)                                                  \
+    if (!(e) || !(e)->impl) {                                               \
+        zl::set_error("null engine handle");                                \
+        return ZL_INVALID_ARGUMENT;                                         \
+    }
+
+extern "C" {
+
+void zl_config_default(zl_config* c)
+{
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->device = 0;
+    c->model_w = 416; c->model_h = 416;          // constants::DEFAULT_MODEL_WIDTH/HEIGHT (src/common/constants.h:26-27)
+    c->num_classes = 4;                          // constants::cs16::CLASS_COUNT (:39)
+    c->scale = ZL_SCALE_N;
+    c->precision = ZL_PRECISION_BF16;
+    c->conf_threshold = 0.5f;                    // DEFAULT_CONF_THRESHOLD (:28)
+    c->iou_threshold = 0.45f;                    // DEFAULT_NMS_THRESHOLD (:29)
+    c->class_weights = nullptr;
+    c->max_batch = 1;
+    c->max_frame_w = 0; c->max_frame_h = 0;
+    c->preprocess_mode = ZL_PRE_STRETCH_NEAREST;
+    c->queue_depth = 8;                          // INFERENCE_QUEUE_SIZE
+    c->num_lanes = 1;
+    c->use_graph = 1;
+    c->batch_window_us = 0;
+}
+
+int32_t zl_engine_create(const zl_config* cfg, zl_engine** out)
+{
+    ZL_GUARD_BEGIN
+    if (!cfg || !out) { zl::set_error("null argument"); return ZL_INVALID_ARGUMENT; }
+    *out = nullptr;
+    std::unique_ptr<Engine> e(new Engine(*cfg));
+    int32_t rc = e->init();
+    if (rc != ZL_OK) return rc;
+    zl_engine* h = new zl_engine{e.release()};
+    *out = h;
+    return ZL_OK;
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_destroy(zl_engine* e)
+{
+    ZL_GUARD_BEGIN
+    if (!e) return ZL_OK;
+    delete e->impl;
+    delete e;
+    return ZL_OK;
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_load_weights_mem(zl_engine* e, const void* blob, size_t len)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (!blob) { zl::set_error("null blob"); return ZL_INVALID_ARGUMENT; }
+    return e->impl->load_weights(blob, len);
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_load_weights(zl_engine* e, const char* path)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (!path) { zl::set_error("null path"); return ZL_INVALID_ARGUMENT; }
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) { zl::set_error(std::string("Model file not found: ") + path); return ZL_MODEL_NOT_FOUND; }   // onnx_engine.cpp:961-966
+    const std::streamsize n = f.tellg();
+    f.seekg(0);
+    std::vector<char> buf((size_t)n);
+    if (!f.read(buf.data(), n)) { zl::set_error(std::string("cannot read ") + path); return ZL_MODEL_LOAD_FAILED; }
+    return e->impl->load_weights(buf.data(), buf.size());
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_warmup(zl_engine* e, int32_t iters)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->warmup(iters);
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_set_callback(zl_engine* e, zl_result_fn fn, void* user)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    e->impl->cb = fn;
+    e->impl->cb_user = user;
+    return ZL_OK;
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_submit(zl_engine* e, uint32_t client_id, uint32_t frame_id, uint64_t timestamp,
+                         int32_t width, int32_t height, const uint8_t* bgr, size_t len, int32_t /*is_keyframe*/)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->submit(client_id, frame_id, timestamp, width, height, bgr, len);
+    ZL_GUARD_END
+}
+
+size_t zl_engine_queue_size(const zl_engine* e)
+{
+    try { return (e && e->impl) ? e->impl->queue_size() : 0; } catch (...) { return 0; }
+}
+
+int32_t zl_engine_drain(zl_engine* e)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->drain();
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_get_stats(const zl_engine* e, zl_stats* out)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (!out) { zl::set_error("null out"); return ZL_INVALID_ARGUMENT; }
+    e->impl->get_stats(out);
+    return ZL_OK;
+    ZL_GUARD_END
+}
+
+int32_t zl_infer_batch(zl_engine* e, const uint8_t* const* frames, const int32_t* widths, const int32_t* heights, int32_t n,
+                       zl_det* dets_out, int32_t det_capacity, int32_t* counts, int32_t* offsets)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->infer_batch(frames, widths, heights, n, dets_out, det_capacity, counts, offsets, nullptr);
+    ZL_GUARD_END
+}
+
+int32_t zl_preprocess(zl_engine* e, const uint8_t* bgr, int32_t width, int32_t height, size_t len, float* out_chw)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->preprocess_one(bgr, width, height, len, out_chw);
+    ZL_GUARD_END
+}
+
+int32_t zl_forward_raw(zl_engine* e, const uint8_t* const* frames, const int32_t* widths, const int32_t* heights, int32_t n, float* raw_out)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (!raw_out) { zl::set_error("null raw_out"); return ZL_INVALID_ARGUMENT; }
+    return e->impl->infer_batch(frames, widths, heights, n, nullptr, 0, nullptr, nullptr, raw_out);
+    ZL_GUARD_END
+}
+
+int32_t zl_decode_nms(zl_engine* e, const float* raw, int32_t n, int32_t nc, int32_t A, const int32_t* img_w, const int32_t* img_h,
+                      float conf_thr, float iou_thr, zl_det* dets_out, int32_t det_capacity, int32_t* counts, int32_t* offsets)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (!dets_out) { zl::set_error("null dets_out"); return ZL_INVALID_ARGUMENT; }
+    return e->impl->decode_nms(raw, n, nc, A, img_w, img_h, conf_thr, iou_thr, dets_out, det_capacity, counts, offsets, 1, nullptr, nullptr, nullptr);
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_num_anchors(const zl_engine* e) { return (e && e->impl) ? e->impl->num_anchors : 0; }
+
+int32_t zl_engine_upload_resident(zl_engine* e, int32_t set, const uint8_t* const* frames, const int32_t* widths, const int32_t* heights, int32_t n)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->upload_resident(set, frames, widths, heights, n);
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_run_resident(zl_engine* e, int32_t n_sets, int32_t steps, float* total_ms, int64_t* launches, int64_t* total_dets)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->run_resident(n_sets, steps, total_ms, launches, total_dets);
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters, zl_op_profile* out, int32_t cap, int32_t* n_out)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->profile(set, iters, out, cap, n_out);
+    ZL_GUARD_END
+}
+
+int32_t zl_bench_preprocess(zl_engine* e, int32_t width, int32_t height, int32_t n, int32_t iters, float* ms_per_launch, double* bytes_per_launch)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->bench_preprocess(width, height, n, iters, ms_per_launch, bytes_per_launch);
+    ZL_GUARD_END
+}
+
+int32_t zl_bench_decode_nms(zl_engine* e, const float* raw, int32_t n, int32_t nc, int32_t A, float conf_thr, float iou_thr,
+                            int32_t iters, float* ms_filter, float* ms_nms, int64_t* kept)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    std::vector<int32_t> iw(n, 640), ih(n, 640);
+    return e->impl->decode_nms(raw, n, nc, A, iw.data(), ih.data(), conf_thr, iou_thr, nullptr, 0, nullptr, nullptr, iters + 1, ms_filter, ms_nms, kept);
+    ZL_GUARD_END
+}
+
+void* zl_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); zl::set_error("cudaHostAlloc failed"); return nullptr; }
+    return p;
+}
+void zl_host_free(void* p) { if (p) cudaFreeHost(p); }
+const char* zl_last_error(void) { return zl::get_error(); }
+const char* zl_version(void) { return "zl_b200 0.1 (sm_100a)"; }
+int32_t zl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- unit-test hook: one convolution, host tensors in/out ----
+static inline uint16_t f2bf_host(float f) {
+    uint32_t u; std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float bf2f_host(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; std::memcpy(&f, &u, 4); return f; }
+
+int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, int32_t h, int32_t w, int32_t cin,
+                     const float* wgt, const float* bias, int32_t cout, int32_t k, int32_t stride, int32_t act_flags,
+                     const float* res, float* y)
+{
+    ZL_GUARD_BEGIN
+    using namespace zl;
+    if (!x || !wgt || !bias || !y) { set_error("null argument"); return ZL_INVALID_ARGUMENT; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) { cudaGetLastError(); set_error("no such CUDA device"); return ZL_INSUFFICIENT_RESOURCES; }
+    ZL_CUDA(cudaSetDevice(device));
+    const int act = act_flags & 1, out_f32 = (act_flags >> 1) & 1, hint = (act_flags >> 8) & 0x1ff;
+    const int pad = k / 2, ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+    ConvWeights cw;
+    cw.name = "test"; cw.cin = cin; cw.cout = cout; cw.k = k; cw.stride = stride; cw.act = act;
+    cw.cout_pad = round_up(cout, 16); cw.ktot = k * k * cin;
+    std::vector<float> b(cw.cout_pad, 0.f);
+    std::copy(bias, bias + cout, b.begin());
+    const size_t nx = (size_t)n * h * w * cin, ny = (size_t)n * ho * wo * cout;
+    std::vector<void*> frees;
+    auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; frees.push_back(p); return p; };
+    auto cleanup = [&] { for (void* p : frees) cudaFree(p); };
+    cw.bias = (float*)dalloc(b.size() * 4);
+    if (!cw.bias) { cleanup(); set_error("oom"); return ZL_INSUFFICIENT_RESOURCES; }
+    cudaMemcpy(cw.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
+    int32_t rc = ZL_OK;
+    cudaStream_t st = nullptr;
+    cudaStreamCreate(&st);
+    if (impl == 0) {
+        std::vector<float> ws((size_t)cw.ktot * cw.cout_pad, 0.f);
+        for (int o = 0; o < cout; ++o) for (int t = 0; t < k * k; ++t) for (int c = 0; c < cin; ++c)
+            ws[((size_t)t * cin + c) * cw.cout_pad + o] = wgt[((size_t)o * k * k + t) * cin + c];
+        cw.w_simt = (float*)dalloc(ws.size() * 4);
+        float* dx = (float*)dalloc(nx * 4); float* dy = (float*)dalloc(ny * 4); float* dr = res ? (float*)dalloc(ny * 4) : nullptr;
+        if (!cw.w_simt || !dx || !dy || (res && !dr)) { cleanup(); set_error("oom"); return ZL_INSUFFICIENT_RESOURCES; }
+        cudaMemcpy(cw.w_simt, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dx, x, nx * 4, cudaMemcpyHostToDevice);
+        if (res) cudaMemcpy(dr, res, ny * 4, cudaMemcpyHostToDevice);
+        View vx{dx, n, h, w, cin, cin, DT_F32}, vy{dy, n, ho, wo, cout, cout, DT_F32}, vr{dr, n, ho, wo, cout, cout, DT_F32};
+        rc = launch_conv_simt(st, cw, vx, vy, res ? &vr : nullptr);
+        if (rc == ZL_OK && cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("conv_simt: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; }
+        if (rc == ZL_OK) cudaMemcpy(y, dy, ny * 4, cudaMemcpyDeviceToHost);
+    } else {
+        std::vector<uint16_t> wt((size_t)cw.cout_pad * cw.ktot, 0), hx(nx), hr(res ? ny : 0);
+        for (int o = 0; o < cout; ++o) for (int t = 0; t < cw.ktot; ++t) wt[(size_t)o * cw.ktot + t] = f2bf_host(wgt[(size_t)o * cw.ktot + t]);
+        for (size_t i = 0; i < nx; ++i) hx[i] = f2bf_host(x[i]);
+        for (size_t i = 0; i < hr.size(); ++i) hr[i] = f2bf_host(res[i]);
+        cw.w_tc = (__nv_bfloat16*)dalloc(wt.size() * 2);
+        void* dx = dalloc(nx * 2); void* dy = dalloc(ny * (out_f32 ? 4 : 2)); void* dr = res ? dalloc(ny * 2) : nullptr;
+        if (!cw.w_tc || !dx || !dy || (res && !dr)) { cleanup(); set_error("oom"); return ZL_INSUFFICIENT_RESOURCES; }
+        cudaMemcpy(cw.w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dx, hx.data(), nx * 2, cudaMemcpyHostToDevice);
+        if (res) cudaMemcpy(dr, hr.data(), ny * 2, cudaMemcpyHostToDevice);
+        cudaMemset(dy, 0xff, ny * (out_f32 ? 4 : 2));
+        View vx{dx, n, h, w, cin, cin, DT_BF16}, vy{dy, n, ho, wo, cout, cout, out_f32 ? DT_F32 : DT_BF16}, vr{dr, n, ho, wo, cout, cout, DT_BF16};
+        ConvTcOp op;
+        rc = conv_tc_prepare(cw, vx, vy, res ? &vr : nullptr, impl == 2, hint, &op);
+        if (rc == ZL_OK) rc = conv_tc_launch(st, op);
+        if (rc == ZL_OK && cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("conv_tc: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; }
+        if (rc == ZL_OK) {
+            if (out_f32) cudaMemcpy(y, dy, ny * 4, cudaMemcpyDeviceToHost);
+            else {
+                std::vector<uint16_t> hy(ny);
+                cudaMemcpy(hy.data(), dy, ny * 2, cudaMemcpyDeviceToHost);
+                for (size_t i = 0; i < ny; ++i) y[i] = bf2f_host(hy[i]);
+            }
+        }
+    }
+    cudaStreamDestroy(st);
+    cleanup();
+    return rc;
+    ZL_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,1037 @@
+// engine.cpp — model graph, buffers, CUDA graphs, batching queue (see engine.h).
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace zl {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+const char* get_error() { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ helpers
+static inline uint16_t f2bf(float f) {          // round-to-nearest-even, NaN preserved
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+static int ch(int c, float width, int maxc) { return (int)std::ceil(std::min(c, maxc) * width / 8.0) * 8; }
+static int rep(int n, float depth) { return std::max((int)std::lround(n * depth), 1); }   // ties: none occur for n in {3,6}
+
+Engine::Engine(const zl_config& c) : cfg(c) {}
+
+Engine::~Engine()
+{
+    stop_workers();
+    cudaSetDevice(cfg.device);
+    for (auto& L : lanes) free_lane(*L);
+    for (auto& w : convs) {
+        if (w->w_simt) cudaFree(w->w_simt);
+        if (w->w_tc) cudaFree(w->w_tc);
+        if (w->bias) cudaFree(w->bias);
+    }
+    if (d_class_weights) cudaFree(d_class_weights);
+    if (h_slots) cudaFreeHost(h_slots);
+}
+
+int32_t Engine::build_model_def()
+{
+    static const float depth[3] = {0.33f, 0.33f, 0.67f}, width[3] = {0.25f, 0.50f, 0.75f};
+    static const int maxc[3] = {1024, 1024, 768};
+    if (cfg.scale < 0 || cfg.scale > 2) ZL_FAIL(ZL_INVALID_ARGUMENT, "scale must be n/s/m");
+    md.scale = cfg.scale;
+    md.nc = cfg.num_classes;
+    const int base[5] = {64, 128, 256, 512, 1024};
+    for (int i = 0; i < 5; ++i) md.c[i] = ch(base[i], width[cfg.scale], maxc[cfg.scale]);
+    md.n[0] = rep(3, depth[cfg.scale]); md.n[1] = rep(6, depth[cfg.scale]);
+    md.n[2] = rep(6, depth[cfg.scale]); md.n[3] = rep(3, depth[cfg.scale]);
+    md.nh = rep(3, depth[cfg.scale]);
+    md.cb = std::max(16, std::max(md.c[2] / 4, 64));
+    md.cc = std::max(md.c[2], std::min(md.nc, 100));
+    return ZL_OK;
+}
+
+int32_t Engine::init()
+{
+    if (cfg.model_w <= 0 || cfg.model_h <= 0 || cfg.model_w % 32 || cfg.model_h % 32)
+        ZL_FAIL(ZL_INVALID_ARGUMENT, "model_w/model_h must be positive multiples of 32");
+    if (cfg.num_classes < 1 || cfg.num_classes > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "num_classes out of range");
+    if (cfg.max_batch < 1 || cfg.max_batch > 256) ZL_FAIL(ZL_INVALID_ARGUMENT, "max_batch must be 1..256");
+    if (cfg.precision != ZL_PRECISION_FP32 && cfg.precision != ZL_PRECISION_BF16) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad precision");
+    if (cfg.preprocess_mode != ZL_PRE_STRETCH_NEAREST) ZL_FAIL(ZL_INVALID_ARGUMENT, "only the reference's nearest-stretch preprocessing is implemented");
+    if (cfg.max_frame_w <= 0) cfg.max_frame_w = cfg.model_w;
+    if (cfg.max_frame_h <= 0) cfg.max_frame_h = cfg.model_h;
+    if (cfg.num_lanes < 1) cfg.num_lanes = 1;
+    if (cfg.num_lanes > 4) cfg.num_lanes = 4;
+    if (cfg.queue_depth < 1) cfg.queue_depth = 8;     // constants::INFERENCE_QUEUE_SIZE (src/common/constants.h)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "no CUDA device: this engine has no CPU fallback");
+    if (cfg.device < 0 || cfg.device >= ndev) ZL_FAIL(ZL_INVALID_ARGUMENT, "device ordinal out of range");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    ZL_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major != 10) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this build is sm_100a only");
+    ZL_TRY(build_model_def());
+    num_anchors = 0;
+    for (int s : {8, 16, 32}) num_anchors += (cfg.model_h / s) * (cfg.model_w / s);
+    if (num_anchors > kMaxAnchors) ZL_FAIL(ZL_INVALID_ARGUMENT, "model input too large (anchor count beyond key range)");
+    if (cfg.class_weights) {
+        ZL_CUDA(cudaMalloc(&d_class_weights, sizeof(float) * cfg.num_classes));
+        ZL_CUDA(cudaMemcpy(d_class_weights, cfg.class_weights, sizeof(float) * cfg.num_classes, cudaMemcpyHostToDevice));
+        cfg.class_weights = nullptr;   // caller's pointer is not retained
+    }
+    for (int i = 0; i < cfg.num_lanes; ++i) {
+        lanes.emplace_back(new Lane());
+        lanes.back()->id = i;
+        ZL_TRY(alloc_lane(*lanes.back()));
+    }
+    return ZL_OK;
+}
+
+// ------------------------------------------------------------------ weights
+int32_t Engine::load_weights(const void* blob, size_t len)
+{
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    const uint8_t* p = (const uint8_t*)blob;
+    if (len < 24 || std::memcmp(p, "ZLW1", 4) != 0) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "not a ZLW1 weights container");
+    uint32_t hdr[5];
+    std::memcpy(hdr, p + 4, 20);
+    if (hdr[0] != 1) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "unsupported ZLW version");
+    if ((int)hdr[1] != cfg.scale || (int)hdr[2] != cfg.num_classes)
+        ZL_FAIL(ZL_MODEL_LOAD_FAILED, "weights are for scale " + std::to_string(hdr[1]) + " nc " + std::to_string(hdr[2]) + ", engine configured otherwise");
+    size_t off = 24;
+    host_w.clear();
+    for (uint32_t i = 0; i < hdr[3]; ++i) {
+        if (off + 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated weights container");
+        uint32_t nl; std::memcpy(&nl, p + off, 4); off += 4;
+        if (off + nl > len || nl > 4096) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated weights container");
+        std::string name((const char*)p + off, nl); off += nl + ((4 - nl % 4) % 4);
+        if (off + 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated weights container");
+        uint32_t nd; std::memcpy(&nd, p + off, 4); off += 4;
+        if (nd > 8 || off + 4ull * nd > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "bad tensor rank");
+        HostTensor t; t.dims.resize(nd);
+        size_t cnt = 1;
+        for (uint32_t d = 0; d < nd; ++d) { std::memcpy(&t.dims[d], p + off, 4); off += 4; cnt *= t.dims[d]; }
+        if (off + cnt * 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated tensor " + name);
+        t.data.resize(cnt);
+        std::memcpy(t.data.data(), p + off, cnt * 4); off += cnt * 4;
+        host_w[name] = std::move(t);
+    }
+
+    // the conv list of YOLOv8, names as ultralytics exports them
+    struct Spec { std::string name; int cin, cout, k, s, act; };
+    std::vector<Spec> specs;
+    auto conv = [&](const std::string& n, int ci, int co, int k, int s, int act = 1) { specs.push_back({n, ci, co, k, s, act}); };
+    auto c2f = [&](int idx, int ci, int co, int n) {
+        const int c = co / 2;
+        const std::string b = "model." + std::to_string(idx);
+        conv(b + ".cv1.conv", ci, 2 * c, 1, 1);
+        for (int j = 0; j < n; ++j) {
+            conv(b + ".m." + std::to_string(j) + ".cv1.conv", c, c, 3, 1);
+            conv(b + ".m." + std::to_string(j) + ".cv2.conv", c, c, 3, 1);
+        }
+        conv(b + ".cv2.conv", (2 + n) * c, co, 1, 1);
+    };
+    const int* c = md.c;
+    conv("model.0.conv", 3, c[0], 3, 2);
+    conv("model.1.conv", c[0], c[1], 3, 2);
+    c2f(2, c[1], c[1], md.n[0]);
+    conv("model.3.conv", c[1], c[2], 3, 2);
+    c2f(4, c[2], c[2], md.n[1]);
+    conv("model.5.conv", c[2], c[3], 3, 2);
+    c2f(6, c[3], c[3], md.n[2]);
+    conv("model.7.conv", c[3], c[4], 3, 2);
+    c2f(8, c[4], c[4], md.n[3]);
+    conv("model.9.cv1.conv", c[4], c[4] / 2, 1, 1);
+    conv("model.9.cv2.conv", c[4] * 2, c[4], 1, 1);
+    c2f(12, c[4] + c[3], c[3], md.nh);
+    c2f(15, c[3] + c[2], c[2], md.nh);
+    conv("model.16.conv", c[2], c[2], 3, 2);
+    c2f(18, c[2] + c[3], c[3], md.nh);
+    conv("model.19.conv", c[3], c[3], 3, 2);
+    c2f(21, c[3] + c[4], c[4], md.nh);
+    for (int l = 0; l < 3; ++l) {
+        const std::string b = "model.22.cv2." + std::to_string(l);
+        conv(b + ".0.conv", c[2 + l], md.cb, 3, 1);
+        conv(b + ".1.conv", md.cb, md.cb, 3, 1);
+        conv(b + ".2", md.cb, 64, 1, 1, 0);
+    }
+    for (int l = 0; l < 3; ++l) {
+        const std::string b = "model.22.cv3." + std::to_string(l);
+        conv(b + ".0.conv", c[2 + l], md.cc, 3, 1);
+        conv(b + ".1.conv", md.cc, md.cc, 3, 1);
+        conv(b + ".2", md.cc, md.nc, 1, 1, 0);
+    }
+
+    for (auto& w : convs) {
+        if (w->w_simt) cudaFree(w->w_simt);
+        if (w->w_tc) cudaFree(w->w_tc);
+        if (w->bias) cudaFree(w->bias);
+    }
+    convs.clear();
+    conv_by_name.clear();
+    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    for (const Spec& s : specs) {
+        auto wi = host_w.find(s.name + ".weight"), bi = host_w.find(s.name + ".bias");
+        if (wi == host_w.end() || bi == host_w.end()) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "missing tensor " + s.name);
+        const HostTensor& W = wi->second;
+        if (W.dims.size() != 4 || (int)W.dims[0] != s.cout || (int)W.dims[1] != s.cin || (int)W.dims[2] != s.k || (int)W.dims[3] != s.k ||
+            bi->second.data.size() != (size_t)s.cout)
+            ZL_FAIL(ZL_MODEL_LOAD_FAILED, "shape mismatch for " + s.name);
+        std::unique_ptr<ConvWeights> cw(new ConvWeights());
+        cw->name = s.name; cw->cin = s.cin; cw->cout = s.cout; cw->k = s.k; cw->stride = s.s; cw->act = s.act;
+        cw->cout_pad = round_up(s.cout, 16);
+        cw->ktot = s.k * s.k * s.cin;
+        std::vector<float> bias(cw->cout_pad, 0.f);
+        std::copy(bi->second.data.begin(), bi->second.data.end(), bias.begin());
+        ZL_CUDA(cudaMalloc(&cw->bias, bias.size() * 4));
+        ZL_CUDA(cudaMemcpy(cw->bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+        const bool need_simt = !bf16 || s.cin == 3;
+        if (need_simt) {
+            std::vector<float> ws((size_t)cw->ktot * cw->cout_pad, 0.f);
+            for (int o = 0; o < s.cout; ++o)
+                for (int ci = 0; ci < s.cin; ++ci)
+                    for (int r = 0; r < s.k; ++r)
+                        for (int q = 0; q < s.k; ++q)
+                            ws[((size_t)(r * s.k + q) * s.cin + ci) * cw->cout_pad + o] = W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q];
+            ZL_CUDA(cudaMalloc(&cw->w_simt, ws.size() * 4));
+            ZL_CUDA(cudaMemcpy(cw->w_simt, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
+        }
+        if (bf16 && s.cin != 3) {
+            std::vector<uint16_t> wt((size_t)cw->cout_pad * cw->ktot, 0);
+            for (int o = 0; o < s.cout; ++o)
+                for (int ci = 0; ci < s.cin; ++ci)
+                    for (int r = 0; r < s.k; ++r)
+                        for (int q = 0; q < s.k; ++q)
+                            wt[(size_t)o * cw->ktot + (size_t)(r * s.k + q) * s.cin + ci] = f2bf(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]);
+            ZL_CUDA(cudaMalloc(&cw->w_tc, wt.size() * 2));
+            ZL_CUDA(cudaMemcpy(cw->w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        }
+        conv_by_name[s.name] = cw.get();
+        convs.push_back(std::move(cw));
+    }
+    host_w.clear();
+    // weights changed: every cached op list / graph is stale
+    for (auto& L : lanes) {
+        std::lock_guard<std::mutex> g(L->mu);
+        for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second);
+        L->graphs.clear();
+        L->ops.clear();
+    }
+    weights_loaded = true;
+    return ZL_OK;
+}
+
+// ------------------------------------------------------------------ lane buffers
+int Engine::inline_dets(int B) const { return std::min<int>(B * 64, B * num_anchors); }
+
+int32_t Engine::alloc_lane(Lane& L)
+{
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    ZL_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    ZL_CUDA(cudaEventCreate(&L.ev0));
+    ZL_CUDA(cudaEventCreate(&L.ev1));
+    const int MB = cfg.max_batch, H = cfg.model_h, W = cfg.model_w, nc = md.nc, A = num_anchors;
+    const int adt = cfg.precision == ZL_PRECISION_BF16 ? DT_BF16 : DT_F32;
+    const size_t es = adt == DT_BF16 ? 2 : 4;
+
+    struct Req { std::string name; int h, w, c, dtype; };
+    std::vector<Req> reqs;
+    auto add = [&](const std::string& n, int h, int w, int c, int dt) { reqs.push_back({n, h, w, c, dt}); };
+    const int* c = md.c;
+    add("X0", H, W, 4, adt);
+    add("A0", H / 2, W / 2, c[0], adt);
+    add("A1", H / 4, W / 4, c[1], adt);
+    add("CAT2", H / 4, W / 4, (2 + md.n[0]) * c[1] / 2, adt);  add("T2", H / 4, W / 4, c[1] / 2, adt);  add("A2", H / 4, W / 4, c[1], adt);
+    add("A3", H / 8, W / 8, c[2], adt);
+    add("CAT4", H / 8, W / 8, (2 + md.n[1]) * c[2] / 2, adt);  add("T4", H / 8, W / 8, c[2] / 2, adt);
+    add("CAT14", H / 8, W / 8, c[3] + c[2], adt);              // [ up(h12) | p3 ]
+    add("A5", H / 16, W / 16, c[3], adt);
+    add("CAT6", H / 16, W / 16, (2 + md.n[2]) * c[3] / 2, adt); add("T6", H / 16, W / 16, c[3] / 2, adt);
+    add("CAT11", H / 16, W / 16, c[4] + c[3], adt);            // [ up(p5) | p4 ]
+    add("A7", H / 32, W / 32, c[4], adt);
+    add("CAT8", H / 32, W / 32, (2 + md.n[3]) * c[4] / 2, adt); add("T8", H / 32, W / 32, c[4] / 2, adt);  add("A8", H / 32, W / 32, c[4], adt);
+    add("CAT9", H / 32, W / 32, 2 * c[4], adt);
+    add("CAT20", H / 32, W / 32, c[3] + c[4], adt);            // [ conv19 | p5 ]
+    add("CAT12", H / 16, W / 16, (2 + md.nh) * c[3] / 2, adt); add("T12", H / 16, W / 16, c[3] / 2, adt);
+    add("CAT17", H / 16, W / 16, c[2] + c[3], adt);            // [ conv16 | h12 ]
+    add("CAT15", H / 8, W / 8, (2 + md.nh) * c[2] / 2, adt);   add("T15", H / 8, W / 8, c[2] / 2, adt);   add("O3", H / 8, W / 8, c[2], adt);
+    add("CAT18", H / 16, W / 16, (2 + md.nh) * c[3] / 2, adt); add("T18", H / 16, W / 16, c[3] / 2, adt); add("O4", H / 16, W / 16, c[3], adt);
+    add("CAT21", H / 32, W / 32, (2 + md.nh) * c[4] / 2, adt); add("T21", H / 32, W / 32, c[4] / 2, adt); add("O5", H / 32, W / 32, c[4], adt);
+    const int ncp = round_up(nc, 4);
+    for (int l = 0; l < 3; ++l) {
+        const int hh = H / (8 << l), ww = W / (8 << l);
+        const std::string s = std::to_string(l);
+        add("HB1_" + s, hh, ww, md.cb, adt); add("HB2_" + s, hh, ww, md.cb, adt); add("BOX_" + s, hh, ww, 64, DT_F32);
+        add("HC1_" + s, hh, ww, md.cc, adt); add("HC2_" + s, hh, ww, md.cc, adt); add("CLS_" + s, hh, ww, ncp, DT_F32);
+    }
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t total = 0;
+    for (auto& r : reqs) total += al((size_t)MB * r.h * r.w * r.c * (r.dtype == DT_F32 ? 4 : es));
+    int key_pitch = 1;
+    while (key_pitch < A) key_pitch <<= 1;
+    const uint32_t det_cap = (uint32_t)MB * A;
+    const size_t raw_b = al((size_t)MB * (4 + nc) * A * 4), keys_b = al((size_t)MB * key_pitch * 8), box_b = al((size_t)MB * A * 16),
+                 cnt_b = al((size_t)MB * 4), hdr_b = al((size_t)(4 + 2 * MB) * 4), det_b = al((size_t)det_cap * sizeof(DevDet)),
+                 desc_b = al((size_t)MB * sizeof(FrameDesc)), rdesc_b = al((size_t)4 * MB * sizeof(FrameDesc));
+    total += raw_b + keys_b + 2 * box_b + cnt_b + hdr_b + det_b + desc_b + rdesc_b;
+    ZL_CUDA(cudaMalloc(&L.arena, total));
+    ZL_CUDA(cudaMemset(L.arena, 0, total));
+    L.arena_bytes = total;
+    char* p = L.arena;
+    for (auto& r : reqs) {
+        View v;
+        v.ptr = p; v.n = MB; v.h = r.h; v.w = r.w; v.c = r.c; v.pitch = r.c; v.dtype = r.dtype;
+        L.bufs[r.name] = v;
+        p += al((size_t)MB * r.h * r.w * r.c * (r.dtype == DT_F32 ? 4 : es));
+    }
+    L.bufs["X0"].c = 3;   // three channels live in a pitch-4 pixel
+    L.raw = (float*)p; p += raw_b;
+    L.pb.keys = (uint64_t*)p; p += keys_b;
+    L.pb.key_pitch = key_pitch;
+    L.pb.box_by_anchor = (float4*)p; p += box_b;
+    L.pb.sorted_box = (float4*)p; p += box_b;
+    L.pb.cand_count = (uint32_t*)p; p += cnt_b;
+    L.pb.header = (uint32_t*)p; p += hdr_b;
+    L.pb.dets = (DevDet*)p; p += det_b;
+    L.pb.maxn = MB;
+    L.pb.cap = det_cap;
+    L.d_descs = (FrameDesc*)p; p += desc_b;
+    L.d_res_descs = (FrameDesc*)p; p += rdesc_b;
+
+    int a0 = 0;
+    for (int l = 0; l < 3; ++l) {
+        const std::string s = std::to_string(l);
+        HeadLevel& hl = L.levels[l];
+        hl.box = (const float*)L.bufs["BOX_" + s].ptr;
+        hl.cls = (const float*)L.bufs["CLS_" + s].ptr;
+        hl.h = H / (8 << l); hl.w = W / (8 << l); hl.stride = 8 << l; hl.cls_pitch = ncp; hl.a0 = a0;
+        a0 += hl.h * hl.w;
+    }
+    L.staging_slots = MB;
+    ZL_CUDA(cudaMalloc(&L.staging, L.staging_slots * slot_bytes()));
+    ZL_CUDA(cudaMemset(L.staging, 128, L.staging_slots * slot_bytes()));
+    ZL_CUDA(cudaHostAlloc(&L.h_descs, sizeof(FrameDesc) * MB * 5, cudaHostAllocDefault));
+    L.h_result_bytes = (size_t)(4 + 2 * MB) * 4 + (size_t)det_cap * sizeof(DevDet);
+    ZL_CUDA(cudaHostAlloc(&L.h_result, L.h_result_bytes, cudaHostAllocDefault));
+    ZL_CUDA(cudaHostAlloc(&L.h_frames, (size_t)MB * slot_bytes(), cudaHostAllocDefault));
+    return ZL_OK;
+}
+
+void Engine::free_lane(Lane& L)
+{
+    for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);
+    L.graphs.clear();
+    if (L.arena) cudaFree(L.arena);
+    if (L.staging) cudaFree(L.staging);
+    if (L.h_descs) cudaFreeHost(L.h_descs);
+    if (L.h_result) cudaFreeHost(L.h_result);
+    if (L.h_frames) cudaFreeHost(L.h_frames);
+    if (L.ev0) cudaEventDestroy(L.ev0);
+    if (L.ev1) cudaEventDestroy(L.ev1);
+    if (L.stream) cudaStreamDestroy(L.stream);
+    L.arena = nullptr; L.staging = nullptr; L.h_descs = nullptr; L.h_result = nullptr; L.h_frames = nullptr;
+}
+
+// ------------------------------------------------------------------ op list for batch size B
+int32_t Engine::build_ops(Lane& L, int B)
+{
+    if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
+    std::vector<Op> ops;
+    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    auto buf = [&](const std::string& n) { return L.bufs.at(n).with_n(B); };
+    int32_t rc = ZL_OK;
+
+    auto conv = [&](const std::string& name, const View& x, const View& y, const View* res) {
+        if (rc != ZL_OK) return;
+        auto it = conv_by_name.find(name);
+        if (it == conv_by_name.end()) { set_error("no weights for " + name); rc = ZL_MODEL_LOAD_FAILED; return; }
+        Op op;
+        op.name = name; op.w = it->second; op.x = x; op.y = y;
+        if (res) { op.res = *res; op.has_res = true; }
+        const ConvWeights& w = *it->second;
+        op.flops = 2.0 * (double)y.pixels() * w.cout * w.ktot;
+        op.bytes = (double)x.pixels() * w.cin * x.esize() + (double)y.pixels() * w.cout * y.esize() +
+                   (double)w.cout * w.ktot * (bf16 ? 2 : 4) + (res ? (double)y.pixels() * w.cout * res->esize() : 0.0);
+        if (!bf16) op.kind = Op::CONV_SIMT;
+        else if (w.cin == 3) op.kind = Op::CONV0;
+        else {
+            op.kind = Op::CONV_TC;
+            // small problems (latency path): split Cout over more CTAs so more than a handful of SMs work
+            int hint = 0;
+            const int mtiles = ceil_div((int)y.pixels(), 128);
+            if (mtiles < 64 && w.cout_pad >= 64) hint = w.cout_pad % 32 == 0 ? 32 : 16;
+            rc = conv_tc_prepare(w, x, y, res, true, hint, &op.tc);
+        }
+        ops.push_back(std::move(op));
+    };
+    auto c2f = [&](int idx, const View& x, const std::string& cat_n, const std::string& tmp_n, const View& out, int n, bool shortcut) {
+        const std::string b = "model." + std::to_string(idx);
+        View cat = buf(cat_n), tmp = buf(tmp_n);
+        const int cw = tmp.c;
+        conv(b + ".cv1.conv", x, cat.slice(0, 2 * cw), nullptr);
+        for (int j = 0; j < n; ++j) {
+            View in = cat.slice((j + 1) * cw, cw), o = cat.slice((j + 2) * cw, cw);
+            conv(b + ".m." + std::to_string(j) + ".cv1.conv", in, tmp, nullptr);
+            conv(b + ".m." + std::to_string(j) + ".cv2.conv", tmp, o, shortcut ? &in : nullptr);
+        }
+        conv(b + ".cv2.conv", cat, out, nullptr);
+    };
+    const int* c = md.c;
+
+    { Op op; op.kind = Op::PRE; op.name = "preprocess"; op.y = buf("X0");
+      op.bytes = (double)B * cfg.model_w * cfg.model_h * (3 + 4 * (bf16 ? 2 : 4)); ops.push_back(op); }
+    conv("model.0.conv", buf("X0"), buf("A0"), nullptr);
+    conv("model.1.conv", buf("A0"), buf("A1"), nullptr);
+    c2f(2, buf("A1"), "CAT2", "T2", buf("A2"), md.n[0], true);
+    conv("model.3.conv", buf("A2"), buf("A3"), nullptr);
+    View p3 = buf("CAT14").slice(c[3], c[2]);
+    c2f(4, buf("A3"), "CAT4", "T4", p3, md.n[1], true);
+    conv("model.5.conv", p3, buf("A5"), nullptr);
+    View p4 = buf("CAT11").slice(c[4], c[3]);
+    c2f(6, buf("A5"), "CAT6", "T6", p4, md.n[2], true);
+    conv("model.7.conv", p4, buf("A7"), nullptr);
+    c2f(8, buf("A7"), "CAT8", "T8", buf("A8"), md.n[3], true);
+    {   // SPPF
+        View cat = buf("CAT9");
+        const int h = c[4] / 2;
+        conv("model.9.cv1.conv", buf("A8"), cat.slice(0, h), nullptr);
+        Op op; op.kind = Op::POOL; op.name = "model.9.pool";
+        op.x = cat.slice(0, h); op.p1 = cat.slice(h, h); op.p2 = cat.slice(2 * h, h); op.p3 = cat.slice(3 * h, h);
+        op.bytes = (double)op.x.pixels() * h * op.x.esize() * 4;
+        ops.push_back(op);
+        View p5 = buf("CAT20").slice(c[3], c[4]);
+        conv("model.9.cv2.conv", cat, p5, nullptr);
+        Op up; up.kind = Op::UPSAMPLE; up.name = "model.10.upsample"; up.x = p5; up.y = buf("CAT11").slice(0, c[4]);
+        up.bytes = (double)up.y.pixels() * c[4] * up.y.esize() * 1.25;
+        ops.push_back(up);
+    }
+    View h12 = buf("CAT17").slice(c[2], c[3]);
+    c2f(12, buf("CAT11"), "CAT12", "T12", h12, md.nh, false);
+    { Op up; up.kind = Op::UPSAMPLE; up.name = "model.13.upsample"; up.x = h12; up.y = buf("CAT14").slice(0, c[3]);
+      up.bytes = (double)up.y.pixels() * c[3] * up.y.esize() * 1.25; ops.push_back(up); }
+    c2f(15, buf("CAT14"), "CAT15", "T15", buf("O3"), md.nh, false);
+    conv("model.16.conv", buf("O3"), buf("CAT17").slice(0, c[2]), nullptr);
+    c2f(18, buf("CAT17"), "CAT18", "T18", buf("O4"), md.nh, false);
+    conv("model.19.conv", buf("O4"), buf("CAT20").slice(0, c[3]), nullptr);
+    c2f(21, buf("CAT20"), "CAT21", "T21", buf("O5"), md.nh, false);
+    const char* outs[3] = {"O3", "O4", "O5"};
+    for (int l = 0; l < 3; ++l) {
+        const std::string s = std::to_string(l), b = "model.22.cv2." + s;
+        conv(b + ".0.conv", buf(outs[l]), buf("HB1_" + s), nullptr);
+        conv(b + ".1.conv", buf("HB1_" + s), buf("HB2_" + s), nullptr);
+        conv(b + ".2", buf("HB2_" + s), buf("BOX_" + s), nullptr);
+    }
+    for (int l = 0; l < 3; ++l) {
+        const std::string s = std::to_string(l), b = "model.22.cv3." + s;
+        conv(b + ".0.conv", buf(outs[l]), buf("HC1_" + s), nullptr);
+        conv(b + ".1.conv", buf("HC1_" + s), buf("HC2_" + s), nullptr);
+        View cls = buf("CLS_" + s); cls.c = md.nc;
+        conv(b + ".2", buf("HC2_" + s), cls, nullptr);
+    }
+    if (rc != ZL_OK) return rc;
+    const double rawb = (double)B * (4 + md.nc) * num_anchors * 4;
+    { Op op; op.kind = Op::DECODE; op.name = "dfl_decode"; op.bytes = (double)B * num_anchors * (64 + md.nc) * 4 + rawb; ops.push_back(op); }
+    { Op op; op.kind = Op::FILTER; op.name = "filter"; op.bytes = rawb; ops.push_back(op); }
+    { Op op; op.kind = Op::NMS; op.name = "nms"; op.bytes = 0; ops.push_back(op); }
+    L.ops[B] = std::move(ops);
+    return ZL_OK;
+}
+
+// ------------------------------------------------------------------ execution
+int32_t Engine::run_ops(Lane& L, int B, bool with_d2h)
+{
+    cudaStream_t st = L.stream;
+    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    auto it = L.ops.find(B);
+    if (it == L.ops.end()) { ZL_TRY(build_ops(L, B)); it = L.ops.find(B); }
+    ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st));
+    ZL_CUDA(cudaMemsetAsync(L.pb.header, 0, sizeof(uint32_t) * 4, st));
+    for (const Op& op : it->second) {
+        switch (op.kind) {
+            case Op::PRE:
+                ZL_TRY(launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, op.y.ptr));
+                break;
+            case Op::CONV_TC: ZL_TRY(conv_tc_launch(st, op.tc)); break;
+            case Op::CONV_SIMT: ZL_TRY(launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr)); break;
+            case Op::CONV0: ZL_TRY(launch_conv0_direct(st, *op.w, op.x, op.y)); break;
+            case Op::POOL: ZL_TRY(launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3)); break;
+            case Op::UPSAMPLE: ZL_TRY(launch_upsample2x(st, op.x, op.y)); break;
+            case Op::DECODE: ZL_TRY(launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw)); break;
+            case Op::FILTER:
+                ZL_TRY(launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb));
+                break;
+            case Op::NMS: ZL_TRY(launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb)); break;
+        }
+    }
+    if (with_d2h) {
+        // header (total, cnt[], off[]) and the first inline_dets records in two fixed-size copies
+        const size_t hdr = (size_t)(4 + 2 * L.pb.maxn) * 4;
+        ZL_CUDA(cudaMemcpyAsync(L.h_result, L.pb.header, hdr, cudaMemcpyDeviceToHost, st));
+        ZL_CUDA(cudaMemcpyAsync(L.h_result + hdr, L.pb.dets, (size_t)inline_dets(B) * sizeof(DevDet), cudaMemcpyDeviceToHost, st));
+    }
+    return ZL_OK;
+}
+
+int Engine::graph_batch_for(int n) const
+{
+    int b = 1;
+    while (b < n) b <<= 1;
+    return std::min(b, cfg.max_batch);
+}
+
+int32_t Engine::ensure_graph(Lane& L, int B)
+{
+    if (L.graphs.count(B)) return ZL_OK;
+    // one un-captured pass first: lazy module load, cudaFuncSetAttribute and op building stay out of the capture
+    ZL_TRY(run_ops(L, B, true));
+    ZL_CUDA(cudaStreamSynchronize(L.stream));
+    cudaGraph_t g = nullptr;
+    ZL_CUDA(cudaStreamBeginCapture(L.stream, cudaStreamCaptureModeThreadLocal));
+    int32_t rc = run_ops(L, B, true);
+    cudaError_t ce = cudaStreamEndCapture(L.stream, &g);
+    if (rc != ZL_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+    cudaGraphExec_t ge = nullptr;
+    ce = cudaGraphInstantiate(&ge, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+    L.graphs[B] = ge;
+    { std::lock_guard<std::mutex> g2(smu); graph_captured++; }
+    return ZL_OK;
+}
+
+int32_t Engine::launch_batch(Lane& L, int B)
+{
+    if (cfg.use_graph) {
+        ZL_TRY(ensure_graph(L, B));
+        ZL_CUDA(cudaGraphLaunch(L.graphs[B], L.stream));
+        return ZL_OK;
+    }
+    return run_ops(L, B, true);
+}
+
+// Runs n (<= max_batch) frames on lane L.  Caller holds L.mu.
+int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
+                               bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts)
+{
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    const int B = graph_batch_for(n);
+    const size_t slot = slot_bytes();
+    for (int i = 0; i < n; ++i) {
+        const size_t bytes = (size_t)ws[i] * hs[i] * 3;
+        if (ws[i] <= 0 || hs[i] <= 0 || bytes > slot) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame_w x max_frame_h");
+        const uint8_t* src = frames[i];
+        if (!frames_pinned) {
+            std::memcpy(L.h_frames + (size_t)i * slot, frames[i], bytes);
+            src = L.h_frames + (size_t)i * slot;
+        }
+        ZL_CUDA(cudaMemcpyAsync(L.staging + (size_t)i * slot, src, bytes, cudaMemcpyHostToDevice, L.stream));
+        L.h_descs[i] = FrameDesc{(uint64_t)i * slot, ws[i], hs[i]};
+    }
+    for (int i = n; i < B; ++i) L.h_descs[i] = L.h_descs[0];     // padding frames repeat frame 0; their results are ignored
+    ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.h_descs, sizeof(FrameDesc) * B, cudaMemcpyHostToDevice, L.stream));
+    ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
+    ZL_TRY(launch_batch(L, B));
+    ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
+    ZL_CUDA(cudaStreamSynchronize(L.stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, L.ev0, L.ev1);
+    { std::lock_guard<std::mutex> g(smu); dev_ms_sum += ms; dev_ms_n++; st_batches++; }
+
+    const uint32_t* hdr = (const uint32_t*)L.h_result;
+    const uint32_t total = hdr[0];
+    const uint32_t* cnt = hdr + 4;
+    const uint32_t* off = hdr + 4 + L.pb.maxn;
+    const size_t hdr_b = (size_t)(4 + 2 * L.pb.maxn) * 4;
+    if (total > L.pb.cap) ZL_FAIL(ZL_INFERENCE_ERROR, "detection buffer overflow");
+    if (total > (uint32_t)inline_dets(B)) {       // rare: more survivors than the inline window
+        ZL_CUDA(cudaMemcpyAsync(L.h_result + hdr_b, L.pb.dets, (size_t)total * sizeof(DevDet), cudaMemcpyDeviceToHost, L.stream));
+        ZL_CUDA(cudaStreamSynchronize(L.stream));
+    }
+    const zl_det* all = (const zl_det*)(L.h_result + hdr_b);
+    static_assert(sizeof(zl_det) == sizeof(DevDet), "layout");
+    dets->clear();
+    for (int i = 0; i < n; ++i) {
+        counts[i] = (int32_t)cnt[i];
+        dets->insert(dets->end(), all + off[i], all + off[i] + cnt[i]);
+    }
+    return ZL_OK;
+}
+
+static bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int32_t Engine::infer_batch(const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
+                            zl_det* out, int cap, int32_t* counts, int32_t* offsets, float* raw_out)
+{
+    if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
+    if (n < 0 || (n > 0 && (!frames || !ws || !hs))) ZL_FAIL(ZL_INVALID_ARGUMENT, "null argument");
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    std::vector<zl_det> dets;
+    int total = 0;
+    bool overflow = false;
+    for (int i0 = 0; i0 < n; i0 += cfg.max_batch) {
+        const int nb = std::min(cfg.max_batch, n - i0);
+        bool pinned = true;
+        for (int i = 0; i < nb; ++i) pinned = pinned && is_pinned(frames[i0 + i]);
+        std::vector<int32_t> cnt(nb);
+        ZL_TRY(run_lane_batch(L, frames + i0, ws + i0, hs + i0, nb, pinned, &dets, cnt.data()));
+        if (raw_out) {
+            const size_t per = (size_t)(4 + md.nc) * num_anchors;
+            ZL_CUDA(cudaMemcpy(raw_out + (size_t)i0 * per, L.raw, per * nb * 4, cudaMemcpyDeviceToHost));
+        }
+        size_t k = 0;
+        for (int i = 0; i < nb; ++i) {
+            if (counts) counts[i0 + i] = cnt[i];
+            if (offsets) offsets[i0 + i] = total;
+            for (int j = 0; j < cnt[i]; ++j, ++k) {
+                if (out && total < cap) out[total] = dets[k]; else if (out) overflow = true;
+                total++;
+            }
+        }
+    }
+    { std::lock_guard<std::mutex> g2(smu); st_count += n; }
+    if (overflow) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "dets_out capacity too small");
+    return ZL_OK;
+}
+
+int32_t Engine::preprocess_one(const uint8_t* bgr, int w, int h, size_t len, float* out_chw)
+{
+    if (!bgr || !out_chw) ZL_FAIL(ZL_INVALID_ARGUMENT, "null argument");
+    if (w <= 0 || h <= 0 || len != (size_t)w * h * 3)      // onnx_engine.cpp:659-665
+        ZL_FAIL(ZL_INVALID_INPUT, "Invalid image data size: expected " + std::to_string((size_t)w * h * 3) + ", got " + std::to_string(len));
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    uint8_t* d_img = nullptr; float* d_out = nullptr; FrameDesc* d_desc = nullptr;
+    const size_t ob = (size_t)3 * cfg.model_w * cfg.model_h * 4;
+    ZL_CUDA(cudaMalloc(&d_img, len));
+    ZL_CUDA(cudaMalloc(&d_out, ob));
+    ZL_CUDA(cudaMalloc(&d_desc, sizeof(FrameDesc)));
+    FrameDesc fd{0, w, h};
+    int32_t rc = ZL_OK;
+    cudaMemcpyAsync(d_img, bgr, len, cudaMemcpyHostToDevice, L.stream);
+    cudaMemcpyAsync(d_desc, &fd, sizeof(fd), cudaMemcpyHostToDevice, L.stream);
+    rc = launch_preprocess(L.stream, d_img, d_desc, 1, cfg.model_w, cfg.model_h, PRE_NCHW_F32, d_out);
+    cudaError_t ce = cudaMemcpyAsync(out_chw, d_out, ob, cudaMemcpyDeviceToHost, L.stream);
+    cudaError_t cs = cudaStreamSynchronize(L.stream);
+    cudaFree(d_img); cudaFree(d_out); cudaFree(d_desc);
+    if (rc != ZL_OK) return rc;
+    if (ce != cudaSuccess || cs != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("preprocess: ") + cudaGetErrorString(cs != cudaSuccess ? cs : ce));
+    return ZL_OK;
+}
+
+int32_t Engine::decode_nms(const float* raw, int n, int nc, int A, const int32_t* iw, const int32_t* ih, float conf, float iou,
+                           zl_det* out, int cap, int32_t* counts, int32_t* offsets,
+                           int iters, float* ms_filter, float* ms_nms, int64_t* kept)
+{
+    if (!raw || n <= 0 || nc <= 0 || A <= 0 || !iw || !ih) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    if (A > kMaxAnchors || nc > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "A or nc beyond supported range");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    int key_pitch = 1;
+    while (key_pitch < A) key_pitch <<= 1;
+    const size_t raw_b = (size_t)n * (4 + nc) * A * 4;
+    float* d_raw = nullptr; int32_t* d_wh = nullptr; char* scratch = nullptr;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t keys_b = al((size_t)n * key_pitch * 8), box_b = al((size_t)n * A * 16), cnt_b = al((size_t)n * 4),
+                 hdr_b = al((size_t)(4 + 2 * n) * 4), det_b = al((size_t)n * A * sizeof(DevDet));
+    cudaError_t e1 = cudaMalloc(&d_raw, raw_b), e2 = cudaMalloc(&d_wh, (size_t)n * 8),
+                e3 = cudaMalloc(&scratch, keys_b + 2 * box_b + cnt_b + hdr_b + det_b);
+    auto cleanup = [&] { cudaFree(d_raw); cudaFree(d_wh); cudaFree(scratch); };
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cleanup(); ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "decode_nms: out of device memory"); }
+    PostBuffers pb{};
+    char* p = scratch;
+    pb.keys = (uint64_t*)p; p += keys_b; pb.key_pitch = key_pitch;
+    pb.box_by_anchor = (float4*)p; p += box_b; pb.sorted_box = (float4*)p; p += box_b;
+    pb.cand_count = (uint32_t*)p; p += cnt_b; pb.header = (uint32_t*)p; p += hdr_b; pb.dets = (DevDet*)p;
+    pb.maxn = n; pb.cap = (uint32_t)n * A;
+    std::vector<int32_t> wh(2 * n);
+    for (int i = 0; i < n; ++i) { wh[2 * i] = iw[i]; wh[2 * i + 1] = ih[i]; }
+    cudaStream_t st = L.stream;
+    int32_t rc = ZL_OK;
+    cudaMemcpyAsync(d_raw, raw, raw_b, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_wh, wh.data(), wh.size() * 4, cudaMemcpyHostToDevice, st);
+    cudaEvent_t ev[3];
+    for (auto& e : ev) cudaEventCreate(&e);
+    float tf = 0, tn = 0;
+    const int reps = std::max(1, iters);
+    for (int it = 0; it < reps && rc == ZL_OK; ++it) {
+        cudaMemsetAsync(pb.cand_count, 0, (size_t)n * 4, st);
+        cudaMemsetAsync(pb.header, 0, 16, st);
+        cudaEventRecord(ev[0], st);
+        rc = launch_filter(st, d_raw, n, nc, A, nullptr, d_wh, conf, nullptr, pb);
+        cudaEventRecord(ev[1], st);
+        if (rc == ZL_OK) rc = launch_nms(st, n, A, iou, pb);
+        cudaEventRecord(ev[2], st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("decode_nms: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; break; }
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]);
+        if (it > 0 || reps == 1) { tf += a; tn += b; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc == ZL_OK) {
+        std::vector<uint32_t> hdr(4 + 2 * n);
+        cudaMemcpy(hdr.data(), pb.header, hdr.size() * 4, cudaMemcpyDeviceToHost);
+        const uint32_t total = hdr[0];
+        if (kept) *kept = total;
+        if (ms_filter) *ms_filter = tf / std::max(1, reps - (reps > 1 ? 1 : 0));
+        if (ms_nms) *ms_nms = tn / std::max(1, reps - (reps > 1 ? 1 : 0));
+        if (out) {
+            std::vector<DevDet> all(total);
+            if (total) cudaMemcpy(all.data(), pb.dets, (size_t)total * sizeof(DevDet), cudaMemcpyDeviceToHost);
+            int run = 0;
+            for (int i = 0; i < n; ++i) {
+                const uint32_t c = hdr[4 + i], o = hdr[4 + n + i];
+                if (counts) counts[i] = (int32_t)c;
+                if (offsets) offsets[i] = run;
+                for (uint32_t j = 0; j < c; ++j) {
+                    if (run < cap) std::memcpy(&out[run], &all[o + j], sizeof(zl_det)); else rc = ZL_INSUFFICIENT_RESOURCES;
+                    run++;
+                }
+            }
+            if (rc == ZL_INSUFFICIENT_RESOURCES) set_error("dets_out capacity too small");
+        }
+    }
+    cleanup();
+    return rc;
+}
+
+// ------------------------------------------------------------------ measurement
+int32_t Engine::upload_resident(int set, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n)
+{
+    if (set < 0 || set > 3 || n < 1 || n > cfg.max_batch) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad resident set / count");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    const size_t slot = slot_bytes();
+    if (L.staging_slots < (size_t)cfg.max_batch * 5) {      // grow once: [live | set0 | set1 | set2 | set3]
+        uint8_t* ns = nullptr;
+        ZL_CUDA(cudaMalloc(&ns, (size_t)cfg.max_batch * 5 * slot));
+        ZL_CUDA(cudaMemset(ns, 128, (size_t)cfg.max_batch * 5 * slot));
+        ZL_CUDA(cudaDeviceSynchronize());
+        cudaFree(L.staging);
+        L.staging = ns;
+        L.staging_slots = (size_t)cfg.max_batch * 5;
+        for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);   // graphs captured the old staging pointer
+        L.graphs.clear();
+    }
+    FrameDesc* hd = L.h_descs + (size_t)cfg.max_batch * (1 + set);
+    for (int i = 0; i < n; ++i) {
+        const size_t bytes = (size_t)ws[i] * hs[i] * 3;
+        if (bytes > slot) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame");
+        const size_t off = ((size_t)(1 + set) * cfg.max_batch + i) * slot;
+        ZL_CUDA(cudaMemcpy(L.staging + off, frames[i], bytes, cudaMemcpyHostToDevice));
+        hd[i] = FrameDesc{off, ws[i], hs[i]};
+    }
+    ZL_CUDA(cudaMemcpy(L.d_res_descs + (size_t)set * cfg.max_batch, hd, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice));
+    L.resident_n[set] = n;
+    return ZL_OK;
+}
+
+int32_t Engine::run_resident(int n_sets, int steps, float* total_ms, int64_t* launches, int64_t* total_dets)
+{
+    if (n_sets < 1 || n_sets > 4 || steps < 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad n_sets / steps");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    const int n = L.resident_n[0];
+    for (int s = 0; s < n_sets; ++s) if (L.resident_n[s] != n || n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident sets not uploaded / unequal");
+    const int B = graph_batch_for(n);
+    if (B != n) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident batch must be a power of two or max_batch");
+    if (cfg.use_graph) ZL_TRY(ensure_graph(L, B));
+    int64_t dets = 0;
+    ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
+    for (int s = 0; s < steps; ++s) {
+        ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)(s % n_sets) * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
+        ZL_TRY(launch_batch(L, B));
+    }
+    ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
+    ZL_CUDA(cudaStreamSynchronize(L.stream));
+    float ms = 0;
+    ZL_CUDA(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
+    dets = ((const uint32_t*)L.h_result)[0];
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int64_t)steps * (int64_t)L.ops[B].size();
+    if (total_dets) *total_dets = dets;
+    return ZL_OK;
+}
+
+int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t* n_out)
+{
+    if (set < 0 || set > 3 || iters < 1 || !out || !n_out) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    const int n = L.resident_n[set];
+    if (n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident set not uploaded");
+    const int B = graph_batch_for(n);
+    if (!L.ops.count(B)) ZL_TRY(build_ops(L, B));
+    ZL_TRY(run_ops(L, B, false));                         // warm
+    ZL_CUDA(cudaStreamSynchronize(L.stream));
+    const std::vector<Op>& ops = L.ops[B];
+    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    std::vector<cudaEvent_t> ev(ops.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    std::vector<double> acc(ops.size(), 0.0);
+    cudaStream_t st = L.stream;
+    int32_t rc = ZL_OK;
+    for (int it = 0; it < iters && rc == ZL_OK; ++it) {
+        cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)set * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, st);
+        cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st);
+        cudaMemsetAsync(L.pb.header, 0, 16, st);
+        for (size_t i = 0; i < ops.size() && rc == ZL_OK; ++i) {
+            const Op& op = ops[i];
+            cudaEventRecord(ev[i], st);
+            switch (op.kind) {
+                case Op::PRE: rc = launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, op.y.ptr); break;
+                case Op::CONV_TC: rc = conv_tc_launch(st, op.tc); break;
+                case Op::CONV_SIMT: rc = launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr); break;
+                case Op::CONV0: rc = launch_conv0_direct(st, *op.w, op.x, op.y); break;
+                case Op::POOL: rc = launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3); break;
+                case Op::UPSAMPLE: rc = launch_upsample2x(st, op.x, op.y); break;
+                case Op::DECODE: rc = launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw); break;
+                case Op::FILTER: rc = launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb); break;
+                case Op::NMS: rc = launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb); break;
+            }
+        }
+        cudaEventRecord(ev[ops.size()], st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("profile: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; }
+        for (size_t i = 0; i < ops.size() && rc == ZL_OK; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc != ZL_OK) return rc;
+    int k = 0;
+    for (size_t i = 0; i < ops.size() && k < cap; ++i, ++k) {
+        zl_op_profile& r = out[k];
+        std::memset(&r, 0, sizeof(r));
+        std::strncpy(r.name, ops[i].name.c_str(), sizeof(r.name) - 1);
+        r.kind = ops[i].kind; r.launches = 1; r.ms = (float)(acc[i] / iters);
+        r.flops = ops[i].flops; r.bytes = ops[i].bytes;
+    }
+    *n_out = k;
+    return ZL_OK;
+}
+
+int32_t Engine::bench_preprocess(int w, int h, int n, int iters, float* ms, double* bytes)
+{
+    if (w <= 0 || h <= 0 || n < 1 || iters < 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    const size_t fb = (size_t)w * h * 3, ob = (size_t)cfg.model_w * cfg.model_h * 4 * (bf16 ? 2 : 4);
+    uint8_t* d_in = nullptr; void* d_out = nullptr; FrameDesc* d_desc = nullptr;
+    ZL_CUDA(cudaMalloc(&d_in, fb * n));
+    ZL_CUDA(cudaMalloc(&d_out, ob * n));
+    ZL_CUDA(cudaMalloc(&d_desc, sizeof(FrameDesc) * n));
+    ZL_CUDA(cudaMemset(d_in, 77, fb * n));
+    std::vector<FrameDesc> hd(n);
+    for (int i = 0; i < n; ++i) hd[i] = FrameDesc{(uint64_t)i * fb, w, h};
+    ZL_CUDA(cudaMemcpy(d_desc, hd.data(), sizeof(FrameDesc) * n, cudaMemcpyHostToDevice));
+    int32_t rc = ZL_OK;
+    for (int i = 0; i < 3 && rc == ZL_OK; ++i) rc = launch_preprocess(L.stream, d_in, d_desc, n, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, d_out);
+    cudaEventRecord(L.ev0, L.stream);
+    for (int i = 0; i < iters && rc == ZL_OK; ++i) rc = launch_preprocess(L.stream, d_in, d_desc, n, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, d_out);
+    cudaEventRecord(L.ev1, L.stream);
+    cudaError_t cs = cudaStreamSynchronize(L.stream);
+    float t = 0;
+    cudaEventElapsedTime(&t, L.ev0, L.ev1);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_desc);
+    if (rc != ZL_OK) return rc;
+    if (cs != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("bench_preprocess: ") + cudaGetErrorString(cs));
+    if (ms) *ms = t / iters;
+    // bytes actually sampled (min(src, dst) pixels x 3) + output written (3 channels x element size)
+    const double sampled = (double)std::min((size_t)w * h, (size_t)cfg.model_w * cfg.model_h) * 3;
+    if (bytes) *bytes = n * (sampled + (double)cfg.model_w * cfg.model_h * 3 * (bf16 ? 2 : 4));
+    return ZL_OK;
+}
+
+int32_t Engine::warmup(int iters)
+{
+    if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
+    // warmupModel (onnx_engine.cpp:919-954): all-128 frame of model size, 3 runs by default
+    const size_t fb = (size_t)cfg.model_w * cfg.model_h * 3;
+    if (fb > slot_bytes()) ZL_FAIL(ZL_INVALID_ARGUMENT, "max_frame smaller than the model input");
+    std::vector<uint8_t> grey(fb, 128);
+    for (auto& Lp : lanes) {
+        Lane& L = *Lp;
+        std::lock_guard<std::mutex> g(L.mu);
+        std::vector<zl_det> dets;
+        for (int B : {1, cfg.max_batch}) {
+            std::vector<const uint8_t*> fr(B, grey.data());
+            std::vector<int32_t> ws(B, cfg.model_w), hs(B, cfg.model_h), cnt(B);
+            for (int i = 0; i < std::max(1, iters); ++i)
+                ZL_TRY(run_lane_batch(L, fr.data(), ws.data(), hs.data(), B, false, &dets, cnt.data()));
+            if (cfg.max_batch == 1) break;
+        }
+    }
+    return start_workers();
+}
+
+// ------------------------------------------------------------------ async path
+int32_t Engine::start_workers()
+{
+    if (running.load()) return ZL_OK;
+    if (!h_slots) {
+        ZL_CUDA(cudaSetDevice(cfg.device));
+        ZL_CUDA(cudaHostAlloc(&h_slots, (size_t)cfg.queue_depth * slot_bytes(), cudaHostAllocDefault));
+        free_slots.clear();
+        for (int i = cfg.queue_depth - 1; i >= 0; --i) free_slots.push_back(i);
+    }
+    stopping = false;
+    running.store(true);
+    for (int i = 0; i < (int)lanes.size(); ++i) workers.emplace_back(&Engine::worker_main, this, i);
+    return ZL_OK;
+}
+
+void Engine::stop_workers()
+{
+    if (!running.load()) return;
+    { std::lock_guard<std::mutex> g(qmu); stopping = true; }
+    qcv.notify_all();
+    order_cv.notify_all();
+    for (auto& t : workers) if (t.joinable()) t.join();
+    workers.clear();
+    running.store(false);
+}
+
+int32_t Engine::submit(uint32_t client_id, uint32_t frame_id, uint64_t ts, int w, int h, const uint8_t* bgr, size_t len)
+{
+    if (!running.load()) ZL_FAIL(ZL_NOT_INITIALIZED, "Inference engine not running");          // onnx_engine.cpp:224-226
+    if (!bgr || w <= 0 || h <= 0 || len != (size_t)w * h * 3)                                   // onnx_engine.cpp:659-665
+        ZL_FAIL(ZL_INVALID_INPUT, "Invalid image data size: expected " + std::to_string((size_t)std::max(w, 0) * std::max(h, 0) * 3) + ", got " + std::to_string(len));
+    if (len > slot_bytes()) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame_w x max_frame_h");
+    int slot;
+    {
+        std::lock_guard<std::mutex> g(qmu);
+        if (free_slots.empty()) {
+            std::lock_guard<std::mutex> g2(smu);
+            st_dropped++;
+            ZL_FAIL(ZL_INFERENCE_ERROR, "inference queue full, frame dropped");               // network_server.cpp:213-215
+        }
+        slot = free_slots.back();
+        free_slots.pop_back();
+        in_flight++;
+    }
+    std::memcpy(h_slots + (size_t)slot * slot_bytes(), bgr, len);       // the reference copies the frame too (onnx_engine.cpp:235)
+    Request r{client_id, frame_id, ts, w, h, slot, std::chrono::steady_clock::now()};
+    {
+        std::lock_guard<std::mutex> g(qmu);
+        queue.push_back(r);
+        std::lock_guard<std::mutex> g2(smu);
+        st_hwm = std::max<uint64_t>(st_hwm, queue.size());
+    }
+    qcv.notify_one();
+    return ZL_OK;
+}
+
+void Engine::worker_main(int lane_id)
+{
+    cudaSetDevice(cfg.device);
+    Lane& L = *lanes[lane_id];
+    std::vector<Request> batch;
+    std::vector<const uint8_t*> fr;
+    std::vector<int32_t> ws, hs, cnt;
+    std::vector<zl_det> dets;
+    while (true) {
+        uint64_t seq;
+        batch.clear();
+        {
+            std::unique_lock<std::mutex> lk(qmu);
+            qcv.wait(lk, [&] { return stopping || !queue.empty(); });
+            if (queue.empty() && stopping) return;
+            if (cfg.batch_window_us > 0 && (int)queue.size() < cfg.max_batch)
+                qcv.wait_for(lk, std::chrono::microseconds(cfg.batch_window_us), [&] { return stopping || (int)queue.size() >= cfg.max_batch; });
+            while (!queue.empty() && (int)batch.size() < cfg.max_batch) { batch.push_back(queue.front()); queue.pop_front(); }
+            if (batch.empty()) continue;        // another lane took the frames while this one sat in the batch window
+            seq = next_seq++;
+        }
+        const int n = (int)batch.size();
+        fr.resize(n); ws.resize(n); hs.resize(n); cnt.assign(n, 0);
+        for (int i = 0; i < n; ++i) { fr[i] = h_slots + (size_t)batch[i].slot * slot_bytes(); ws[i] = batch[i].w; hs[i] = batch[i].h; }
+        int32_t rc;
+        std::string err;
+        {
+            std::lock_guard<std::mutex> g(L.mu);
+            rc = run_lane_batch(L, fr.data(), ws.data(), hs.data(), n, true, &dets, cnt.data());
+            if (rc != ZL_OK) err = get_error();
+        }
+        // deliver in pop order across lanes
+        {
+            std::unique_lock<std::mutex> lk(qmu);
+            order_cv.wait(lk, [&] { return deliver_seq == seq; });
+        }
+        const auto now = std::chrono::steady_clock::now();
+        size_t k = 0;
+        for (int i = 0; i < n; ++i) {
+            const int c = rc == ZL_OK ? cnt[i] : 0;
+            if (cb) cb(cb_user, batch[i].client_id, batch[i].frame_id, batch[i].timestamp, rc, c ? dets.data() + k : nullptr, c);
+            k += c;
+        }
+        {
+            std::lock_guard<std::mutex> g(smu);
+            for (int i = 0; i < n; ++i) {
+                lat_ms.push_back(std::chrono::duration<double, std::milli>(now - batch[i].t_submit).count());
+                if (lat_ms.size() > 1000) lat_ms.pop_front();
+            }
+            if (rc == ZL_OK) st_count += n; else st_errors += n;
+        }
+        {
+            std::lock_guard<std::mutex> g(qmu);
+            for (int i = 0; i < n; ++i) free_slots.push_back(batch[i].slot);
+            in_flight -= n;
+            deliver_seq++;
+        }
+        order_cv.notify_all();
+        done_cv.notify_all();
+    }
+}
+
+int32_t Engine::drain()
+{
+    std::unique_lock<std::mutex> lk(qmu);
+    done_cv.wait(lk, [&] { return in_flight == 0 || !running.load(); });
+    return ZL_OK;
+}
+
+size_t Engine::queue_size() const
+{
+    std::lock_guard<std::mutex> g(qmu);
+    return queue.size();
+}
+
+void Engine::get_stats(zl_stats* o) const
+{
+    std::memset(o, 0, sizeof(*o));
+    { std::lock_guard<std::mutex> g(qmu); o->queue_size = queue.size(); }
+    std::lock_guard<std::mutex> g(smu);
+    o->inference_count = st_count; o->inference_errors = st_errors; o->dropped_frames = st_dropped;
+    o->queue_high_water_mark = st_hwm; o->batches = st_batches;
+    if (!lat_ms.empty()) {
+        std::vector<double> v(lat_ms.begin(), lat_ms.end());
+        double s = 0; for (double x : v) s += x;
+        o->avg_inference_time_ms = s / v.size();
+        std::sort(v.begin(), v.end());
+        o->p99_inference_time_ms = v[std::min(v.size() - 1, (size_t)(v.size() * 0.99))];
+    }
+    o->avg_device_time_ms = dev_ms_n ? dev_ms_sum / dev_ms_n : 0.0;
+    o->graph_captured = graph_captured; o->device = cfg.device; o->precision = cfg.precision; o->running = running.load() ? 1 : 0;
+}
+
+}  // namespace zl

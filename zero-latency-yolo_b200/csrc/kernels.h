@@ -1,0 +1,97 @@
+// kernels.h — launchers of the sm_100a kernels (one translation unit per family).
+#pragma once
+#include <vector>
+
+#include "common.h"
+
+namespace zl {
+
+// ---------------------------------------------------------------- weights
+// One convolution's parameters, resident on one device.  BN is already folded
+// (SURVEY.md Appendix A), so a conv is y = act(W*x + b) (+ residual).
+struct ConvWeights {
+    std::string name;
+    int32_t cin = 0, cout = 0, k = 1, stride = 1, act = 1;
+    int32_t cout_pad = 0;          // multiple of 16 (tcgen05 N granularity)
+    int32_t ktot = 0;              // k*k*cin
+    float* w_simt = nullptr;       // fp32 [ktot][cout_pad]  (k index = (r*k+s)*cin + c)
+    __nv_bfloat16* w_tc = nullptr; // bf16 [cout_pad][ktot]  K-major rows for UMMA B
+    float* bias = nullptr;         // fp32 [cout_pad]
+};
+
+// ---------------------------------------------------------------- P1
+enum PreLayout : int32_t {
+    PRE_NCHW_F32 = 0,    // [n,3,mh,mw] fp32 planar: the tensor the reference feeds ORT (onnx_engine.cpp:560)
+    PRE_NHWC4_F32 = 1,   // [n,mh,mw,4] fp32 (R,G,B,0): input of the fp32 conv path
+    PRE_NHWC4_BF16 = 2   // [n,mh,mw,4] bf16 (R,G,B,0): input of the bf16 conv path
+};
+int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
+                          int32_t mw, int32_t mh, int32_t layout, void* out);
+
+// ---------------------------------------------------------------- convs
+// fp32 CUDA-core implicit GEMM (exact mode) — any cin/cout, k in {1,3}, stride in {1,2}.
+int32_t launch_conv_simt(cudaStream_t st, const ConvWeights& w, const View& x, const View& y, const View* res);
+// bf16 first layer (cin=3 padded to 4): direct conv on CUDA cores, bf16 NHWC out.
+int32_t launch_conv0_direct(cudaStream_t st, const ConvWeights& w, const View& x, const View& y);
+
+// tcgen05 implicit GEMM.  A operand staged either by TMA (1x1 convs: plain 2-D
+// tiled map over [pixels][cin]) or by producer warps gathering NHWC rows into
+// the swizzled UMMA layout (3x3, any stride); B (weights) always by TMA.
+struct ConvTcOp {
+    CUtensorMap tmap_w;
+    CUtensorMap tmap_a;
+    const __nv_bfloat16* x;
+    void* y;
+    const __nv_bfloat16* res;
+    const float* bias;
+    int32_t N, H, W, Cin, xpitch;
+    int32_t Ho, Wo, Cout, ypitch, rpitch, y_f32;
+    int32_t k, stride, pad, act;
+    int32_t kc, swz, nkb, cchunks;     // channels per K-block, swizzle bytes, #K-blocks, chunks per tap
+    int32_t ntile, ngrid;              // N tile (<=256, multiple of 16) and number of N tiles
+    int32_t m_total, a_tma;
+    int32_t stages, smem_bytes, tmem_cols;
+    double flops, bytes;
+};
+int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, const View* res,
+                        bool allow_tma_a, int32_t ntile_hint, ConvTcOp* op);
+int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& op);
+
+// ---------------------------------------------------------------- pool / upsample
+// SPPF: p1 = max5(a), p2 = max5(p1) = max9(a), p3 = max13(a) in one pass.
+int32_t launch_sppf_pool(cudaStream_t st, const View& a, const View& p1, const View& p2, const View& p3);
+int32_t launch_upsample2x(cudaStream_t st, const View& x, const View& y);
+
+// ---------------------------------------------------------------- D1 / F1 / N1
+struct HeadLevel {
+    const float* box;   // [n,h,w,64] fp32
+    const float* cls;   // [n,h,w,cls_pitch] fp32 (nc valid)
+    int32_t h, w, stride, cls_pitch, a0;   // a0 = first anchor index of the level
+};
+// Detect tail -> raw head output [n, 4+nc, A] fp32 (the reference's output0).
+int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw);
+
+struct PostBuffers {
+    uint64_t* keys;        // [n][key_pitch] candidate sort keys (key_pitch = pow2 >= A)
+    int32_t key_pitch;
+    float4* box_by_anchor; // [n][A]
+    float4* sorted_box;    // [n][A] scratch
+    uint32_t* cand_count;  // [n]
+    uint32_t* header;      // [4 + 2*maxn]: total, pad[3], cnt[maxn], off[maxn]
+    DevDet* dets;          // [cap]
+    int32_t maxn;
+    uint32_t cap;
+};
+// postProcess decode part (onnx_engine.cpp:773-819): argmax / threshold / normalise, ballot compaction.
+int32_t launch_filter(cudaStream_t st, const float* raw, int32_t n, int32_t nc, int32_t A,
+                      const FrameDesc* descs, const int32_t* img_wh, float conf_thr,
+                      const float* class_weights, const PostBuffers& pb);
+// applyNMS (onnx_engine.cpp:837-878): per-frame key sort + per-class greedy bitmask suppression.
+int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb);
+int32_t nms_configure();   // one-time cudaFuncSetAttribute calls
+
+// ---------------------------------------------------------------- TMA helper
+int32_t make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                          uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes);
+
+}  // namespace zl

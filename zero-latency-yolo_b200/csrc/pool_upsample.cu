@@ -1,0 +1,142 @@
+// pool_upsample.cu — SPPF max-pools and nearest 2x upsample (NHWC, channel-sliced views).
+//
+// Part of the graph the reference runs inside Ort::Session::Run
+// (src/inference/onnx_engine.cpp:577-585; SURVEY.md Appendix A: SPPF = three
+// chained 5x5/s1/p2 max-pools == 5x5, 9x9, 13x13 windows of the same input
+// with -inf padding; Upsample = nearest, scale 2).  Both are pure HBM traffic:
+// 16-byte vector loads/stores, results written straight into the concat buffer.
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace zl {
+namespace {
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    using V = float4;
+    __device__ static void load(const float* p, float (&f)[4]) { float4 v = __ldg(reinterpret_cast<const float4*>(p)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+    __device__ static void store(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    __device__ static void load(const __nv_bfloat16* p, float (&f)[8]) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+            f[2 * i] = __bfloat162float(h.x);
+            f[2 * i + 1] = __bfloat162float(h.y);
+        }
+    }
+    __device__ static void store(__nv_bfloat16* p, const float (&f)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+// One thread: one pixel x one channel vector; windows 5/9/13 share the scan.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sppf_pool_kernel(const T* __restrict__ a, T* __restrict__ p1, T* __restrict__ p2, T* __restrict__ p3,
+                 int N, int H, int W, int C, int apitch, int p1pitch, int p2pitch, int p3pitch)
+{
+    constexpr int VN = Vec<T>::N;
+    const int cv = C / VN;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * H * W * cv) return;
+    const int c = (int)(idx % cv) * VN;
+    const long long pix = idx / cv;
+    const int x = (int)(pix % W);
+    const int y = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float m5[VN], m9[VN], m13[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) m5[i] = m9[i] = m13[i] = -FLT_MAX;
+    for (int dy = -6; dy <= 6; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -6; dx <= 6; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W) continue;
+            float v[VN];
+            Vec<T>::load(a + ((size_t)(n * H + yy) * W + xx) * apitch + c, v);
+            const bool in9 = (dy >= -4 && dy <= 4 && dx >= -4 && dx <= 4);
+            const bool in5 = (dy >= -2 && dy <= 2 && dx >= -2 && dx <= 2);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) {
+                m13[i] = fmaxf(m13[i], v[i]);
+                if (in9) m9[i] = fmaxf(m9[i], v[i]);
+                if (in5) m5[i] = fmaxf(m5[i], v[i]);
+            }
+        }
+    }
+    const size_t o = (size_t)pix;
+    Vec<T>::store(p1 + o * p1pitch + c, m5);
+    Vec<T>::store(p2 + o * p2pitch + c, m9);
+    Vec<T>::store(p3 + o * p3pitch + c, m13);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xpitch, int ypitch)
+{
+    constexpr int VN = Vec<T>::N;
+    const int cv = C / VN;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * Ho * Wo * cv) return;
+    const int c = (int)(idx % cv) * VN;
+    const long long pix = idx / cv;
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    float v[VN];
+    Vec<T>::load(x + ((size_t)(n * H + (oy >> 1)) * W + (ox >> 1)) * xpitch + c, v);
+    Vec<T>::store(y + (size_t)pix * ypitch + c, v);
+}
+
+bool aligned16(const View& v) { return (reinterpret_cast<uintptr_t>(v.ptr) & 15) == 0 && (v.pitch * v.esize()) % 16 == 0; }
+
+}  // namespace
+
+int32_t launch_sppf_pool(cudaStream_t st, const View& a, const View& p1, const View& p2, const View& p3)
+{
+    const int vn = a.dtype == DT_F32 ? 4 : 8;
+    if (a.c % vn || !aligned16(a) || !aligned16(p1) || !aligned16(p2) || !aligned16(p3))
+        ZL_FAIL(ZL_INVALID_ARGUMENT, "sppf_pool: views must be 16-B aligned");
+    const long long total = (long long)a.pixels() * (a.c / vn);
+    const int grid = (int)((total + 255) / 256);
+    if (a.dtype == DT_F32)
+        sppf_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)a.ptr, (float*)p1.ptr, (float*)p2.ptr, (float*)p3.ptr,
+                                                      a.n, a.h, a.w, a.c, a.pitch, p1.pitch, p2.pitch, p3.pitch);
+    else
+        sppf_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a.ptr, (__nv_bfloat16*)p1.ptr, (__nv_bfloat16*)p2.ptr,
+                                                              (__nv_bfloat16*)p3.ptr, a.n, a.h, a.w, a.c, a.pitch, p1.pitch, p2.pitch, p3.pitch);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+int32_t launch_upsample2x(cudaStream_t st, const View& x, const View& y)
+{
+    const int vn = x.dtype == DT_F32 ? 4 : 8;
+    if (x.c % vn || y.h != 2 * x.h || y.w != 2 * x.w || y.c != x.c || !aligned16(x) || !aligned16(y))
+        ZL_FAIL(ZL_INVALID_ARGUMENT, "upsample2x: view mismatch");
+    const long long total = (long long)y.pixels() * (x.c / vn);
+    const int grid = (int)((total + 255) / 256);
+    if (x.dtype == DT_F32)
+        upsample2x_kernel<float><<<grid, 256, 0, st>>>((const float*)x.ptr, (float*)y.ptr, x.n, x.h, x.w, x.c, x.pitch, y.pitch);
+    else
+        upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x.ptr, (__nv_bfloat16*)y.ptr, x.n, x.h, x.w, x.c, x.pitch, y.pitch);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+}  // namespace zl

@@ -1,0 +1,347 @@
+// postprocess.cu — D1 (Detect tail), F1 (decode/threshold), N1 (class-aware NMS).
+//
+// D1 is the tail of the ONNX graph (DFL softmax expectation, dist2bbox, x stride,
+// sigmoid) and produces the reference's `output0`
+// [n, 4+nc, A] (src/inference/onnx_engine.cpp:50,767-774).
+// F1 restates the decode loop of postProcess (onnx_engine.cpp:773-819):
+//   per-anchor argmax with strict '>' from 0.0f, keep on '>= threshold',
+//   box / REQUEST-frame width,height.
+// N1 restates applyNMS + calculateIoU (onnx_engine.cpp:837-909): sort by
+//   (class asc, confidence desc) — completed to a total order with the anchor
+//   index ascending, because the reference's std::sort is unstable — then a
+//   greedy per-class sweep that suppresses on IoU > threshold.
+// All fp32 arithmetic that decides an outcome uses the *_rn intrinsics so no
+// FMA contraction can make a comparison differ from the IEEE CPU oracle.
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace zl {
+namespace {
+
+// ============================================================= D1: DFL decode
+constexpr int kDflAnchors = 32;    // anchors per CTA
+constexpr int kDflThreads = 256;   // 8 warps, 4 anchors each
+
+__global__ void __launch_bounds__(kDflThreads)
+dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, int nc, int A, float* __restrict__ raw)
+{
+    extern __shared__ float stage[];                 // [(4+nc)][33]
+    const int f = blockIdx.y;
+    const int a0 = blockIdx.x * kDflAnchors;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rows = 4 + nc;
+
+    for (int i = 0; i < kDflAnchors / 8; ++i) {
+        const int la = warp * (kDflAnchors / 8) + i;
+        const int a = a0 + la;
+        if (a >= A) break;                           // warp-uniform
+        const HeadLevel& lv = (a >= l2.a0) ? l2 : (a >= l1.a0 ? l1 : l0);
+        const int idx = a - lv.a0;
+        const int y = idx / lv.w, x = idx - y * lv.w;
+        const size_t pix = (size_t)(f * lv.h + y) * lv.w + x;
+        // ---- box: 4 sides x 16 bins; lane owns bins (lane&15) of sides (lane>>4) and 2+(lane>>4)
+        const float* bp = lv.box + pix * 64;
+        const float va = __ldg(bp + lane), vb = __ldg(bp + 32 + lane);
+        float ma = va, mb = vb;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+        }
+        const float ea = expf(va - ma), eb = expf(vb - mb);
+        const float bin = (float)(lane & 15);
+        float sa = ea, sb = eb, wa = ea * bin, wb = eb * bin;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            wa += __shfl_xor_sync(0xffffffffu, wa, o);
+            wb += __shfl_xor_sync(0xffffffffu, wb, o);
+        }
+        const float da = wa / sa, db = wb / sb;       // lanes 0-15: left,right ; lanes 16-31: top,bottom
+        const float dl = __shfl_sync(0xffffffffu, da, 0), dt = __shfl_sync(0xffffffffu, da, 16);
+        const float dr = __shfl_sync(0xffffffffu, db, 0), dbm = __shfl_sync(0xffffffffu, db, 16);
+        if (lane == 0) {
+            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, s = (float)lv.stride;
+            const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + dbm;
+            stage[0 * 33 + la] = (x1 + x2) * 0.5f * s;
+            stage[1 * 33 + la] = (y1 + y2) * 0.5f * s;
+            stage[2 * 33 + la] = (x2 - x1) * s;
+            stage[3 * 33 + la] = (y2 - y1) * s;
+        }
+        // ---- classes: sigmoid, transposed through smem
+        const float* cp = lv.cls + pix * lv.cls_pitch;
+        for (int c = lane; c < nc; c += 32) {
+            const float z = __ldg(cp + c);
+            stage[(4 + c) * 33 + la] = 1.0f / (1.0f + expf(-z));
+        }
+    }
+    __syncthreads();
+    float* out = raw + (size_t)f * rows * A;
+    for (int i = threadIdx.x; i < rows * kDflAnchors; i += kDflThreads) {
+        const int r = i / kDflAnchors, la = i - r * kDflAnchors;
+        if (a0 + la < A) out[(size_t)r * A + a0 + la] = stage[r * 33 + la];
+    }
+}
+
+// ============================================================= F1: filter
+// key = class[12] | (~confidence bits)[32] | anchor[20]: ascending key order ==
+// (class asc, confidence desc, anchor asc).  Confidence is > 0 here, so its
+// IEEE bit pattern is monotone.
+__device__ __forceinline__ uint64_t make_key(int cls, float conf, int anchor) {
+    return ((uint64_t)(uint32_t)cls << 52) | ((uint64_t)(~__float_as_uint(conf)) << kKeyAnchorBits) | (uint64_t)(uint32_t)anchor;
+}
+__device__ __forceinline__ int key_class(uint64_t k) { return (int)(k >> 52); }
+__device__ __forceinline__ float key_conf(uint64_t k) { return __uint_as_float(~(uint32_t)(k >> kKeyAnchorBits)); }
+__device__ __forceinline__ int key_anchor(uint64_t k) { return (int)(k & ((1u << kKeyAnchorBits) - 1)); }
+
+__global__ void __launch_bounds__(256)
+filter_kernel(const float* __restrict__ raw, int nc, int A, const FrameDesc* __restrict__ descs,
+              const int32_t* __restrict__ img_wh, float conf_thr, const float* __restrict__ class_weights,
+              uint64_t* __restrict__ keys, int key_pitch, float4* __restrict__ box_by_anchor, uint32_t* __restrict__ cand_count)
+{
+    const int f = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* r = raw + (size_t)f * (4 + nc) * A;
+    bool keep = false;
+    float max_conf = 0.0f;
+    int max_id = -1;
+    if (a < A) {
+        for (int j = 0; j < nc; ++j) {
+            float s = __ldg(r + (size_t)(4 + j) * A + a);
+            if (class_weights) s = __fmul_rn(s, __ldg(class_weights + j));
+            if (s > max_conf) { max_conf = s; max_id = j; }
+        }
+        keep = (max_conf >= conf_thr) && (max_id >= 0);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    if (ballot == 0u) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cand_count + f, (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+        int iw, ih;
+        if (img_wh) { iw = img_wh[2 * f]; ih = img_wh[2 * f + 1]; } else { iw = descs[f].w; ih = descs[f].h; }
+        const float fw = (float)iw, fh = (float)ih;
+        const float cx = __ldg(r + a), cy = __ldg(r + (size_t)A + a), w = __ldg(r + 2 * (size_t)A + a), h = __ldg(r + 3 * (size_t)A + a);
+        const uint32_t slot = base + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+        keys[(size_t)f * key_pitch + slot] = make_key(max_id, max_conf, a);
+        box_by_anchor[(size_t)f * A + a] = make_float4(__fdiv_rn(cx, fw), __fdiv_rn(cy, fh), __fdiv_rn(w, fw), __fdiv_rn(h, fh));
+    }
+}
+
+// ============================================================= N1: NMS
+constexpr int kNmsThreads = 1024;
+
+// calculateIoU (onnx_engine.cpp:881-909) with IEEE single ops in the reference's order.
+__device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
+    const float ahw = __fmul_rn(a.z, 0.5f), ahh = __fmul_rn(a.w, 0.5f);
+    const float bhw = __fmul_rn(b.z, 0.5f), bhh = __fmul_rn(b.w, 0.5f);
+    const float x1_min = __fsub_rn(a.x, ahw), y1_min = __fsub_rn(a.y, ahh);
+    const float x1_max = __fadd_rn(a.x, ahw), y1_max = __fadd_rn(a.y, ahh);
+    const float x2_min = __fsub_rn(b.x, bhw), y2_min = __fsub_rn(b.y, bhh);
+    const float x2_max = __fadd_rn(b.x, bhw), y2_max = __fadd_rn(b.y, bhh);
+    const float xo = fmaxf(0.0f, __fsub_rn(fminf(x1_max, x2_max), fmaxf(x1_min, x2_min)));
+    const float yo = fmaxf(0.0f, __fsub_rn(fminf(y1_max, y2_max), fmaxf(y1_min, y2_min)));
+    const float inter = __fmul_rn(xo, yo);
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    return uni > 0.0f ? __fdiv_rn(inter, uni) : 0.0f;
+}
+
+// One CTA per frame.  Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | scan scratch.
+__global__ void __launch_bounds__(kNmsThreads)
+nms_kernel(int A, float iou_thr, int key_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
+           float4* __restrict__ sorted_box, const uint32_t* __restrict__ cand_count, uint32_t* __restrict__ header,
+           DevDet* __restrict__ dets, int maxn, uint32_t cap)
+{
+    extern __shared__ __align__(16) uint8_t nms_smem[];
+    __shared__ uint32_t s_warp_tot[32];
+    __shared__ uint32_t s_base;
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = (int)min(cand_count[f], (uint32_t)A);
+    uint32_t* h_total = header;
+    uint32_t* h_cnt = header + 4;
+    uint32_t* h_off = header + 4 + maxn;
+    if (n == 0) {
+        if (tid == 0) { h_cnt[f] = 0; h_off[f] = 0; }
+        return;
+    }
+    int P = 1;
+    while (P < n) P <<= 1;
+    uint64_t* gkeys = keys_g + (size_t)f * key_pitch;
+    // keys live in smem when they fit, else they are sorted in place in global memory
+    // (each frame's slice holds key_pitch = pow2 >= A slots, so the +inf padding is real)
+    const bool in_smem = P <= key_cap_smem;
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(nms_smem);
+    volatile uint32_t* removed = reinterpret_cast<volatile uint32_t*>(nms_smem + (size_t)key_cap_smem * 8);
+    const int nwords = (n + 31) >> 5;
+
+    if (in_smem) {
+        for (int i = tid; i < P; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
+    } else {
+        for (int i = n + tid; i < P; i += kNmsThreads) gkeys[i] = ~0ull;
+    }
+    for (int i = tid; i < nwords; i += kNmsThreads) removed[i] = 0u;
+    __syncthreads();
+
+    // ---- bitonic sort, ascending
+    if (n > 1) {
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < P; i += kNmsThreads) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        uint64_t a, b;
+                        uint64_t* kk = in_smem ? skeys : gkeys;
+                        a = kk[i]; b = kk[ixj];
+                        const bool up = (i & k) == 0;
+                        if ((a > b) == up) { kk[i] = b; kk[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    const uint64_t* K = in_smem ? skeys : gkeys;
+
+    // ---- gather boxes into sorted order
+    float4* sb = sorted_box + (size_t)f * A;
+    for (int i = tid; i < n; i += kNmsThreads) sb[i] = box_by_anchor[(size_t)f * A + key_anchor(K[i])];
+    __syncthreads();
+
+    // ---- greedy sweep, one warp per class segment (segments found by their head element)
+    if (n > 1) {
+        for (int head = warp; head < n; head += kNmsThreads / 32) {
+            // every warp scans candidate heads strided by warp id; a head is an index whose class differs from its predecessor
+            // (cheap test, the heavy work only starts on real heads)
+            bool is_head = head == 0 || key_class(K[head]) != key_class(K[head - 1]);
+            if (!is_head) continue;
+            const int cls = key_class(K[head]);
+            // segment end = first index with a larger class (binary search on the sorted keys)
+            int lo = head + 1, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (key_class(K[mid]) > cls) hi = mid; else lo = mid + 1;
+            }
+            const int end = lo;
+            for (int i = head; i < end - 1; ++i) {
+                const uint32_t wi = removed[i >> 5];
+                if ((wi >> (i & 31)) & 1u) continue;        // is_removed[i]  (onnx_engine.cpp:857)
+                const float4 bi = sb[i];
+                for (int j0 = (i + 1) & ~31; j0 < end; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool sup = false;
+                    if (j > i && j < end) {
+                        const bool gone = (removed[j >> 5] >> (j & 31)) & 1u;
+                        if (!gone) sup = iou_ref(bi, sb[j]) > iou_thr;     // strict '>' (onnx_engine.cpp:871)
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                    if (bal != 0u && lane == 0) atomicOr(const_cast<uint32_t*>(&removed[j0 >> 5]), bal);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- ordered compaction of survivors
+    uint32_t kept_total = 0;
+    for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
+        const int i = i0 + tid;
+        const bool keep = i < n && !((removed[i >> 5] >> (i & 31)) & 1u);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+        for (int w = 0; w < kNmsThreads / 32; ++w) { const uint32_t c = s_warp_tot[w]; if (w < warp) woff += c; tot += c; }
+        kept_total += tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        s_base = atomicAdd(h_total, kept_total);
+        h_cnt[f] = kept_total;
+        h_off[f] = s_base;
+    }
+    __syncthreads();
+    const uint32_t base = s_base;
+    uint32_t running = 0;
+    for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
+        const int i = i0 + tid;
+        const bool keep = i < n && !((removed[i >> 5] >> (i & 31)) & 1u);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+        for (int w = 0; w < kNmsThreads / 32; ++w) { const uint32_t c = s_warp_tot[w]; if (w < warp) woff += c; tot += c; }
+        if (keep) {
+            const uint32_t slot = base + running + woff + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            if (slot < cap) {
+                const uint64_t k = K[i];
+                const float4 b = sb[i];
+                DevDet d;
+                d.x = b.x; d.y = b.y; d.w = b.z; d.h = b.w; d.conf = key_conf(k); d.cls = key_class(k);
+                dets[slot] = d;
+            }
+        }
+        running += tot;
+        __syncthreads();
+    }
+}
+
+int g_nms_smem_keys = 0;   // key capacity (elements) of the smem sort buffer
+
+}  // namespace
+
+int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw)
+{
+    dim3 grid(ceil_div(A, kDflAnchors), n);
+    const size_t smem = (size_t)(4 + nc) * 33 * sizeof(float);
+    if (smem > 48 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "dfl_decode: nc too large");
+    dfl_decode_kernel<<<grid, kDflThreads, smem, st>>>(lv[0], lv[1], lv[2], nc, A, raw);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+int32_t launch_filter(cudaStream_t st, const float* raw, int32_t n, int32_t nc, int32_t A,
+                      const FrameDesc* descs, const int32_t* img_wh, float conf_thr,
+                      const float* class_weights, const PostBuffers& pb)
+{
+    if (A > kMaxAnchors || nc > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "filter: A or nc beyond key range");
+    dim3 grid(ceil_div(A, 256), n);
+    filter_kernel<<<grid, 256, 0, st>>>(raw, nc, A, descs, img_wh, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+int32_t nms_configure()
+{
+    // 16384 keys (128 KB) + removed bitmask for up to 2^20 candidates would not fit; the
+    // bitmask is sized for kMaxAnchors only when keys spill to global.  Budget: 200 KB.
+    ZL_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    g_nms_smem_keys = 16384;
+    return ZL_OK;
+}
+
+int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb)
+{
+    // smem plan: keys (only as many as can ever be needed) + removed bitmask (A bits)
+    int key_cap = 1;
+    while (key_cap < A) key_cap <<= 1;
+    if (key_cap > 16384) key_cap = 0;              // too many to sort in smem -> sort in global memory
+    const size_t mask_bytes = (size_t)ceil_div(A, 32) * 4;
+    const size_t smem = (size_t)key_cap * 8 + mask_bytes;
+    if (smem > 200 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "nms: anchor count too large for the suppression bitmask");
+    static thread_local int last_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != last_dev) { ZL_TRY(nms_configure()); last_dev = dev; }
+    nms_kernel<<<n, kNmsThreads, smem, st>>>(A, iou_thr, key_cap, pb.key_pitch, pb.keys, pb.box_by_anchor, pb.sorted_box, pb.cand_count,
+                                            pb.header, pb.dets, pb.maxn, pb.cap);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+}  // namespace zl

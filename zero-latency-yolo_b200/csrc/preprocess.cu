@@ -1,0 +1,102 @@
+// preprocess.cu — P1: fused resize + BGR->RGB + /255 + layout change, one pass.
+//
+// Replaces OnnxInferenceEngine::preProcess (reference:
+// src/inference/onnx_engine.cpp:649-700; identical body at :703-755).  Parity
+// mode reproduces the reference exactly: nearest-neighbour STRETCH with
+//   scale = float(src)/dst (fp32 divide), src_idx = min(int(i*scale), src-1)
+// (fp32 multiply, truncation), channel read at 2-c, value/255.0f (fp32 divide,
+// round-to-nearest).  No FMA contraction is possible in these expressions but
+// the intrinsics pin the rounding anyway.
+//
+// HBM-bound: each thread produces 4 consecutive output pixels of one row and
+// issues one 16/32-byte store (NHWC4) or three 16-byte stores (NCHW planes).
+#include "kernels.h"
+
+namespace zl {
+namespace {
+
+__device__ __forceinline__ int src_index(int i, float scale, int src_dim) {
+    int s = __float2int_rz(__fmul_rn((float)i, scale));
+    return min(s, src_dim - 1);
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs,
+                  int mw, int mh, void* __restrict__ out)
+{
+    const int f = blockIdx.y;
+    const int wq = (mw + 3) >> 2;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= wq * mh) return;
+    const int y = item / wq;
+    const int x0 = (item - y * wq) * 4;
+    const FrameDesc d = descs[f];
+    const uint8_t* __restrict__ img = staging + d.offset;
+    const float scale_w = __fdiv_rn((float)d.w, (float)mw);
+    const float scale_h = __fdiv_rn((float)d.h, (float)mh);
+    const int sy = src_index(y, scale_h, d.h);
+    const uint8_t* __restrict__ row = img + (size_t)sy * d.w * 3;
+
+    float r[4], g[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = min(x0 + i, mw - 1);
+        const int sx = src_index(x, scale_w, d.w);
+        const uint8_t* px = row + (size_t)sx * 3;
+        // source is BGR; the reference reads channel 2-c for output channel c
+        b[i] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
+        g[i] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
+        r[i] = __fdiv_rn((float)__ldg(px + 2), 255.0f);
+    }
+    const int nvalid = min(4, mw - x0);
+    if (LAYOUT == PRE_NCHW_F32) {
+        float* o = reinterpret_cast<float*>(out) + (size_t)f * 3 * mh * mw + (size_t)y * mw + x0;
+        const size_t plane = (size_t)mh * mw;
+        if (nvalid == 4 && (mw & 3) == 0) {
+            *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+            *reinterpret_cast<float4*>(o + plane) = make_float4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<float4*>(o + 2 * plane) = make_float4(b[0], b[1], b[2], b[3]);
+        } else {
+            for (int i = 0; i < nvalid; ++i) { o[i] = r[i]; o[plane + i] = g[i]; o[2 * plane + i] = b[i]; }
+        }
+    } else if (LAYOUT == PRE_NHWC4_F32) {
+        float4* o = reinterpret_cast<float4*>(out) + ((size_t)f * mh + y) * mw + x0;
+        for (int i = 0; i < nvalid; ++i) o[i] = make_float4(r[i], g[i], b[i], 0.0f);
+    } else {
+        uint2* o = reinterpret_cast<uint2*>(out) + ((size_t)f * mh + y) * mw + x0;
+        uint2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 rg = __floats2bfloat162_rn(r[i], g[i]);
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(b[i], 0.0f);
+            v[i] = make_uint2(*reinterpret_cast<uint32_t*>(&rg), *reinterpret_cast<uint32_t*>(&b0));
+        }
+        if (nvalid == 4 && (mw & 3) == 0) {
+            reinterpret_cast<uint4*>(o)[0] = make_uint4(v[0].x, v[0].y, v[1].x, v[1].y);
+            reinterpret_cast<uint4*>(o)[1] = make_uint4(v[2].x, v[2].y, v[3].x, v[3].y);
+        } else {
+            for (int i = 0; i < nvalid; ++i) o[i] = v[i];
+        }
+    }
+}
+
+}  // namespace
+
+int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
+                          int32_t mw, int32_t mh, int32_t layout, void* out)
+{
+    if (n <= 0) return ZL_OK;
+    const int threads = 256;
+    dim3 grid(ceil_div(ceil_div(mw, 4) * mh, threads), n);
+    switch (layout) {
+        case PRE_NCHW_F32: preprocess_kernel<PRE_NCHW_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
+        case PRE_NHWC4_F32: preprocess_kernel<PRE_NHWC4_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
+        case PRE_NHWC4_BF16: preprocess_kernel<PRE_NHWC4_BF16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
+        default: ZL_FAIL(ZL_INVALID_ARGUMENT, "bad preprocess layout");
+    }
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+}  // namespace zl
