@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 YOLOv8 detector (contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's engine
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json `metric`, configs[2]): YOLOv8n 640x640, batch 64 per GPU, bf16 tensor-core
+path, nc=80, synthetic frames + seeded random-init weights.  One "step" = one pass of the whole hot
+path (preprocess -> 63 convs -> DFL decode -> filter -> NMS -> D2H of the detections) over one batch.
+`value` = frames/s with the frames already resident in HBM (4 rotating input sets, 315 MB > L2),
+timed with CUDA events on the engine's stream inside the C library; `e2e` = the same metric through
+zl_infer_batch() with HOST (pinned) frames, H2D and D2H copies inside the timed region.
+Multi-GPU: frames never share state, so ranks are independent replicas fed their own batches
+(no collective on the data path; NCCL is used only for the barrier and the max-over-ranks time).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "zero-latency-yolo_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+SCALE, NC, HW, BATCH = "n", 80, 640, 64
+CONF, IOU = 0.5, 0.45
+WORKLOAD = f"YOLOv8{SCALE} {HW}x{HW} batch {BATCH} per GPU, bf16 tcgen05 path, nc={NC}, conf {CONF} iou {IOU}"
+METRIC, UNIT = "frames_per_sec_yolov8n_640_b64", "frames/s"
+FLOPS_PER_FRAME = 8.7429e9          # conv FLOPs (2*MAC), v8n 640 nc=80
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(n_sets, seed0=5678):
+    from oracle import synth
+    return [synth.frames_structured(BATCH, HW, HW, seed=seed0 + s) for s in range(n_sets)]
+
+
+def make_model():
+    from oracle import yolov8_ref, zlw
+    tensors = yolov8_ref.synthetic_model(SCALE, NC, seed=0)
+    return tensors, zlw.dumps(tensors, SCALE, NC)
+
+
+# ----------------------------------------------------------------------------- CPU legs (oracle port)
+def cpu_pipeline_fps(tensors, frames, threads, batch):
+    """Reference path on host cores: P1 (C) -> YOLOv8 (torch CPU fp32, stand-in for the ORT CPU session)
+    -> F1/N1 (C).  batch=1 is how the reference runs (onnx_engine.cpp:348-352 never batches)."""
+    import torch
+    from oracle import oracle_c, yolov8_ref
+    torch.set_num_threads(threads)
+    sess = yolov8_ref.Session(tensors, SCALE, NC)
+    t0 = time.perf_counter()
+    ndet = 0
+    for i0 in range(0, len(frames), batch):
+        chunk = frames[i0:i0 + batch]
+        x = np.stack([oracle_c.preprocess(f, HW, HW, HW, HW)[1] for f in chunk])
+        raw = sess.run(x)
+        for j in range(len(chunk)):
+            d, _ = oracle_c.postprocess(raw[j], HW, HW, CONF, IOU)
+            ndet += len(d)
+    dt = time.perf_counter() - t0
+    return len(frames) / dt, dt, ndet
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  It cannot be compiled here
+    (ONNX Runtime and the model are absent, sources have compile errors: SURVEY.md §0 fact 5), so this
+    is the oracle port, b=1 sequential like the reference, all host threads."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    tensors, _ = make_model()
+    sample = 8                                       # frames per step: bounded sample of the 64-frame batch
+    frames = list(make_inputs(1)[0][:sample])
+    for _ in range(max(args.warmup, 1)):
+        cpu_pipeline_fps(tensors, frames[:2], cores, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pipeline_fps(tensors, frames, cores, 1)
+    dt = time.perf_counter() - t0
+    fps = args.steps * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.replace("bf16 tcgen05 path", "fp32 CPU path"), "sample": f"{sample} frames per step, b=1 sequential"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps x {sample} frames, b=1 sequential, torch-CPU stand-in for ORT-CPU + C pre/post"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import zlb200
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    tensors, blob = make_model()
+    n_sets = 4
+    sets = make_inputs(n_sets, seed0=5678 + 100 * rank)
+    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=zlb200.BF16, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank)
+    eng.load_weights_blob(blob)
+    eng.warmup(1)
+    for s in range(n_sets):
+        eng.upload_resident(s, list(sets[s]))
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    eng.run_resident(n_sets, max(args.warmup, 3))
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ms, launches, _ = eng.run_resident(n_sets, args.steps)
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * BATCH * args.steps / (max_ms / 1e3)
+
+    # ---- end to end through the public C-ABI call with pinned HOST frames
+    pinned = zlb200.pinned_array((BATCH, HW, HW, 3))
+    pinned[:] = sets[0]
+    pframes = [pinned[i] for i in range(BATCH)]
+    for _ in range(3):
+        dets = eng.infer(pframes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dets = eng.infer(pframes)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_fps = world * BATCH * args.steps / float(t.item())
+    n_det = sum(len(d) for d in dets)
+    d2h = (4 + 2 * BATCH) * 4 + min(BATCH * 64, BATCH * eng.A) * 24
+
+    if rank != 0:
+        return
+
+    # ---- per-kernel roofline (rank 0): same pass, un-captured, one CUDA-event pair per kernel
+    prof = eng.profile(0, 3)
+    tc = [p for p in prof if p["kind"] == 1]
+    tc_ms = sum(p["ms"] for p in tc)
+    tc_flops = sum(p["flops"] for p in tc)
+    tc_bytes = sum(p["bytes"] for p in tc)
+    step_ms_prof = sum(p["ms"] for p in prof)
+    tflops = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    gbs = tc_bytes / (tc_ms * 1e-3) / 1e9 if tc_ms > 0 else 0.0
+    ridge = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)
+    ai = tc_flops / tc_bytes if tc_bytes else 0.0
+    hbm_bound = ai < ridge
+    roofline = {
+        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % len(tc),
+        "bound": "hbm" if hbm_bound else "tensor",
+        "achieved": gbs if hbm_bound else tflops,
+        "peak": peaks["hbm"] if hbm_bound else peaks["tf_sust"],
+        "unit": "GB/s" if hbm_bound else "TFLOP/s",
+        "frac": (gbs / peaks["hbm"]) if hbm_bound else (tflops / peaks["tf_sust"]),
+        "traffic": None,
+        "peak_source": peaks["src"] + (", sustained figure: kernel timed inside a long step" if not hbm_bound else ""),
+        "tensor_tflops": tflops, "tensor_frac_of_sustained": tflops / peaks["tf_sust"],
+        "hbm_gbs_algorithmic": gbs, "hbm_frac": gbs / peaks["hbm"],
+        "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+        "share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
+        "how": "zl_engine_profile: CUDA-event pair around every kernel on the engine stream, 3 passes after the timed region",
+    }
+    top = sorted(prof, key=lambda p: -p["ms"])[:8]
+    roofline["top_kernels_ms"] = [{"name": p["name"], "ms": round(p["ms"], 4),
+                                   "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["ms"] > 0 and p["flops"] else None,
+                                   "gbs": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1) if p["ms"] > 0 and p["bytes"] else None} for p in top]
+    pre = [p for p in prof if p["kind"] == 0][0]
+    roofline["preprocess"] = {"ms": pre["ms"], "gbs": pre["bytes"] / (pre["ms"] * 1e-3) / 1e9 if pre["ms"] > 0 else None,
+                              "hbm_frac": (pre["bytes"] / (pre["ms"] * 1e-3) / 1e9) / peaks["hbm"] if pre["ms"] > 0 else None}
+
+    # ---- b=1 416x416 latency (BASELINE configs[1]), CUDA graph, frame in pinned host memory
+    latency = None
+    try:
+        from oracle import synth, yolov8_ref, zlw
+        t4 = yolov8_ref.synthetic_model("n", 4, seed=0)
+        e1 = zlb200.Engine(416, 416, 4, "n", precision=zlb200.BF16, max_batch=1, device=local_rank)
+        e1.load_weights_blob(zlw.dumps(t4, "n", 4))
+        e1.warmup(3)
+        pf = zlb200.pinned_array((416, 416, 3))
+        pf[:] = synth.frames_structured(1, 416, 416)[0]
+        lat = np.sort(e1.bench_latency(pf, warmup=200, iters=2000))
+        latency = {"workload": "YOLOv8n 416x416 b=1 nc=4, CUDA graph, pinned host frame -> detections on host",
+                   "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]), "mean_ms": float(lat.mean()),
+                   "device_ms": e1.stats()["avg_device_time_ms"], "iters": 2000}
+        e1.close()
+    except Exception as ex:  # the headline number must still print
+        latency = {"error": str(ex)}
+
+    # ---- CPU baseline on the box's host cores (N=1 only): bounded sample of the same workload
+    cpu_baseline = None
+    if world == 1:
+        cores = os.cpu_count() or 1
+        sample = list(sets[0][:16])
+        cpu_pipeline_fps(tensors, sample[:2], cores, 1)
+        fps1, dt1, _ = cpu_pipeline_fps(tensors, sample, cores, 1)
+        fps8, dt8, _ = cpu_pipeline_fps(tensors, sample, cores, 8)
+        cpu_baseline = {"value": fps1, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"16 frames b=1 sequential ({dt1:.1f}s), as the reference runs; batched b=8: {fps8:.1f} frames/s ({dt8:.1f}s)",
+                        "note": "torch-CPU fp32 stand-in for the ORT-CPU session + C pre/post (reference not compilable here)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "inputs": f"{n_sets} rotating resident input sets of {BATCH} frames ({n_sets * BATCH * HW * HW * 3 / 1e6:.0f} MB > 126 MB L2)",
+                   "frames_per_step_per_gpu": BATCH, "parallelism": f"frame-sharded replicas x{world}, no collective"},
+        "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * HW * HW * 3, "d2h_bytes_per_step": d2h,
+                "api": "zl_infer_batch (C-ABI) on pinned host frames, synchronous", "detections_last_step": n_det},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "latency_b1_416": latency,
+        "tensor_roof_frac_whole_step": value * FLOPS_PER_FRAME / (world * peaks["tf_sust"] * 1e12),
+        "wall_ms_per_step_rank0": wall_ms / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

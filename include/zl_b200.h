@@ -187,6 +187,10 @@ ZL_API int32_t zl_engine_run_resident(zl_engine* e, int32_t n_sets, int32_t step
 /* Same pass, un-captured, one CUDA-event pair per kernel; fills up to cap records. */
 ZL_API int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters,
                                  zl_op_profile* out, int32_t cap, int32_t* n_out);
+/* b=1 latency loop in C (no interpreter in the timed path): `iters` synchronous runInference calls on one
+ * HOST frame (pinned or not), each timed with steady_clock from call to detections-on-host; ms_out[iters]. */
+ZL_API int32_t zl_bench_latency(zl_engine* e, const uint8_t* bgr, int32_t width, int32_t height,
+                                int32_t warmup, int32_t iters, float* ms_out);
 /* Stand-alone kernels with device-resident synthetic data, for roofline lines. */
 ZL_API int32_t zl_bench_preprocess(zl_engine* e, int32_t width, int32_t height, int32_t n,
                                    int32_t iters, float* ms_per_launch, double* bytes_per_launch);

@@ -28,8 +28,9 @@ from oracle.zlw import SCALES, _ch, _rep, conv_specs
 class _Net:
     """Functional forward over a dict of folded tensors (name -> np/torch array)."""
 
-    def __init__(self, tensors, scale: str, nc: int):
-        self.t = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in tensors.items()}
+    def __init__(self, tensors, scale: str, nc: int, dtype=torch.float32):
+        self.dtype = dtype
+        self.t = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32).to(dtype) for k, v in tensors.items()}
         self.scale, self.nc = scale, nc
         depth, width, max_c = SCALES[scale]
         self.n = [_rep(3, depth), _rep(6, depth), _rep(6, depth), _rep(3, depth)]
@@ -99,20 +100,21 @@ class _Net:
 def dfl_decode(boxes, clss, strides=(8, 16, 32)):
     """Detect tail: DFL softmax expectation, dist2bbox(xywh), x stride, sigmoid."""
     B = boxes[0].shape[0]
+    dt = boxes[0].dtype
     box = torch.cat([b.reshape(B, 64, -1) for b in boxes], 2)            # [B,64,A]
     cls = torch.cat([c.reshape(B, c.shape[1], -1) for c in clss], 2)     # [B,nc,A]
     A = box.shape[2]
     anc, strd = [], []
     for b, s in zip(boxes, strides):
         h, w = b.shape[2:]
-        sy, sx = torch.meshgrid(torch.arange(h, dtype=torch.float32) + 0.5,
-                                torch.arange(w, dtype=torch.float32) + 0.5, indexing="ij")
+        sy, sx = torch.meshgrid(torch.arange(h, dtype=dt) + 0.5,
+                                torch.arange(w, dtype=dt) + 0.5, indexing="ij")
         anc.append(torch.stack([sx.reshape(-1), sy.reshape(-1)], 0))      # [2, h*w] (x, y)
-        strd.append(torch.full((h * w,), float(s)))
+        strd.append(torch.full((h * w,), float(s), dtype=dt))
     anc = torch.cat(anc, 1)                                               # [2,A]
     strd = torch.cat(strd)                                                # [A]
     prob = box.view(B, 4, 16, A).softmax(2)
-    dist = (prob * torch.arange(16, dtype=torch.float32).view(1, 1, 16, 1)).sum(2)   # [B,4,A] l,t,r,b
+    dist = (prob * torch.arange(16, dtype=dt).view(1, 1, 16, 1)).sum(2)   # [B,4,A] l,t,r,b
     lt, rb = dist[:, :2], dist[:, 2:]
     x1y1 = anc.unsqueeze(0) - lt
     x2y2 = anc.unsqueeze(0) + rb
@@ -123,14 +125,21 @@ def dfl_decode(boxes, clss, strides=(8, 16, 32)):
 
 
 @torch.inference_mode()
-def forward_raw(tensors, scale, nc, images_nchw, return_maps=False):
-    """images_nchw: [B,3,H,W] fp32 -> output0 [B,4+nc,A] fp32 (numpy)."""
-    net = _Net(tensors, scale, nc)
-    x = torch.as_tensor(np.asarray(images_nchw), dtype=torch.float32)
+def forward_raw(tensors, scale, nc, images_nchw, return_maps=False, fp64=False):
+    """images_nchw: [B,3,H,W] fp32 -> output0 [B,4+nc,A] fp32 (numpy).
+
+    fp64=False: fp32 arithmetic end to end, like the reference's ORT CPU session.
+    fp64=True : same fp32 weights and inputs, every op evaluated in float64 and the
+    result rounded once to fp32 — the summation-order-free value both the fp32 CPU
+    session and the CUDA exact mode approximate (see DESIGN.md "fp32 parity").
+    """
+    dt = torch.float64 if fp64 else torch.float32
+    net = _Net(tensors, scale, nc, dtype=dt)
+    x = torch.as_tensor(np.asarray(images_nchw), dtype=torch.float32).to(dt)
     boxes, clss = net.head_maps(net.features(x))
-    out = dfl_decode(boxes, clss)
+    out = dfl_decode(boxes, clss).to(torch.float32)
     if return_maps:
-        return out.numpy(), [b.numpy() for b in boxes], [c.numpy() for c in clss]
+        return out.numpy(), [b.to(torch.float32).numpy() for b in boxes], [c.to(torch.float32).numpy() for c in clss]
     return out.numpy()
 
 

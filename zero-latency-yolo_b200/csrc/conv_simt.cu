@@ -2,9 +2,14 @@
 //
 // (1) conv_simt_kernel: fp32 implicit GEMM used by the exact ("fp32") mode, the
 //     mode that must match the reference's ONNX Runtime CPU session within 1e-3
-//     abs on raw head outputs (BASELINE.json north_star).  fp32 operands, fp32
-//     FMA accumulation, accurate expf in SiLU.  Replaces the same
-//     Ort::Session::Run nodes as conv_tc.cu (onnx_engine.cpp:577-585).
+//     abs on raw head outputs (BASELINE.json north_star).  fp32 operands and
+//     fp32 activation storage like the reference, but products are accumulated
+//     in fp64 and the bias/SiLU/residual epilogue runs in fp64 before the single
+//     rounding to fp32: two fp32-accumulating implementations of this 25-layer
+//     stack differ by ~3e-3 px on the box rows from summation order alone
+//     (measured: torch-CPU fp32 vs this kernel with fp32 accumulators), so the
+//     1e-3 gate is only meaningful against a summation-order-free result.
+//     Replaces the same Ort::Session::Run nodes as conv_tc.cu (onnx_engine.cpp:577-585).
 // (2) conv0_direct_kernel: the bf16 path's first layer (3->c1, 3x3 s2), whose
 //     K = 27 is too small for an MMA tile and which is purely HBM-bound.
 #include "kernels.h"
@@ -43,7 +48,7 @@ conv_simt_kernel(const SimtParams p)
     const int bk = t >> 4, bn4 = (t & 15) * 4;
     // compute role
     const int tx = t & 15, ty = t >> 4;
-    float acc[4][4] = {};
+    double acc[4][4] = {};
 
     for (int kk = 0; kk < p.ktot; kk += BK) {
         float av[4] = {0.f, 0.f, 0.f, 0.f};
@@ -88,7 +93,7 @@ conv_simt_kernel(const SimtParams p)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma((double)aa[i], (double)bb[j], acc[i][j]);
         }
     }
 #pragma unroll
@@ -99,10 +104,10 @@ conv_simt_kernel(const SimtParams p)
         for (int j = 0; j < 4; ++j) {
             const int c = n0 + tx * 4 + j;
             if (c >= p.Cout) continue;
-            float v = acc[i][j] + __ldg(p.bias + c);
-            if (p.act) v = v / (1.0f + expf(-v));
-            if (p.res) v += __ldg(p.res + (size_t)m * p.rpitch + c);
-            p.y[(size_t)m * p.ypitch + c] = v;
+            double v = acc[i][j] + (double)__ldg(p.bias + c);
+            if (p.act) v = v / (1.0 + exp(-v));
+            if (p.res) v += (double)__ldg(p.res + (size_t)m * p.rpitch + c);
+            p.y[(size_t)m * p.ypitch + c] = (float)v;
         }
     }
 }

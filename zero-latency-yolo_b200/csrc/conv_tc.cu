@@ -43,7 +43,7 @@ struct Params {
     int32_t Ho, Wo, Cout, ypitch, rpitch, y_f32;
     int32_t k, stride, pad, act;
     int32_t kc, nkb, cchunks;
-    int32_t ntile, m_total, a_tma, stages;
+    int32_t ntile, m_total, a_tma, stages, y_vec, r_vec;
     uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
 };
 
@@ -293,7 +293,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const bool full = (cg + 16 <= p.Cout);
             if (p.res != nullptr) {
                 const __nv_bfloat16* rp = p.res + (size_t)m * p.rpitch + cg;
-                if (full) {
+                if (full && p.r_vec) {
                     uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
                     uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
                     const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -309,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             }
             if (p.y_f32) {
                 float* yp = reinterpret_cast<float*>(p.y) + (size_t)m * p.ypitch + cg;
-                if (full && ((p.ypitch & 3) == 0)) {
+                if (full && p.y_vec) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -318,7 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 }
             } else {
                 __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)m * p.ypitch + cg;
-                if (full) {
+                if (full && p.y_vec) {
                     uint32_t w[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -397,10 +397,7 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     const int pad = w.k / 2;
     const int Ho = (x.h + 2 * pad - w.k) / w.stride + 1, Wo = (x.w + 2 * pad - w.k) / w.stride + 1;
     if (y.h != Ho || y.w != Wo || y.n != x.n || y.c != w.cout) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: output view mismatch (" + w.name + ")");
-    if (y.dtype == DT_BF16 && ((y.pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(y.ptr) & 15)))
-        ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: output slice not 16-B aligned");
-    if (res && (res->dtype != DT_BF16 || res->c != w.cout || (res->pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(res->ptr) & 15)))
-        ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: residual view mismatch");
+    if (res && (res->dtype != DT_BF16 || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: residual view mismatch");
 
     ConvTcOp& o = *op;
     o.x = reinterpret_cast<const __nv_bfloat16*>(x.ptr);
@@ -410,6 +407,9 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     o.N = x.n; o.H = x.h; o.W = x.w; o.Cin = w.cin; o.xpitch = x.pitch;
     o.Ho = Ho; o.Wo = Wo; o.Cout = w.cout; o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
+    // 16-byte vector stores / residual loads need aligned slices; otherwise the epilogue goes scalar
+    o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
+    o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
     o.k = w.k; o.stride = w.stride; o.pad = pad; o.act = w.act;
     o.kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
     o.swz = o.kc * 2;
@@ -477,7 +477,7 @@ int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& o)
     p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32;
     p.k = o.k; p.stride = o.stride; p.pad = o.pad; p.act = o.act;
     p.kc = o.kc; p.nkb = o.nkb; p.cchunks = o.cchunks;
-    p.ntile = o.ntile; p.m_total = o.m_total; p.a_tma = o.a_tma; p.stages = o.stages;
+    p.ntile = o.ntile; p.m_total = o.m_total; p.a_tma = o.a_tma; p.stages = o.stages; p.y_vec = o.y_vec; p.r_vec = o.r_vec;
     p.a_bytes = kTileM * o.kc * 2;
     p.b_bytes = (uint32_t)o.ntile * o.kc * 2;
     p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);

@@ -465,7 +465,7 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h)
             case Op::CONV0: ZL_TRY(launch_conv0_direct(st, *op.w, op.x, op.y)); break;
             case Op::POOL: ZL_TRY(launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3)); break;
             case Op::UPSAMPLE: ZL_TRY(launch_upsample2x(st, op.x, op.y)); break;
-            case Op::DECODE: ZL_TRY(launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw)); break;
+            case Op::DECODE: ZL_TRY(launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw, !bf16)); break;
             case Op::FILTER:
                 ZL_TRY(launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb));
                 break;
@@ -805,7 +805,7 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
                 case Op::CONV0: rc = launch_conv0_direct(st, *op.w, op.x, op.y); break;
                 case Op::POOL: rc = launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3); break;
                 case Op::UPSAMPLE: rc = launch_upsample2x(st, op.x, op.y); break;
-                case Op::DECODE: rc = launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw); break;
+                case Op::DECODE: rc = launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw, !bf16); break;
                 case Op::FILTER: rc = launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb); break;
                 case Op::NMS: rc = launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb); break;
             }
@@ -859,6 +859,25 @@ int32_t Engine::bench_preprocess(int w, int h, int n, int iters, float* ms, doub
     // bytes actually sampled (min(src, dst) pixels x 3) + output written (3 channels x element size)
     const double sampled = (double)std::min((size_t)w * h, (size_t)cfg.model_w * cfg.model_h) * 3;
     if (bytes) *bytes = n * (sampled + (double)cfg.model_w * cfg.model_h * 3 * (bf16 ? 2 : 4));
+    return ZL_OK;
+}
+
+int32_t Engine::bench_latency(const uint8_t* bgr, int w, int h, int warm, int iters, float* ms_out)
+{
+    if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
+    if (!bgr || !ms_out || iters < 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    const bool pinned = is_pinned(bgr);
+    std::vector<zl_det> dets;
+    int32_t cnt = 0;
+    const uint8_t* fr[1] = {bgr};
+    for (int i = 0; i < warm + iters; ++i) {
+        const auto t0 = std::chrono::steady_clock::now();
+        ZL_TRY(run_lane_batch(L, fr, &w, &h, 1, pinned, &dets, &cnt));
+        const auto t1 = std::chrono::steady_clock::now();
+        if (i >= warm) ms_out[i - warm] = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    }
     return ZL_OK;
 }
 

@@ -49,7 +49,7 @@ struct ConvTcOp {
     int32_t k, stride, pad, act;
     int32_t kc, swz, nkb, cchunks;     // channels per K-block, swizzle bytes, #K-blocks, chunks per tap
     int32_t ntile, ngrid;              // N tile (<=256, multiple of 16) and number of N tiles
-    int32_t m_total, a_tma;
+    int32_t m_total, a_tma, y_vec, r_vec;
     int32_t stages, smem_bytes, tmem_cols;
     double flops, bytes;
 };
@@ -69,7 +69,7 @@ struct HeadLevel {
     int32_t h, w, stride, cls_pitch, a0;   // a0 = first anchor index of the level
 };
 // Detect tail -> raw head output [n, 4+nc, A] fp32 (the reference's output0).
-int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw);
+int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw, bool precise);
 
 struct PostBuffers {
     uint64_t* keys;        // [n][key_pitch] candidate sort keys (key_pitch = pow2 >= A)

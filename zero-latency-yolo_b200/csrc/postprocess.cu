@@ -13,6 +13,7 @@
 // All fp32 arithmetic that decides an outcome uses the *_rn intrinsics so no
 // FMA contraction can make a comparison differ from the IEEE CPU oracle.
 #include <cfloat>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -23,6 +24,8 @@ namespace {
 constexpr int kDflAnchors = 32;    // anchors per CTA
 constexpr int kDflThreads = 256;   // 8 warps, 4 anchors each
 
+// PRECISE = fp64 softmax / sigmoid / box arithmetic (exact mode); otherwise fp32 (bf16 mode).
+template <bool PRECISE>
 __global__ void __launch_bounds__(kDflThreads)
 dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, int nc, int A, float* __restrict__ raw)
 {
@@ -49,9 +52,12 @@ dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, in
             ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
             mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
         }
-        const float ea = expf(va - ma), eb = expf(vb - mb);
-        const float bin = (float)(lane & 15);
-        float sa = ea, sb = eb, wa = ea * bin, wb = eb * bin;
+        using T = typename std::conditional<PRECISE, double, float>::type;
+        T ea, eb;
+        if (PRECISE) { ea = (T)exp((double)va - (double)ma); eb = (T)exp((double)vb - (double)mb); }
+        else { ea = (T)expf(va - ma); eb = (T)expf(vb - mb); }
+        const T bin = (T)(lane & 15);
+        T sa = ea, sb = eb, wa = ea * bin, wb = eb * bin;
 #pragma unroll
         for (int o = 8; o >= 1; o >>= 1) {
             sa += __shfl_xor_sync(0xffffffffu, sa, o);
@@ -59,22 +65,22 @@ dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, in
             wa += __shfl_xor_sync(0xffffffffu, wa, o);
             wb += __shfl_xor_sync(0xffffffffu, wb, o);
         }
-        const float da = wa / sa, db = wb / sb;       // lanes 0-15: left,right ; lanes 16-31: top,bottom
-        const float dl = __shfl_sync(0xffffffffu, da, 0), dt = __shfl_sync(0xffffffffu, da, 16);
-        const float dr = __shfl_sync(0xffffffffu, db, 0), dbm = __shfl_sync(0xffffffffu, db, 16);
+        const T da = wa / sa, db = wb / sb;           // lanes 0-15: left,right ; lanes 16-31: top,bottom
+        const T dl = __shfl_sync(0xffffffffu, da, 0), dt = __shfl_sync(0xffffffffu, da, 16);
+        const T dr = __shfl_sync(0xffffffffu, db, 0), dbm = __shfl_sync(0xffffffffu, db, 16);
         if (lane == 0) {
-            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, s = (float)lv.stride;
-            const float x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + dbm;
-            stage[0 * 33 + la] = (x1 + x2) * 0.5f * s;
-            stage[1 * 33 + la] = (y1 + y2) * 0.5f * s;
-            stage[2 * 33 + la] = (x2 - x1) * s;
-            stage[3 * 33 + la] = (y2 - y1) * s;
+            const T ax = (T)x + (T)0.5, ay = (T)y + (T)0.5, s = (T)lv.stride;
+            const T x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + dbm;
+            stage[0 * 33 + la] = (float)((x1 + x2) * (T)0.5 * s);
+            stage[1 * 33 + la] = (float)((y1 + y2) * (T)0.5 * s);
+            stage[2 * 33 + la] = (float)((x2 - x1) * s);
+            stage[3 * 33 + la] = (float)((y2 - y1) * s);
         }
         // ---- classes: sigmoid, transposed through smem
         const float* cp = lv.cls + pix * lv.cls_pitch;
         for (int c = lane; c < nc; c += 32) {
             const float z = __ldg(cp + c);
-            stage[(4 + c) * 33 + la] = 1.0f / (1.0f + expf(-z));
+            stage[(4 + c) * 33 + la] = PRECISE ? (float)(1.0 / (1.0 + exp(-(double)z))) : 1.0f / (1.0f + expf(-z));
         }
     }
     __syncthreads();
@@ -295,12 +301,13 @@ int g_nms_smem_keys = 0;   // key capacity (elements) of the smem sort buffer
 
 }  // namespace
 
-int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw)
+int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw, bool precise)
 {
     dim3 grid(ceil_div(A, kDflAnchors), n);
     const size_t smem = (size_t)(4 + nc) * 33 * sizeof(float);
     if (smem > 48 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "dfl_decode: nc too large");
-    dfl_decode_kernel<<<grid, kDflThreads, smem, st>>>(lv[0], lv[1], lv[2], nc, A, raw);
+    if (precise) dfl_decode_kernel<true><<<grid, kDflThreads, smem, st>>>(lv[0], lv[1], lv[2], nc, A, raw);
+    else dfl_decode_kernel<false><<<grid, kDflThreads, smem, st>>>(lv[0], lv[1], lv[2], nc, A, raw);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }

@@ -55,7 +55,7 @@ EXPORTS = [
     "zl_engine_load_weights_mem", "zl_engine_warmup", "zl_engine_set_callback", "zl_engine_submit",
     "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
-    "zl_engine_run_resident", "zl_engine_profile", "zl_bench_preprocess", "zl_bench_decode_nms",
+    "zl_engine_run_resident", "zl_engine_profile", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
     "zl_test_conv", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
 
@@ -97,6 +97,7 @@ def lib():
             "zl_engine_upload_resident": (i32, [vp, i32, vp, vp, vp, i32]),
             "zl_engine_run_resident": (i32, [vp, i32, i32, C.POINTER(f32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "zl_engine_profile": (i32, [vp, i32, i32, C.POINTER(OpProfile), i32, C.POINTER(i32)]),
+            "zl_bench_latency": (i32, [vp, vp, i32, i32, i32, i32, vp]),
             "zl_bench_preprocess": (i32, [vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(C.c_double)]),
             "zl_bench_decode_nms": (i32, [vp, vp, i32, i32, i32, f32, f32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int64)]),
             "zl_test_conv": (i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
@@ -261,6 +262,12 @@ class Engine:
         _check(lib().zl_engine_profile(self.h, set_idx, iters, arr, 256, C.byref(n)))
         return [dict(name=arr[i].name.decode(), kind=arr[i].kind, ms=arr[i].ms, flops=arr[i].flops, bytes=arr[i].bytes)
                 for i in range(n.value)]
+
+    def bench_latency(self, frame, warmup=50, iters=500):
+        f = frame if isinstance(frame, np.ndarray) else np.ascontiguousarray(frame, np.uint8)
+        out = np.zeros(iters, np.float32)
+        _check(lib().zl_bench_latency(self.h, _ptr(f), f.shape[1], f.shape[0], warmup, iters, _ptr(out)))
+        return out
 
     def bench_preprocess(self, w, h, n, iters=20):
         ms, b = C.c_float(), C.c_double()
