@@ -54,7 +54,7 @@ enum {
 
 /* ---- enums ---- */
 enum { ZL_SCALE_N = 0, ZL_SCALE_S = 1, ZL_SCALE_M = 2 };          /* YOLOv8 n / s / m */
-enum { ZL_PRECISION_FP32 = 0, ZL_PRECISION_BF16 = 1 };            /* fp32 = exact CUDA-core mode, bf16 = tcgen05 */
+enum { ZL_PRECISION_FP32 = 0, ZL_PRECISION_BF16 = 1, ZL_PRECISION_FP16 = 2 };   /* fp32 = exact CUDA-core mode; bf16 / fp16 = tcgen05, fp32 accumulate */
 enum { ZL_PRE_STRETCH_NEAREST = 0, ZL_PRE_LETTERBOX = 1 };        /* 0 = the reference's behaviour (parity mode) */
 
 /* One detection as the device emits it: the first 24 bytes of the reference's

@@ -115,6 +115,28 @@ def test_conv_tcgen05(built_lib, case, impl):
     assert np.abs(y16 - ref).max() < 1.2e-2 * max(1.0, np.abs(ref).max()), "bf16-out mismatch"
 
 
+def _h(a):
+    return torch.tensor(a).to(torch.float16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("case", CONV_CASES[:6])
+def test_conv_tcgen05_fp16(built_lib, case):
+    import zlb200
+    n, h, w, cin, cout, k, s, act, use_res = case
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = _h(rng.normal(size=(n, h, w, cin)).astype(np.float32))
+    wt = _h((rng.normal(size=(cout, k, k, cin)) / np.sqrt(cin * k * k)).astype(np.float32))
+    b = rng.normal(size=cout).astype(np.float32)
+    pad = k // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    res = _h(rng.normal(size=(n, ho, wo, cout)).astype(np.float32)) if use_res else None
+    ref = _torch_conv(x, wt, b, s, act, res)
+    y32 = zlb200.test_conv(x, wt, b, stride=s, act=act, res=res, impl=2, out_f32=True, fp16=True)
+    assert np.abs(y32 - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())
+    y16 = zlb200.test_conv(x, wt, b, stride=s, act=act, res=res, impl=2, out_f32=False, fp16=True)
+    assert np.abs(y16 - ref).max() < 2e-3 * max(1.0, np.abs(ref).max())      # half has 3 more mantissa bits than bf16
+
+
 @pytest.mark.parametrize("hint", [16, 32, 64])
 def test_conv_tcgen05_n_split(built_lib, hint):
     import zlb200

@@ -2,6 +2,8 @@
 // No exception may cross this boundary (the reference wraps every engine call in
 // try/catch and returns Result::error, onnx_engine.cpp:165-169,621-645).
 #include <cstring>
+
+#include <cuda_fp16.h>
 #include <fstream>
 #include <new>
 #include <vector>
@@ -266,6 +268,8 @@ static inline uint16_t f2bf_host(float f) {
     return (uint16_t)(u >> 16);
 }
 static inline float bf2f_host(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint16_t f2h_host(float f) { const __half h = __float2half_rn(f); uint16_t u; std::memcpy(&u, &h, 2); return u; }
+static inline float h2f_host(uint16_t v) { __half h; std::memcpy(&h, &v, 2); return __half2float(h); }
 
 int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, int32_t h, int32_t w, int32_t cin,
                      const float* wgt, const float* bias, int32_t cout, int32_t k, int32_t stride, int32_t act_flags,
@@ -277,7 +281,9 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) { cudaGetLastError(); set_error("no such CUDA device"); return ZL_INSUFFICIENT_RESOURCES; }
     ZL_CUDA(cudaSetDevice(device));
-    const int act = act_flags & 1, out_f32 = (act_flags >> 1) & 1, hint = (act_flags >> 8) & 0x1ff;
+    const int act = act_flags & 1, out_f32 = (act_flags >> 1) & 1, f16 = (act_flags >> 2) & 1, hint = (act_flags >> 8) & 0x1ff;
+    auto cvt = [&](float v) { return f16 ? f2h_host(v) : f2bf_host(v); };
+    const int dt16 = f16 ? DT_F16 : DT_BF16;
     const int pad = k / 2, ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
     ConvWeights cw;
     cw.name = "test"; cw.cin = cin; cw.cout = cout; cw.k = k; cw.stride = stride; cw.act = act;
@@ -310,9 +316,9 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
         if (rc == ZL_OK) cudaMemcpy(y, dy, ny * 4, cudaMemcpyDeviceToHost);
     } else {
         std::vector<uint16_t> wt((size_t)cw.cout_pad * cw.ktot, 0), hx(nx), hr(res ? ny : 0);
-        for (int o = 0; o < cout; ++o) for (int t = 0; t < cw.ktot; ++t) wt[(size_t)o * cw.ktot + t] = f2bf_host(wgt[(size_t)o * cw.ktot + t]);
-        for (size_t i = 0; i < nx; ++i) hx[i] = f2bf_host(x[i]);
-        for (size_t i = 0; i < hr.size(); ++i) hr[i] = f2bf_host(res[i]);
+        for (int o = 0; o < cout; ++o) for (int t = 0; t < cw.ktot; ++t) wt[(size_t)o * cw.ktot + t] = cvt(wgt[(size_t)o * cw.ktot + t]);
+        for (size_t i = 0; i < nx; ++i) hx[i] = cvt(x[i]);
+        for (size_t i = 0; i < hr.size(); ++i) hr[i] = cvt(res[i]);
         cw.w_tc = (__nv_bfloat16*)dalloc(wt.size() * 2);
         void* dx = dalloc(nx * 2); void* dy = dalloc(ny * (out_f32 ? 4 : 2)); void* dr = res ? dalloc(ny * 2) : nullptr;
         if (!cw.w_tc || !dx || !dy || (res && !dr)) { cleanup(); set_error("oom"); return ZL_INSUFFICIENT_RESOURCES; }
@@ -320,7 +326,7 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
         cudaMemcpy(dx, hx.data(), nx * 2, cudaMemcpyHostToDevice);
         if (res) cudaMemcpy(dr, hr.data(), ny * 2, cudaMemcpyHostToDevice);
         cudaMemset(dy, 0xff, ny * (out_f32 ? 4 : 2));
-        View vx{dx, n, h, w, cin, cin, DT_BF16}, vy{dy, n, ho, wo, cout, cout, out_f32 ? DT_F32 : DT_BF16}, vr{dr, n, ho, wo, cout, cout, DT_BF16};
+        View vx{dx, n, h, w, cin, cin, dt16}, vy{dy, n, ho, wo, cout, cout, out_f32 ? DT_F32 : dt16}, vr{dr, n, ho, wo, cout, cout, dt16};
         ConvTcOp op;
         rc = conv_tc_prepare(cw, vx, vy, res ? &vr : nullptr, impl == 2, hint, &op);
         if (rc == ZL_OK) rc = conv_tc_launch(st, op);
@@ -330,7 +336,7 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
             else {
                 std::vector<uint16_t> hy(ny);
                 cudaMemcpy(hy.data(), dy, ny * 2, cudaMemcpyDeviceToHost);
-                for (size_t i = 0; i < ny; ++i) y[i] = bf2f_host(hy[i]);
+                for (size_t i = 0; i < ny; ++i) y[i] = f16 ? h2f_host(hy[i]) : bf2f_host(hy[i]);
             }
         }
     }

@@ -43,7 +43,7 @@ struct Status {
     } while (0)
 
 // ---- tensor view: NHWC slice of a (possibly wider) buffer -----------------
-enum DType : int32_t { DT_F32 = 0, DT_BF16 = 1 };
+enum DType : int32_t { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };   // both 16-bit formats share the h16 buffers
 
 struct View {
     void* ptr = nullptr;   // already offset to the first channel of the slice
@@ -51,6 +51,7 @@ struct View {
     int32_t pitch = 0;     // elements between consecutive pixels of the underlying buffer
     int32_t dtype = DT_BF16;
     size_t esize() const { return dtype == DT_F32 ? 4 : 2; }
+    bool is16() const { return dtype != DT_F32; }
     size_t pixels() const { return (size_t)n * h * w; }
     View slice(int32_t c0, int32_t cn) const {
         View v = *this;

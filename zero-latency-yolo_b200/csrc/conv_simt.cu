@@ -12,6 +12,7 @@
 //     Replaces the same Ort::Session::Run nodes as conv_tc.cu (onnx_engine.cpp:577-585).
 // (2) conv0_direct_kernel: the bf16 path's first layer (3->c1, 3x3 s2), whose
 //     K = 27 is too small for an MMA tile and which is purely HBM-bound.
+#include "half16.cuh"
 #include "kernels.h"
 
 namespace zl {
@@ -115,7 +116,7 @@ conv_simt_kernel(const SimtParams p)
 // First layer of the bf16 path: x = [n,H,W,4] bf16 (R,G,B,0), 3x3 stride 2 pad 1.
 __global__ void __launch_bounds__(128)
 conv0_direct_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                    __nv_bfloat16* __restrict__ y, int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int ypitch)
+                    __nv_bfloat16* __restrict__ y, int N, int H, int W, int Ho, int Wo, int Cout, int cout_pad, int ypitch, int f16)
 {
     extern __shared__ float ws[];            // [27][cout_pad] + bias[cout_pad]
     for (int i = threadIdx.x; i < 27 * cout_pad; i += blockDim.x) ws[i] = w[i];
@@ -135,9 +136,9 @@ conv0_direct_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
             float a = 0.f, b = 0.f, c = 0.f;
             if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
                 const uint2 v = __ldg(reinterpret_cast<const uint2*>(x + ((size_t)(n * H + iy) * W + ix) * 4));
-                const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
-                const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
-                a = __bfloat162float(p0.x); b = __bfloat162float(p0.y); c = __bfloat162float(p1.x);
+                float pad_;
+                unpack2_16(v.x, f16, a, b);
+                unpack2_16(v.y, f16, c, pad_);
             }
             in[(r * 3 + s) * 3 + 0] = a; in[(r * 3 + s) * 3 + 1] = b; in[(r * 3 + s) * 3 + 2] = c;
         }
@@ -163,8 +164,7 @@ conv0_direct_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float a = acc[2 * j], b = acc[2 * j + 1];
-            __nv_bfloat162 h = __floats2bfloat162_rn(a / (1.0f + __expf(-a)), b / (1.0f + __expf(-b)));
-            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+            pk[j] = pack2_16(a / (1.0f + __expf(-a)), b / (1.0f + __expf(-b)), f16);
         }
         if (c0 + 16 <= Cout) {
             reinterpret_cast<uint4*>(yp + c0)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -200,14 +200,14 @@ int32_t launch_conv_simt(cudaStream_t st, const ConvWeights& w, const View& x, c
 
 int32_t launch_conv0_direct(cudaStream_t st, const ConvWeights& w, const View& x, const View& y)
 {
-    if (w.cin != 3 || w.k != 3 || w.stride != 2 || x.pitch != 4 || x.dtype != DT_BF16 || y.dtype != DT_BF16)
+    if (w.cin != 3 || w.k != 3 || w.stride != 2 || x.pitch != 4 || !x.is16() || y.dtype != x.dtype)
         ZL_FAIL(ZL_INVALID_ARGUMENT, "conv0_direct: expects the 3->c 3x3 s2 first layer on NHWC4 bf16");
     const int Ho = (x.h + 2 - 3) / 2 + 1, Wo = (x.w + 2 - 3) / 2 + 1;
     if (y.h != Ho || y.w != Wo || y.c != w.cout || (y.pitch % 8) != 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv0_direct: output view mismatch");
     const int m_total = x.n * Ho * Wo;
     const size_t smem = (size_t)28 * w.cout_pad * sizeof(float);
     conv0_direct_kernel<<<ceil_div(m_total, 128), 128, smem, st>>>((const __nv_bfloat16*)x.ptr, w.w_simt, w.bias, (__nv_bfloat16*)y.ptr,
-                                                                  x.n, x.h, x.w, Ho, Wo, w.cout, w.cout_pad, y.pitch);
+                                                                  x.n, x.h, x.w, Ho, Wo, w.cout, w.cout_pad, y.pitch, x.dtype == DT_F16 ? 1 : 0);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }

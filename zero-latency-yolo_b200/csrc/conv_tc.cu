@@ -23,6 +23,7 @@
 
 #include <mutex>
 
+#include "half16.cuh"
 #include "kernels.h"
 
 namespace zl {
@@ -43,7 +44,7 @@ struct Params {
     int32_t Ho, Wo, Cout, ypitch, rpitch, y_f32;
     int32_t k, stride, pad, act;
     int32_t kc, nkb, cchunks;
-    int32_t ntile, m_total, a_tma, stages, y_vec, r_vec;
+    int32_t ntile, m_total, a_tma, stages, y_vec, r_vec, f16;
     uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
 };
 
@@ -201,8 +202,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t swz = (uint32_t)p.kc * 2u;
-        // kind::f16 instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3, M>>4
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        // kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), K-major both, N>>3, M>>4
+        const uint32_t fmt = p.f16 ? 0u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
         const int ksteps = p.kc / 16;
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % stages;
@@ -299,12 +301,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[i]);
-                        f[2 * i] += __bfloat162float(h.x);
-                        f[2 * i + 1] += __bfloat162float(h.y);
+                        float a, b;
+                        unpack2_16(rw[i], p.f16, a, b);
+                        f[2 * i] += a;
+                        f[2 * i + 1] += b;
                     }
                 } else {
-                    for (int i = 0; i < 16 && cg + i < p.Cout; ++i) f[i] += __bfloat162float(rp[i]);
+                    for (int i = 0; i < 16 && cg + i < p.Cout; ++i) f[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
                 }
             }
             if (p.y_f32) {
@@ -321,14 +324,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 if (full && p.y_vec) {
                     uint32_t w[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                        w[i] = *reinterpret_cast<uint32_t*>(&h);
-                    }
+                    for (int i = 0; i < 8; ++i) w[i] = pack2_16(f[2 * i], f[2 * i + 1], p.f16);
                     reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                     reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 } else {
-                    for (int i = 0; i < 16 && cg + i < p.Cout; ++i) yp[i] = __float2bfloat16_rn(f[i]);
+                    for (int i = 0; i < 16 && cg + i < p.Cout; ++i) reinterpret_cast<uint16_t*>(yp)[i] = pack1_16(f[i], p.f16);
                 }
             }
         }
@@ -359,8 +359,8 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-int32_t make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
-                          uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes)
+int32_t make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes, bool f16)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) ZL_FAIL(ZL_SYSTEM_ERROR, "cuTensorMapEncodeTiled entry point not available");
@@ -374,7 +374,7 @@ int32_t make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
                           : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                           : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) ZL_FAIL(ZL_SYSTEM_ERROR, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
@@ -390,14 +390,15 @@ int32_t make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, ui
 int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, const View* res,
                         bool allow_tma_a, int32_t ntile_hint, ConvTcOp* op)
 {
-    if (x.dtype != DT_BF16) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: input must be bf16");
+    if (!x.is16()) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: input must be bf16 or fp16");
+    if (y.is16() && y.dtype != x.dtype) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: 16-bit output must use the input format");
     if (x.c != w.cin || (w.cin % 16) != 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: Cin must be a multiple of 16 (" + w.name + ")");
     if ((x.pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(x.ptr) & 15)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: input slice not 16-B aligned");
     if (w.k != 1 && w.k != 3) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: k must be 1 or 3");
     const int pad = w.k / 2;
     const int Ho = (x.h + 2 * pad - w.k) / w.stride + 1, Wo = (x.w + 2 * pad - w.k) / w.stride + 1;
     if (y.h != Ho || y.w != Wo || y.n != x.n || y.c != w.cout) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: output view mismatch (" + w.name + ")");
-    if (res && (res->dtype != DT_BF16 || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: residual view mismatch");
+    if (res && (res->dtype != x.dtype || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_tc: residual view mismatch");
 
     ConvTcOp& o = *op;
     o.x = reinterpret_cast<const __nv_bfloat16*>(x.ptr);
@@ -407,6 +408,7 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     o.N = x.n; o.H = x.h; o.W = x.w; o.Cin = w.cin; o.xpitch = x.pitch;
     o.Ho = Ho; o.Wo = Wo; o.Cout = w.cout; o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
+    o.f16 = x.dtype == DT_F16 ? 1 : 0;
     // 16-byte vector stores / residual loads need aligned slices; otherwise the epilogue goes scalar
     o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
@@ -442,9 +444,9 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     while (cols < ntile) cols <<= 1;
     o.tmem_cols = cols;
 
-    ZL_TRY(make_tmap_2d_bf16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, ntile, o.swz));
+    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, ntile, o.swz, o.f16));
     if (o.a_tma) {
-        ZL_TRY(make_tmap_2d_bf16(&o.tmap_a, x.ptr, (uint64_t)w.cin, (uint64_t)o.m_total, (uint64_t)x.pitch * 2, o.kc, kTileM, o.swz));
+        ZL_TRY(make_tmap_2d_16(&o.tmap_a, x.ptr, (uint64_t)w.cin, (uint64_t)o.m_total, (uint64_t)x.pitch * 2, o.kc, kTileM, o.swz, o.f16));
     } else {
         o.tmap_a = o.tmap_w;
     }
@@ -477,7 +479,7 @@ int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& o)
     p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32;
     p.k = o.k; p.stride = o.stride; p.pad = o.pad; p.act = o.act;
     p.kc = o.kc; p.nkb = o.nkb; p.cchunks = o.cchunks;
-    p.ntile = o.ntile; p.m_total = o.m_total; p.a_tma = o.a_tma; p.stages = o.stages; p.y_vec = o.y_vec; p.r_vec = o.r_vec;
+    p.ntile = o.ntile; p.m_total = o.m_total; p.a_tma = o.a_tma; p.stages = o.stages; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16;
     p.a_bytes = kTileM * o.kc * 2;
     p.b_bytes = (uint32_t)o.ntile * o.kc * 2;
     p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);

@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 namespace zl {
 
 // ------------------------------------------------------------------ errors
@@ -21,6 +23,8 @@ static inline uint16_t f2bf(float f) {          // round-to-nearest-even, NaN pr
     u += 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
+
+static inline uint16_t f2h(float f) { const __half h = __float2half_rn(f); uint16_t u; std::memcpy(&u, &h, 2); return u; }
 
 static int ch(int c, float width, int maxc) { return (int)std::ceil(std::min(c, maxc) * width / 8.0) * 8; }
 static int rep(int n, float depth) { return std::max((int)std::lround(n * depth), 1); }   // ties: none occur for n in {3,6}
@@ -64,7 +68,7 @@ int32_t Engine::init()
         ZL_FAIL(ZL_INVALID_ARGUMENT, "model_w/model_h must be positive multiples of 32");
     if (cfg.num_classes < 1 || cfg.num_classes > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "num_classes out of range");
     if (cfg.max_batch < 1 || cfg.max_batch > 256) ZL_FAIL(ZL_INVALID_ARGUMENT, "max_batch must be 1..256");
-    if (cfg.precision != ZL_PRECISION_FP32 && cfg.precision != ZL_PRECISION_BF16) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad precision");
+    if (cfg.precision < ZL_PRECISION_FP32 || cfg.precision > ZL_PRECISION_FP16) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad precision");
     if (cfg.preprocess_mode != ZL_PRE_STRETCH_NEAREST) ZL_FAIL(ZL_INVALID_ARGUMENT, "only the reference's nearest-stretch preprocessing is implemented");
     if (cfg.max_frame_w <= 0) cfg.max_frame_w = cfg.model_w;
     if (cfg.max_frame_h <= 0) cfg.max_frame_h = cfg.model_h;
@@ -178,7 +182,8 @@ int32_t Engine::load_weights(const void* blob, size_t len)
     }
     convs.clear();
     conv_by_name.clear();
-    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
+    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
     for (const Spec& s : specs) {
         auto wi = host_w.find(s.name + ".weight"), bi = host_w.find(s.name + ".bias");
         if (wi == host_w.end() || bi == host_w.end()) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "missing tensor " + s.name);
@@ -211,7 +216,7 @@ int32_t Engine::load_weights(const void* blob, size_t len)
                 for (int ci = 0; ci < s.cin; ++ci)
                     for (int r = 0; r < s.k; ++r)
                         for (int q = 0; q < s.k; ++q)
-                            wt[(size_t)o * cw->ktot + (size_t)(r * s.k + q) * s.cin + ci] = f2bf(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]);
+                            wt[(size_t)o * cw->ktot + (size_t)(r * s.k + q) * s.cin + ci] = f16 ? f2h(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]) : f2bf(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]);
             ZL_CUDA(cudaMalloc(&cw->w_tc, wt.size() * 2));
             ZL_CUDA(cudaMemcpy(cw->w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         }
@@ -240,8 +245,8 @@ int32_t Engine::alloc_lane(Lane& L)
     ZL_CUDA(cudaEventCreate(&L.ev0));
     ZL_CUDA(cudaEventCreate(&L.ev1));
     const int MB = cfg.max_batch, H = cfg.model_h, W = cfg.model_w, nc = md.nc, A = num_anchors;
-    const int adt = cfg.precision == ZL_PRECISION_BF16 ? DT_BF16 : DT_F32;
-    const size_t es = adt == DT_BF16 ? 2 : 4;
+    const int adt = cfg.precision == ZL_PRECISION_BF16 ? DT_BF16 : (cfg.precision == ZL_PRECISION_FP16 ? DT_F16 : DT_F32);
+    const size_t es = adt == DT_F32 ? 4 : 2;
 
     struct Req { std::string name; int h, w, c, dtype; };
     std::vector<Req> reqs;
@@ -346,7 +351,8 @@ int32_t Engine::build_ops(Lane& L, int B)
 {
     if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
     std::vector<Op> ops;
-    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
+    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
     auto buf = [&](const std::string& n) { return L.bufs.at(n).with_n(B); };
     int32_t rc = ZL_OK;
 
@@ -450,7 +456,8 @@ int32_t Engine::build_ops(Lane& L, int B)
 int32_t Engine::run_ops(Lane& L, int B, bool with_d2h)
 {
     cudaStream_t st = L.stream;
-    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
+    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
     auto it = L.ops.find(B);
     if (it == L.ops.end()) { ZL_TRY(build_ops(L, B)); it = L.ops.find(B); }
     ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st));
@@ -458,7 +465,7 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h)
     for (const Op& op : it->second) {
         switch (op.kind) {
             case Op::PRE:
-                ZL_TRY(launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, op.y.ptr));
+                ZL_TRY(launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr));
                 break;
             case Op::CONV_TC: ZL_TRY(conv_tc_launch(st, op.tc)); break;
             case Op::CONV_SIMT: ZL_TRY(launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr)); break;
@@ -785,7 +792,8 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
     ZL_TRY(run_ops(L, B, false));                         // warm
     ZL_CUDA(cudaStreamSynchronize(L.stream));
     const std::vector<Op>& ops = L.ops[B];
-    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
+    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
     std::vector<cudaEvent_t> ev(ops.size() + 1);
     for (auto& e : ev) cudaEventCreate(&e);
     std::vector<double> acc(ops.size(), 0.0);
@@ -799,7 +807,7 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
             const Op& op = ops[i];
             cudaEventRecord(ev[i], st);
             switch (op.kind) {
-                case Op::PRE: rc = launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, op.y.ptr); break;
+                case Op::PRE: rc = launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr); break;
                 case Op::CONV_TC: rc = conv_tc_launch(st, op.tc); break;
                 case Op::CONV_SIMT: rc = launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr); break;
                 case Op::CONV0: rc = launch_conv0_direct(st, *op.w, op.x, op.y); break;
@@ -834,7 +842,8 @@ int32_t Engine::bench_preprocess(int w, int h, int n, int iters, float* ms, doub
     ZL_CUDA(cudaSetDevice(cfg.device));
     Lane& L = *lanes[0];
     std::lock_guard<std::mutex> g(L.mu);
-    const bool bf16 = cfg.precision == ZL_PRECISION_BF16;
+    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
+    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
     const size_t fb = (size_t)w * h * 3, ob = (size_t)cfg.model_w * cfg.model_h * 4 * (bf16 ? 2 : 4);
     uint8_t* d_in = nullptr; void* d_out = nullptr; FrameDesc* d_desc = nullptr;
     ZL_CUDA(cudaMalloc(&d_in, fb * n));
@@ -845,9 +854,9 @@ int32_t Engine::bench_preprocess(int w, int h, int n, int iters, float* ms, doub
     for (int i = 0; i < n; ++i) hd[i] = FrameDesc{(uint64_t)i * fb, w, h};
     ZL_CUDA(cudaMemcpy(d_desc, hd.data(), sizeof(FrameDesc) * n, cudaMemcpyHostToDevice));
     int32_t rc = ZL_OK;
-    for (int i = 0; i < 3 && rc == ZL_OK; ++i) rc = launch_preprocess(L.stream, d_in, d_desc, n, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, d_out);
+    for (int i = 0; i < 3 && rc == ZL_OK; ++i) rc = launch_preprocess(L.stream, d_in, d_desc, n, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, d_out);
     cudaEventRecord(L.ev0, L.stream);
-    for (int i = 0; i < iters && rc == ZL_OK; ++i) rc = launch_preprocess(L.stream, d_in, d_desc, n, cfg.model_w, cfg.model_h, bf16 ? PRE_NHWC4_BF16 : PRE_NHWC4_F32, d_out);
+    for (int i = 0; i < iters && rc == ZL_OK; ++i) rc = launch_preprocess(L.stream, d_in, d_desc, n, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, d_out);
     cudaEventRecord(L.ev1, L.stream);
     cudaError_t cs = cudaStreamSynchronize(L.stream);
     float t = 0;

@@ -23,7 +23,8 @@ struct ConvWeights {
 enum PreLayout : int32_t {
     PRE_NCHW_F32 = 0,    // [n,3,mh,mw] fp32 planar: the tensor the reference feeds ORT (onnx_engine.cpp:560)
     PRE_NHWC4_F32 = 1,   // [n,mh,mw,4] fp32 (R,G,B,0): input of the fp32 conv path
-    PRE_NHWC4_BF16 = 2   // [n,mh,mw,4] bf16 (R,G,B,0): input of the bf16 conv path
+    PRE_NHWC4_BF16 = 2,  // [n,mh,mw,4] bf16 (R,G,B,0): input of the bf16 conv path
+    PRE_NHWC4_F16 = 3    // same, IEEE half
 };
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
                           int32_t mw, int32_t mh, int32_t layout, void* out);
@@ -49,7 +50,7 @@ struct ConvTcOp {
     int32_t k, stride, pad, act;
     int32_t kc, swz, nkb, cchunks;     // channels per K-block, swizzle bytes, #K-blocks, chunks per tap
     int32_t ntile, ngrid;              // N tile (<=256, multiple of 16) and number of N tiles
-    int32_t m_total, a_tma, y_vec, r_vec;
+    int32_t m_total, a_tma, y_vec, r_vec, f16;
     int32_t stages, smem_bytes, tmem_cols;
     double flops, bytes;
 };
@@ -91,7 +92,7 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
 int32_t nms_configure();   // one-time cudaFuncSetAttribute calls
 
 // ---------------------------------------------------------------- TMA helper
-int32_t make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
-                          uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes);
+int32_t make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes, bool f16);
 
 }  // namespace zl

@@ -7,6 +7,7 @@
 // 16-byte vector loads/stores, results written straight into the concat buffer.
 #include <cfloat>
 
+#include "half16.cuh"
 #include "kernels.h"
 
 namespace zl {
@@ -19,25 +20,19 @@ template <> struct Vec<float> {
     __device__ static void load(const float* p, float (&f)[4]) { float4 v = __ldg(reinterpret_cast<const float4*>(p)); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
     __device__ static void store(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
 };
-template <> struct Vec<__nv_bfloat16> {
+template <bool F16> struct H16 { uint16_t v; };      // 16-bit element tagged with its format
+template <bool F16> struct Vec<H16<F16>> {
     static constexpr int N = 8;
-    __device__ static void load(const __nv_bfloat16* p, float (&f)[8]) {
+    __device__ static void load(const H16<F16>* p, float (&f)[8]) {
         uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-            f[2 * i] = __bfloat162float(h.x);
-            f[2 * i + 1] = __bfloat162float(h.y);
-        }
+        for (int i = 0; i < 4; ++i) unpack2_16(w[i], F16, f[2 * i], f[2 * i + 1]);
     }
-    __device__ static void store(__nv_bfloat16* p, const float (&f)[8]) {
+    __device__ static void store(H16<F16>* p, const float (&f)[8]) {
         uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
+        for (int i = 0; i < 4; ++i) w[i] = pack2_16(f[2 * i], f[2 * i + 1], F16);
         *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 };
@@ -117,9 +112,12 @@ int32_t launch_sppf_pool(cudaStream_t st, const View& a, const View& p1, const V
     if (a.dtype == DT_F32)
         sppf_pool_kernel<float><<<grid, 256, 0, st>>>((const float*)a.ptr, (float*)p1.ptr, (float*)p2.ptr, (float*)p3.ptr,
                                                       a.n, a.h, a.w, a.c, a.pitch, p1.pitch, p2.pitch, p3.pitch);
+    else if (a.dtype == DT_F16)
+        sppf_pool_kernel<H16<true>><<<grid, 256, 0, st>>>((const H16<true>*)a.ptr, (H16<true>*)p1.ptr, (H16<true>*)p2.ptr,
+                                                          (H16<true>*)p3.ptr, a.n, a.h, a.w, a.c, a.pitch, p1.pitch, p2.pitch, p3.pitch);
     else
-        sppf_pool_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a.ptr, (__nv_bfloat16*)p1.ptr, (__nv_bfloat16*)p2.ptr,
-                                                              (__nv_bfloat16*)p3.ptr, a.n, a.h, a.w, a.c, a.pitch, p1.pitch, p2.pitch, p3.pitch);
+        sppf_pool_kernel<H16<false>><<<grid, 256, 0, st>>>((const H16<false>*)a.ptr, (H16<false>*)p1.ptr, (H16<false>*)p2.ptr,
+                                                           (H16<false>*)p3.ptr, a.n, a.h, a.w, a.c, a.pitch, p1.pitch, p2.pitch, p3.pitch);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }
@@ -134,7 +132,7 @@ int32_t launch_upsample2x(cudaStream_t st, const View& x, const View& y)
     if (x.dtype == DT_F32)
         upsample2x_kernel<float><<<grid, 256, 0, st>>>((const float*)x.ptr, (float*)y.ptr, x.n, x.h, x.w, x.c, x.pitch, y.pitch);
     else
-        upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x.ptr, (__nv_bfloat16*)y.ptr, x.n, x.h, x.w, x.c, x.pitch, y.pitch);
+        upsample2x_kernel<H16<false>><<<grid, 256, 0, st>>>((const H16<false>*)x.ptr, (H16<false>*)y.ptr, x.n, x.h, x.w, x.c, x.pitch, y.pitch);   // pure copy: format-agnostic
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }

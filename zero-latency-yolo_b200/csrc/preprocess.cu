@@ -10,6 +10,7 @@
 //
 // HBM-bound: each thread produces 4 consecutive output pixels of one row and
 // issues one 16/32-byte store (NHWC4) or three 16-byte stores (NCHW planes).
+#include "half16.cuh"
 #include "kernels.h"
 
 namespace zl {
@@ -68,9 +69,7 @@ preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restri
         uint2 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 rg = __floats2bfloat162_rn(r[i], g[i]);
-            __nv_bfloat162 b0 = __floats2bfloat162_rn(b[i], 0.0f);
-            v[i] = make_uint2(*reinterpret_cast<uint32_t*>(&rg), *reinterpret_cast<uint32_t*>(&b0));
+            v[i] = make_uint2(pack2_16(r[i], g[i], LAYOUT == PRE_NHWC4_F16), pack2_16(b[i], 0.0f, LAYOUT == PRE_NHWC4_F16));
         }
         if (nvalid == 4 && (mw & 3) == 0) {
             reinterpret_cast<uint4*>(o)[0] = make_uint4(v[0].x, v[0].y, v[1].x, v[1].y);
@@ -93,6 +92,7 @@ int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDe
         case PRE_NCHW_F32: preprocess_kernel<PRE_NCHW_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
         case PRE_NHWC4_F32: preprocess_kernel<PRE_NHWC4_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
         case PRE_NHWC4_BF16: preprocess_kernel<PRE_NHWC4_BF16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
+        case PRE_NHWC4_F16: preprocess_kernel<PRE_NHWC4_F16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
         default: ZL_FAIL(ZL_INVALID_ARGUMENT, "bad preprocess layout");
     }
     ZL_CUDA(cudaGetLastError());

@@ -18,7 +18,7 @@ OK, INVALID_ARGUMENT, NOT_INITIALIZED = 0, 2, 3
 INFERENCE_ERROR, MODEL_NOT_FOUND, MODEL_LOAD_FAILED, INVALID_INPUT = 200, 201, 202, 203
 SYSTEM_ERROR, INSUFFICIENT_RESOURCES = 300, 303
 SCALE = {"n": 0, "s": 1, "m": 2}
-FP32, BF16 = 0, 1
+FP32, BF16, FP16 = 0, 1, 2
 
 DET_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("w", "<f4"), ("h", "<f4"),
                       ("confidence", "<f4"), ("class_id", "<i4")])
@@ -282,7 +282,7 @@ class Engine:
         return mf.value, mn.value, kept.value
 
 
-def test_conv(x_nhwc, w_ohwi, bias, stride=1, act=True, res=None, impl=0, device=0, out_f32=False, ntile_hint=0):
+def test_conv(x_nhwc, w_ohwi, bias, stride=1, act=True, res=None, impl=0, device=0, out_f32=False, ntile_hint=0, fp16=False):
     """One conv through the engine's kernels. x: [n,h,w,cin] fp32, w: [cout,k,k,cin] fp32."""
     x = np.ascontiguousarray(x_nhwc, np.float32)
     w = np.ascontiguousarray(w_ohwi, np.float32)
@@ -293,7 +293,7 @@ def test_conv(x_nhwc, w_ohwi, bias, stride=1, act=True, res=None, impl=0, device
     ho, wo = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
     y = np.zeros((n, ho, wo, cout), np.float32)
     r = np.ascontiguousarray(res, np.float32) if res is not None else None
-    flags = (1 if act else 0) | (2 if out_f32 else 0) | (ntile_hint << 8)
+    flags = (1 if act else 0) | (2 if out_f32 else 0) | (4 if fp16 else 0) | (ntile_hint << 8)
     _check(lib().zl_test_conv(device, impl, _ptr(x), n, h, wd, cin, _ptr(w), _ptr(b), cout, k, stride, flags,
                               _ptr(r) if r is not None else None, _ptr(y)))
     return y
