@@ -90,6 +90,23 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def shard_frames(n_total, rank, world):
+    """Frame-sharding rule of the multi-GPU path: frames are independent units, rank r
+    takes the contiguous slice [lo, hi) and never exchanges anything with the other ranks."""
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def reduce_max(value, dist, device="cpu"):
+    """Max over ranks of a per-rank scalar (the only collective in the bench: timing, not data)."""
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def make_inputs(n_sets, seed0=5678):
     from oracle import synth
     return [synth.frames_structured(BATCH, HW, HW, seed=seed0 + s) for s in range(n_sets)]
@@ -174,7 +191,8 @@ def run_ours(args, rank, local_rank, world):
     tensors, blob = make_model()
     n_sets = 4
     sets = make_inputs(n_sets, seed0=5678 + 100 * rank)
-    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=zlb200.BF16, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank)
+    prec = zlb200.FP16 if args.dtype == "fp16" else zlb200.BF16
+    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=prec, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank)
     eng.load_weights_blob(blob)
     eng.warmup(1)
     for s in range(n_sets):
@@ -191,10 +209,7 @@ def run_ours(args, rank, local_rank, world):
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
     barrier()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
+    max_ms = reduce_max(ms, dist, "cuda")
     value = world * BATCH * args.steps / (max_ms / 1e3)
 
     # ---- end to end through the public C-ABI call with pinned HOST frames
@@ -209,10 +224,7 @@ def run_ours(args, rank, local_rank, world):
         dets = eng.infer(pframes)
     e2e_s = time.perf_counter() - t0
     barrier()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_fps = world * BATCH * args.steps / float(t.item())
+    e2e_fps = world * BATCH * args.steps / reduce_max(e2e_s, dist, "cuda")
     n_det = sum(len(d) for d in dets)
     d2h = (4 + 2 * BATCH) * 4 + min(BATCH * 64, BATCH * eng.A) * 24
 
@@ -257,9 +269,11 @@ def run_ours(args, rank, local_rank, world):
     # ---- b=1 416x416 latency (BASELINE configs[1]), CUDA graph, frame in pinned host memory
     latency = None
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         from oracle import synth, yolov8_ref, zlw
         t4 = yolov8_ref.synthetic_model("n", 4, seed=0)
-        e1 = zlb200.Engine(416, 416, 4, "n", precision=zlb200.BF16, max_batch=1, device=local_rank)
+        e1 = zlb200.Engine(416, 416, 4, "n", precision=prec, max_batch=1, device=local_rank)
         e1.load_weights_blob(zlw.dumps(t4, "n", 4))
         e1.warmup(3)
         pf = zlb200.pinned_array((416, 416, 3))
@@ -274,7 +288,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- CPU baseline on the box's host cores (N=1 only): bounded sample of the same workload
     cpu_baseline = None
-    if world == 1:
+    if world == 1 and not args.quick:
         cores = os.cpu_count() or 1
         sample = list(sets[0][:16])
         cpu_pipeline_fps(tensors, sample[:2], cores, 1)
@@ -287,8 +301,8 @@ def run_ours(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "inputs": f"{n_sets} rotating resident input sets of {BATCH} frames ({n_sets * BATCH * HW * HW * 3 / 1e6:.0f} MB > 126 MB L2)",
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": WORKLOAD.replace("bf16", args.dtype), "inputs": f"{n_sets} rotating resident input sets of {BATCH} frames ({n_sets * BATCH * HW * HW * 3 / 1e6:.0f} MB > 126 MB L2)",
                    "frames_per_step_per_gpu": BATCH, "parallelism": f"frame-sharded replicas x{world}, no collective"},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * HW * HW * 3, "d2h_bytes_per_step": d2h,
                 "api": "zl_infer_batch (C-ABI) on pinned host frames, synchronous", "detections_last_step": n_det},
@@ -312,6 +326,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"], help="16-bit tensor-core format (same speed; fp16 meets the IoU>=0.99 parity gate)")
+    ap.add_argument("--quick", action="store_true", help="skip the latency and CPU-baseline legs (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -202,7 +202,7 @@ ZL_API int32_t zl_bench_decode_nms(zl_engine* e, const float* raw, int32_t n, in
 /* One convolution through the engine's conv kernels, host tensors in/out.
  * x: [n,h,w,cin] fp32 NHWC; wgt: [cout,kh,kw,cin] fp32; bias: [cout];
  * res: optional [n,ho,wo,cout]; y: [n,ho,wo,cout] fp32.  impl: 0 = fp32 SIMT,
- * 1 = tcgen05 (A via software gather), 2 = tcgen05 (A via TMA). */
+ * 1 = tcgen05 (A via software gather), 2 = tcgen05 (A via TMA where possible), 3 = persistent halo kernel (3x3 s1). */
 ZL_API int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, int32_t h, int32_t w,
                             int32_t cin, const float* wgt, const float* bias, int32_t cout,
                             int32_t k, int32_t stride, int32_t act, const float* res, float* y);

@@ -115,6 +115,36 @@ def test_conv_tcgen05(built_lib, case, impl):
     assert np.abs(y16 - ref).max() < 1.2e-2 * max(1.0, np.abs(ref).max()), "bf16-out mismatch"
 
 
+HALO_CASES = [
+    # n, h, w, cin, cout, res, fp16, out_f32, ctas (0 = one per SM)
+    (1, 16, 8, 64, 64, False, False, True, 0),      # exactly one tile
+    (2, 80, 80, 64, 64, True, False, False, 0),     # P3 head shape, SW128
+    (1, 40, 40, 32, 32, True, False, True, 0),      # SW64
+    (1, 24, 24, 16, 16, True, False, True, 0),      # SW32
+    (2, 37, 29, 64, 80, False, False, True, 0),     # ragged tiles, Cout 80
+    (1, 52, 52, 80, 80, False, False, True, 0),     # Cin 80 -> five 16-channel chunks
+    (3, 33, 47, 64, 64, True, True, False, 3),      # fp16, 3 persistent CTAs -> many tiles per CTA, both TMEM buffers
+    (2, 64, 64, 32, 48, False, True, True, 5),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo(built_lib, case):
+    import zlb200
+    n, h, w, cin, cout, use_res, fp16, out_f32, ctas = case
+    cvt = _h if fp16 else _bf
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = cvt(rng.normal(size=(n, h, w, cin)).astype(np.float32))
+    wt = cvt((rng.normal(size=(cout, 3, 3, cin)) / np.sqrt(cin * 9)).astype(np.float32))
+    b = rng.normal(size=cout).astype(np.float32)
+    res = cvt(rng.normal(size=(n, h, w, cout)).astype(np.float32)) if use_res else None
+    ref = _torch_conv(x, wt, b, 1, True, res)
+    y = zlb200.test_conv(x, wt, b, stride=1, act=True, res=res, impl=3, out_f32=out_f32, fp16=fp16, ntile_hint=ctas)
+    tol = 2e-3 if (out_f32 or fp16) else 1.2e-2
+    err = np.abs(y - ref)
+    assert err.max() < tol * max(1.0, np.abs(ref).max()), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
 def _h(a):
     return torch.tensor(a).to(torch.float16).to(torch.float32).numpy()
 

@@ -1,0 +1,51 @@
+"""The C++ host adapter (B200InferenceEngine : IInferenceEngine) driven the way the reference server drives its engine."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "zero-latency-yolo_b200", "host")
+EXE = os.path.join(ROOT, "zero-latency-yolo_b200", "lib", "host_test")
+
+
+@pytest.fixture(scope="module")
+def host_exe(built_lib):
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return EXE
+
+
+def test_registry_errors_and_no_fallback(host_exe):
+    out = subprocess.run([host_exe, "cpu"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_test cpu: ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_adapter_end_to_end_matches_c_abi(host_exe, model_n4, tmp_path):
+    import zlb200
+    from oracle import synth
+    tensors, blob = model_n4
+    wpath = tmp_path / "model.zlw"
+    wpath.write_bytes(blob)
+    frames = synth.frames_structured(6, 600, 800, seed=17)           # the reference client's default 800x600 frames
+    fpath = tmp_path / "frames.bin"
+    fpath.write_bytes(frames.tobytes())
+    opath = tmp_path / "dets.bin"
+    out = subprocess.run([host_exe, "gpu", str(wpath), "4", "fp16", str(opath), str(fpath), "6", "800", "600"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP16, max_batch=4, max_frame=(800, 600))
+    e.load_weights_blob(blob)
+    ref = e.infer(list(frames))
+    e.close()
+    raw = opath.read_bytes()
+    off = 0
+    for i in range(6):
+        c = int(np.frombuffer(raw, "<u4", 1, off)[0]); off += 4
+        recs = np.frombuffer(raw, np.uint8, c * 40, off).reshape(c, 40); off += c * 40
+        assert c == len(ref[i])
+        assert np.array_equal(recs[:, :24].reshape(-1), ref[i].view(np.uint8).reshape(-1))   # Detection's first 24 bytes == zl_det
+        assert np.all(recs[:, 24:28] == 0)                                                   # track_id = 0 (onnx_engine.cpp:812)
+    assert sum(len(r) for r in ref) > 5

@@ -327,9 +327,17 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
         if (res) cudaMemcpy(dr, hr.data(), ny * 2, cudaMemcpyHostToDevice);
         cudaMemset(dy, 0xff, ny * (out_f32 ? 4 : 2));
         View vx{dx, n, h, w, cin, cin, dt16}, vy{dy, n, ho, wo, cout, cout, out_f32 ? DT_F32 : dt16}, vr{dr, n, ho, wo, cout, cout, dt16};
-        ConvTcOp op;
-        rc = conv_tc_prepare(cw, vx, vy, res ? &vr : nullptr, impl == 2, hint, &op);
-        if (rc == ZL_OK) rc = conv_tc_launch(st, op);
+        if (impl == 3) {
+            ConvHaloOp hop;
+            cudaDeviceProp prop;
+            cudaGetDeviceProperties(&prop, device);
+            rc = conv_halo_prepare(cw, vx, vy, res ? &vr : nullptr, &hop);
+            if (rc == ZL_OK) rc = conv_halo_launch(st, hop, hint > 0 ? hint : prop.multiProcessorCount);   // hint = CTA count (forces several tiles per CTA)
+        } else {
+            ConvTcOp op;
+            rc = conv_tc_prepare(cw, vx, vy, res ? &vr : nullptr, impl == 2, hint, &op);
+            if (rc == ZL_OK) rc = conv_tc_launch(st, op);
+        }
         if (rc == ZL_OK && cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("conv_tc: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; }
         if (rc == ZL_OK) {
             if (out_f32) cudaMemcpy(y, dy, ny * 4, cudaMemcpyDeviceToHost);

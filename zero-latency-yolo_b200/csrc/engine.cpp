@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_fp16.h>
@@ -83,6 +84,8 @@ int32_t Engine::init()
     cudaDeviceProp prop;
     ZL_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
     if (prop.major != 10) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this build is sm_100a only");
+    num_sms = prop.multiProcessorCount;
+    if (const char* ev = getenv("ZL_DISABLE_HALO")) use_halo = !(ev[0] == '1');
     ZL_TRY(build_model_def());
     num_anchors = 0;
     for (int s : {8, 16, 32}) num_anchors += (cfg.model_h / s) * (cfg.model_w / s);
@@ -369,7 +372,12 @@ int32_t Engine::build_ops(Lane& L, int B)
                    (double)w.cout * w.ktot * (bf16 ? 2 : 4) + (res ? (double)y.pixels() * w.cout * res->esize() : 0.0);
         if (!bf16) op.kind = Op::CONV_SIMT;
         else if (w.cin == 3) op.kind = Op::CONV0;
-        else {
+        else if (use_halo && conv_halo_supported(w, x, y, nullptr) &&
+                 ceil_div(y.w, 8) * ceil_div(y.h, 16) * y.n >= 2 * num_sms) {
+            // big 3x3 stride-1 layers: persistent halo kernel (input read ~1.4x instead of 9x)
+            op.kind = Op::CONV_HALO;
+            rc = conv_halo_prepare(w, x, y, res, &op.halo);
+        } else {
             op.kind = Op::CONV_TC;
             // small problems (latency path): split Cout over more CTAs so more than a handful of SMs work
             int hint = 0;
@@ -468,6 +476,7 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h)
                 ZL_TRY(launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr));
                 break;
             case Op::CONV_TC: ZL_TRY(conv_tc_launch(st, op.tc)); break;
+            case Op::CONV_HALO: ZL_TRY(conv_halo_launch(st, op.halo, num_sms)); break;
             case Op::CONV_SIMT: ZL_TRY(launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr)); break;
             case Op::CONV0: ZL_TRY(launch_conv0_direct(st, *op.w, op.x, op.y)); break;
             case Op::POOL: ZL_TRY(launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3)); break;
@@ -809,6 +818,7 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
             switch (op.kind) {
                 case Op::PRE: rc = launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr); break;
                 case Op::CONV_TC: rc = conv_tc_launch(st, op.tc); break;
+                case Op::CONV_HALO: rc = conv_halo_launch(st, op.halo, num_sms); break;
                 case Op::CONV_SIMT: rc = launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr); break;
                 case Op::CONV0: rc = launch_conv0_direct(st, *op.w, op.x, op.y); break;
                 case Op::POOL: rc = launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3); break;

@@ -34,11 +34,12 @@ struct ModelDef {
 };
 
 struct Op {
-    enum Kind : int32_t { PRE = 0, CONV_TC = 1, CONV_SIMT = 2, CONV0 = 3, POOL = 4, UPSAMPLE = 5, DECODE = 6, FILTER = 7, NMS = 8 };
+    enum Kind : int32_t { PRE = 0, CONV_TC = 1, CONV_SIMT = 2, CONV0 = 3, POOL = 4, UPSAMPLE = 5, DECODE = 6, FILTER = 7, NMS = 8, CONV_HALO = 9 };
     int32_t kind = PRE;
     std::string name;
     const ConvWeights* w = nullptr;
     ConvTcOp tc;
+    ConvHaloOp halo;
     View x, y, res, p1, p2, p3;
     bool has_res = false;
     double flops = 0, bytes = 0;
@@ -108,6 +109,8 @@ public:
     zl_result_fn cb = nullptr;
     void* cb_user = nullptr;
     int num_anchors = 0;
+    int num_sms = 148;
+    bool use_halo = true;
     bool weights_loaded = false;
 
 private:

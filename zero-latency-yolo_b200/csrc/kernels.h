@@ -58,6 +58,26 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
                         bool allow_tma_a, int32_t ntile_hint, ConvTcOp* op);
 int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& op);
 
+// Persistent 3x3 stride-1 conv with halo reuse (conv_halo.cu): weights resident in smem, one TMA patch
+// load per tile and channel chunk, nine shifted UMMA views of the same patch.
+struct ConvHaloOp {
+    CUtensorMap tmap_w;
+    CUtensorMap tmap_x;
+    void* y;
+    const __nv_bfloat16* res;
+    const float* bias;
+    int32_t N, H, W, Cin, Cout, ntile;
+    int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
+    int32_t kc, cchunks, stages;
+    int32_t tiles_x, tiles_y, num_tiles;
+    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, tmem_cols;
+    int32_t smem_bytes;
+    double flops, bytes;
+};
+bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int* smem_out);
+int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, ConvHaloOp* op);
+int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms);
+
 // ---------------------------------------------------------------- pool / upsample
 // SPPF: p1 = max5(a), p2 = max5(p1) = max9(a), p3 = max13(a) in one pass.
 int32_t launch_sppf_pool(cudaStream_t st, const View& a, const View& p1, const View& p2, const View& p3);
