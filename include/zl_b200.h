@@ -207,6 +207,11 @@ ZL_API int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_
                             int32_t cin, const float* wgt, const float* bias, int32_t cout,
                             int32_t k, int32_t stride, int32_t act, const float* res, float* y);
 
+/* Measurement hook: cycles for `count` tcgen05.mma (M=128) of width N with the given swizzle / group stride /
+ * accumulator rotation; sizes the conv tiles (DESIGN.md "UMMA probe"). */
+ZL_API int32_t zl_probe_umma(int32_t device, int32_t N, int32_t swz, int32_t sbo_a, int32_t nacc, int32_t count,
+                             int32_t shift_rows, int32_t ksteps, int32_t grid, int64_t* issue_cycles, int64_t* total_cycles);
+
 /* ---- host memory + errors ---- */
 ZL_API void*   zl_host_alloc(size_t bytes);   /* pinned */
 ZL_API void    zl_host_free(void* p);

@@ -125,6 +125,8 @@ HALO_CASES = [
     (1, 52, 52, 80, 80, False, False, True, 0),     # Cin 80 -> five 16-channel chunks
     (3, 33, 47, 64, 64, True, True, False, 3),      # fp16, 3 persistent CTAs -> many tiles per CTA, both TMEM buffers
     (2, 64, 64, 32, 48, False, True, True, 5),
+    (1, 160, 40, 16, 16, True, True, False, 0),     # four stacked sub-tiles per tile
+    (2, 70, 30, 32, 32, True, False, True, 2),      # two sub-tiles, ragged in both directions
 ]
 
 

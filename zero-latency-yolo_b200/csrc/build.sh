@@ -6,7 +6,7 @@ OUT=../lib
 mkdir -p "$OUT" .obj
 NVCC=${NVCC:-nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xcompiler -Wall)
-SRCS=(conv_tc.cu conv_halo.cu conv_simt.cu preprocess.cu pool_upsample.cu postprocess.cu engine.cpp capi.cpp)
+SRCS=(conv_tc.cu conv_halo.cu umma_probe.cu conv_simt.cu preprocess.cu pool_upsample.cu postprocess.cu engine.cpp capi.cpp)
 pids=()
 for s in "${SRCS[@]}"; do
   o=.obj/${s%.*}.o

@@ -373,7 +373,7 @@ int32_t Engine::build_ops(Lane& L, int B)
         if (!bf16) op.kind = Op::CONV_SIMT;
         else if (w.cin == 3) op.kind = Op::CONV0;
         else if (use_halo && conv_halo_supported(w, x, y, nullptr) &&
-                 ceil_div(y.w, 8) * ceil_div(y.h, 16) * y.n >= 2 * num_sms) {
+                 ceil_div(y.w, 8) * ceil_div(y.h, 16) * y.n >= 4 * num_sms) {
             // big 3x3 stride-1 layers: persistent halo kernel (input read ~1.4x instead of 9x)
             op.kind = Op::CONV_HALO;
             rc = conv_halo_prepare(w, x, y, res, &op.halo);
@@ -798,6 +798,7 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
     if (n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident set not uploaded");
     const int B = graph_batch_for(n);
     if (!L.ops.count(B)) ZL_TRY(build_ops(L, B));
+    ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)set * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
     ZL_TRY(run_ops(L, B, false));                         // warm
     ZL_CUDA(cudaStreamSynchronize(L.stream));
     const std::vector<Op>& ops = L.ops[B];

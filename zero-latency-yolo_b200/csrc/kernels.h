@@ -63,12 +63,13 @@ int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& op);
 struct ConvHaloOp {
     CUtensorMap tmap_w;
     CUtensorMap tmap_x;
+    CUtensorMap tmap_y;
     void* y;
     const __nv_bfloat16* res;
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
-    int32_t kc, cchunks, stages;
+    int32_t kc, cchunks, stages, sub, y_tma;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, tmem_cols;
     int32_t smem_bytes;

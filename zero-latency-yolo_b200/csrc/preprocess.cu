@@ -33,6 +33,7 @@ preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restri
     const int y = item / wq;
     const int x0 = (item - y * wq) * 4;
     const FrameDesc d = descs[f];
+    if (d.w <= 0 || d.h <= 0) return;                 // unused batch slot
     const uint8_t* __restrict__ img = staging + d.offset;
     const float scale_w = __fdiv_rn((float)d.w, (float)mw);
     const float scale_h = __fdiv_rn((float)d.h, (float)mh);

@@ -111,6 +111,18 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
         : "memory");
 }
 
+// smem -> global tensor store (bulk async group); OOB elements of the box are clipped by the hardware.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Descriptor with an explicit stride between 8-row groups (halo kernel: groups are rows of a wider patch).
 __device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t addr, uint32_t swz_bytes, uint32_t sbo_bytes) {
     const uint64_t layout = swz_bytes == 128 ? 2ull : (swz_bytes == 64 ? 4ull : 6ull);

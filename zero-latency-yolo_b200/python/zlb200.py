@@ -56,7 +56,7 @@ EXPORTS = [
     "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
     "zl_engine_run_resident", "zl_engine_profile", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
-    "zl_test_conv", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
+    "zl_test_conv", "zl_probe_umma", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
             "zl_bench_preprocess": (i32, [vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(C.c_double)]),
             "zl_bench_decode_nms": (i32, [vp, vp, i32, i32, i32, f32, f32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int64)]),
             "zl_test_conv": (i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
+            "zl_probe_umma": (i32, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "zl_host_alloc": (vp, [sz]),
             "zl_host_free": (None, [vp]),
             "zl_last_error": (C.c_char_p, []),
@@ -297,3 +298,9 @@ def test_conv(x_nhwc, w_ohwi, bias, stride=1, act=True, res=None, impl=0, device
     _check(lib().zl_test_conv(device, impl, _ptr(x), n, h, wd, cin, _ptr(w), _ptr(b), cout, k, stride, flags,
                               _ptr(r) if r is not None else None, _ptr(y)))
     return y
+
+
+def probe_umma(N, swz=128, sbo=None, nacc=1, count=512, shift_rows=0, ksteps=4, grid=1, device=0):
+    a, b = C.c_int64(), C.c_int64()
+    _check(lib().zl_probe_umma(device, N, swz, sbo if sbo is not None else 8 * swz, nacc, count, shift_rows, ksteps, grid, C.byref(a), C.byref(b)))
+    return a.value / count, b.value / count
