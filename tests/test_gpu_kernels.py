@@ -147,6 +147,36 @@ def test_conv_halo(built_lib, case):
     assert err.max() < tol * max(1.0, np.abs(ref).max()), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
 
 
+PERSIST_1X1_CASES = [
+    # n, h, w, cin, cout, fp16, out_f32, ctas
+    (1, 16, 8, 64, 64, False, True, 0),       # one tile
+    (2, 80, 80, 32, 32, False, False, 0),     # sub = 2
+    (1, 160, 160, 48, 32, True, False, 0),    # Cin 48 -> three 16-channel chunks (layer 2 cv2)
+    (2, 40, 40, 384, 128, True, False, 0),    # six 64-channel chunks (layer 12 cv1)
+    (1, 20, 20, 256, 256, False, False, 4),   # N = 256: both accumulators fill TMEM
+    (4, 20, 20, 128, 64, True, True, 3),      # fp32 output (direct store path)
+    (1, 52, 52, 64, 80, False, True, 0),      # Cout 80
+    (4, 26, 26, 192, 128, True, False, 7),
+    (1, 24, 24, 16, 16, True, False, 0),      # sub = 4 (36 rows of 8)
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_1X1_CASES)
+def test_conv_persistent_1x1(built_lib, case):
+    import zlb200
+    n, h, w, cin, cout, fp16, out_f32, ctas = case
+    cvt = _h if fp16 else _bf
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = cvt(rng.normal(size=(n, h, w, cin)).astype(np.float32))
+    wt = cvt((rng.normal(size=(cout, 1, 1, cin)) / np.sqrt(cin)).astype(np.float32))
+    b = rng.normal(size=cout).astype(np.float32)
+    ref = _torch_conv(x, wt, b, 1, True, None)
+    y = zlb200.test_conv(x, wt, b, stride=1, act=True, impl=3, out_f32=out_f32, fp16=fp16, ntile_hint=ctas)
+    tol = 2e-3 if (out_f32 or fp16) else 1.2e-2
+    err = np.abs(y - ref)
+    assert err.max() < tol * max(1.0, np.abs(ref).max()), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
 def _h(a):
     return torch.tensor(a).to(torch.float16).to(torch.float32).numpy()
 

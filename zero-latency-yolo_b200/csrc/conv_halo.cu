@@ -31,7 +31,9 @@ namespace {
 using namespace tc;
 
 constexpr int kTW = 8, kTH = 16;            // one MMA sub-tile: 8 (w) x 16 (h) output pixels = 128 GEMM rows
-constexpr int kPW = kTW + 2;                 // patch width; patch height = 16*sub + 2
+// TAPS == 9: 3x3 conv, patch = tile + 1-pixel halo (width 10, height 16*sub + 2)
+// TAPS == 1: 1x1 conv, patch = tile (width 8, height 16*sub); the pixel list is viewed as an 8-wide image
+template <int TAPS> struct Geo { static constexpr int PW = TAPS == 9 ? kTW + 2 : kTW, HALO = TAPS == 9 ? 1 : 0; };
 constexpr int kEpiWarps = 16;                // 4 per TMEM lane quarter, each owning a share of the accumulator columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxPatchStages = 12;
@@ -51,14 +53,15 @@ struct HaloParams {
 // Measured on B200 (umma_probe.cu): a tcgen05.mma with N <= 64 occupies the tensor pipe for ~48 cycles, so
 // the single issuing thread must spend far less than that per instruction: both descriptors are the
 // stage's base descriptor plus a compile-time constant in the 14-bit address field.
-template <int KSTEPS, int SUB>
+template <int KSTEPS, int SUB, int TAPS>
 __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uint64_t adesc0, uint64_t bdesc0, uint32_t wtile16,
                                             uint32_t btap_stride16, uint32_t idesc, bool first_chunk)
 {
     constexpr uint32_t swz16 = (uint32_t)KSTEPS * 2u;        // bytes per pixel row / 16
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t aoff = (uint32_t)((tap / 3) * kPW + (tap % 3)) * swz16;
+    constexpr int kPW = Geo<TAPS>::PW;
+    for (int tap = 0; tap < TAPS; ++tap) {
+        const uint32_t aoff = TAPS == 9 ? (uint32_t)((tap / 3) * kPW + (tap % 3)) * swz16 : 0u;
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)tap * btap_stride16);
         (void)wtile16;
 #pragma unroll
@@ -72,11 +75,13 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
     }
 }
 
+template <int TAPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const __grid_constant__ CUtensorMap tmap_y, const HaloParams p)
 {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int kPW = Geo<TAPS>::PW, kHalo = Geo<TAPS>::HALO;
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
 
@@ -87,9 +92,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const uint32_t bar_tfull = bar_wfull + 8u;                     // 2 x 8
     const uint32_t bar_tempty = bar_tfull + 16u;                   // 2 x 8
     const uint32_t tmem_slot = bar_tempty + 16u;
-    const uint32_t bias_off = 512u;                                // fp32 bias[ntile <= 128] in the second half of the block
-    const uint32_t wbase = base + 1024u;
-    const uint32_t nwt = 9u * (uint32_t)p.cchunks;
+    const uint32_t bias_off = 1024u;                               // fp32 bias[ntile <= 256] in its own 1 KB block
+    const uint32_t wbase = base + 2048u;
+    const uint32_t nwt = (uint32_t)TAPS * (uint32_t)p.cchunks;
     const uint32_t pbase = wbase + nwt * p.wtile_alloc;
     const uint32_t obase = pbase + (uint32_t)p.stages * p.patch_alloc;    // per-epilogue-warp output staging: 2 x 1 KB each
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -139,7 +144,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     mbar_wait(bar_pempty + 8u * s, ph ^ 1u);
                     mbar_arrive_expect_tx(bar_pfull + 8u * s, p.patch_bytes);
-                    tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc, cc * p.kc, tx * kTW - 1, ty * kTH * p.sub - 1, n);
+                    tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -173,15 +178,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     const uint32_t nt = (uint32_t)p.ntile;
                     const bool first = cc == 0;
                     switch (sel) {
-                        case 0: issue_chunk<4, 1>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 1: issue_chunk<4, 2>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 2: issue_chunk<4, 4>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 3: issue_chunk<2, 1>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 4: issue_chunk<2, 2>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 5: issue_chunk<2, 4>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 6: issue_chunk<1, 1>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 7: issue_chunk<1, 2>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        default: issue_chunk<1, 4>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 0: issue_chunk<4, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 1: issue_chunk<4, 2, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 2: issue_chunk<4, 4, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 3: issue_chunk<2, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 4: issue_chunk<2, 2, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 5: issue_chunk<2, 4, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 6: issue_chunk<1, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 7: issue_chunk<1, 2, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        default: issue_chunk<1, 4, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
                     }
                     umma_commit(bar_pempty + 8u * s);
                     if (cc == p.cchunks - 1) umma_commit(bar_tfull + 8u * acc);
@@ -336,7 +341,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f16, int patch_h)
+int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f16, int patch_w, int patch_h)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -348,7 +353,7 @@ int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f1
     }
     cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
     cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.w * x.pitch * 2, (cuuint64_t)x.h * x.w * x.pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kPW, (cuuint32_t)patch_h, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)patch_w, (cuuint32_t)patch_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x.ptr, dims, strides, box, estr,
@@ -382,34 +387,52 @@ int32_t make_tmap_out(CUtensorMap* map, const View& y, bool f16)
 
 }  // namespace
 
-// Sub-tiles per tile: small-Cout layers stack several 8x16 sub-tiles along h so one barrier round trip,
-// one patch and one epilogue pass cover more pixels (accumulator columns: sub * Cout_pad <= 128).
-static int halo_sub(const ConvWeights& w, const View& x)
+// Sub-tiles per tile: narrow layers stack several 8x16 sub-tiles along h so one barrier round trip, one
+// patch and one epilogue pass cover more pixels.  An MMA with N <= 64 costs ~48 tensor-pipe cycles whatever
+// N is (umma_probe), so stacking only pays for per-tile overheads; wide layers keep one sub-tile.
+static int halo_sub(const ConvWeights& w, int rows)
 {
-    // an MMA with N <= 64 costs ~48 tensor-pipe cycles whatever N is (umma_probe), so stacking only pays
-    // for the per-tile overheads of the narrow layers; wide layers keep one sub-tile (no wasted rows)
     int sub = w.cout_pad <= 16 ? 4 : (w.cout_pad <= 32 ? 2 : 1);
-    while (sub > 1 && kTH * sub > round_up(x.h, kTH)) --sub;     // do not make tiles taller than the image
+    while (sub > 1 && kTH * sub > round_up(rows, kTH)) --sub;     // do not make tiles taller than the image
     return sub;
+}
+
+// 1x1 convs see their input as an 8-pixel-wide image of the flattened pixel list, so a tile is 128*sub
+// consecutive pixels and no rows are wasted on small maps.
+static bool persist_views(const ConvWeights& w, const View& x, const View& y, View* xv, View* yv)
+{
+    *xv = x; *yv = y;
+    if (w.k == 3) return true;
+    const size_t m = x.pixels();
+    if (m % 8 != 0) return false;
+    xv->n = 1; xv->w = 8; xv->h = (int32_t)(m / 8);
+    yv->n = 1; yv->w = 8; yv->h = (int32_t)(m / 8);
+    return true;
 }
 
 bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int* smem_out)
 {
-    if (w.k != 3 || w.stride != 1 || !x.is16() || (w.cin % 16) != 0 || w.cout_pad > 128) return false;
+    if (!((w.k == 3 || w.k == 1) && w.stride == 1) || !x.is16() || (w.cin % 16) != 0 || w.cout_pad > 256) return false;
     if ((x.pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(x.ptr) & 15)) return false;
     if (y.is16() && y.dtype != x.dtype) return false;
+    View xv, yv;
+    if (!persist_views(w, x, y, &xv, &yv)) return false;
+    const int taps = w.k * w.k, pw = w.k == 3 ? kTW + 2 : kTW, halo2 = w.k == 3 ? 2 : 0;
     const int kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
     const int cchunks = w.cin / kc;
-    const int sub = halo_sub(w, x);
+    const int sub = halo_sub(w, xv.h);
+    if (2 * sub * w.cout_pad > 512) return false;                 // two accumulator buffers must fit TMEM
     const uint32_t wtile_alloc = ((uint32_t)w.cout_pad * kc * 2 + 1023u) & ~1023u;
-    const uint32_t patch_alloc = ((uint32_t)kPW * (kTH * sub + 2) * kc * 2 + 1023u) & ~1023u;
-    const uint32_t fixed = 2048u + 9u * cchunks * wtile_alloc + (uint32_t)kEpiWarps * 2048u;   // barriers + weights + output staging
+    const uint32_t patch_alloc = ((uint32_t)pw * (kTH * sub + halo2) * kc * 2 + 1023u) & ~1023u;
+    const uint32_t fixed = 3072u + (uint32_t)taps * cchunks * wtile_alloc + (uint32_t)kEpiWarps * 2048u;   // barriers + bias + weights + output staging
     const uint32_t budget = 227u * 1024u;
-    if (fixed + (uint32_t)(cchunks + 1) * patch_alloc > budget) return false;      // need more than one tile's patches in flight
+    const int min_stages = cchunks + 1 < 3 ? cchunks + 1 : 3;
+    if (fixed + (uint32_t)min_stages * patch_alloc > budget) return false;
     if (smem_out) {
         int stages = (int)((budget - fixed) / patch_alloc);
         if (stages > kMaxPatchStages) stages = kMaxPatchStages;
         if (stages > 3 * cchunks) stages = 3 * cchunks;
+        if (stages < 2) stages = 2;
         *smem_out = (int)(fixed + (uint32_t)stages * patch_alloc);
     }
     return true;
@@ -418,14 +441,18 @@ bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int
 int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, ConvHaloOp* op)
 {
     int smem = 0;
-    if (!conv_halo_supported(w, x, y, &smem)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_halo: layer not supported (" + w.name + ")");
-    if (y.h != x.h || y.w != x.w || y.n != x.n || y.c != w.cout || x.c != w.cin) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_halo: view mismatch (" + w.name + ")");
-    if (res && (res->dtype != x.dtype || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_halo: residual view mismatch");
+    if (!conv_halo_supported(w, x, y, &smem)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: layer not supported (" + w.name + ")");
+    if (y.h != x.h || y.w != x.w || y.n != x.n || y.c != w.cout || x.c != w.cin) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: view mismatch (" + w.name + ")");
+    if (res && (res->dtype != x.dtype || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: residual view mismatch");
+    View xv, yv;
+    persist_views(w, x, y, &xv, &yv);
+    const int pw = w.k == 3 ? kTW + 2 : kTW, halo2 = w.k == 3 ? 2 : 0;
     ConvHaloOp& o = *op;
+    o.taps = w.k * w.k;
     o.y = y.ptr;
     o.res = res ? reinterpret_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
     o.bias = w.bias;
-    o.N = x.n; o.H = x.h; o.W = x.w; o.Cin = w.cin; o.Cout = w.cout; o.ntile = w.cout_pad;
+    o.N = xv.n; o.H = xv.h; o.W = xv.w; o.Cin = w.cin; o.Cout = w.cout; o.ntile = w.cout_pad;
     o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
     o.f16 = x.dtype == DT_F16 ? 1 : 0;
@@ -434,22 +461,22 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
     o.kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
     o.cchunks = w.cin / o.kc;
-    o.sub = halo_sub(w, x);
-    o.tiles_x = ceil_div(x.w, kTW); o.tiles_y = ceil_div(x.h, kTH * o.sub);
-    o.num_tiles = o.tiles_x * o.tiles_y * x.n;
+    o.sub = halo_sub(w, xv.h);
+    o.tiles_x = ceil_div(xv.w, kTW); o.tiles_y = ceil_div(xv.h, kTH * o.sub);
+    o.num_tiles = o.tiles_x * o.tiles_y * xv.n;
     o.wtile_bytes = (uint32_t)w.cout_pad * o.kc * 2;
     o.wtile_alloc = (o.wtile_bytes + 1023u) & ~1023u;
-    o.patch_bytes = (uint32_t)kPW * (kTH * o.sub + 2) * o.kc * 2;
+    o.patch_bytes = (uint32_t)pw * (kTH * o.sub + halo2) * o.kc * 2;
     o.patch_alloc = (o.patch_bytes + 1023u) & ~1023u;
     o.smem_bytes = smem;
-    o.stages = (int)((smem - 2048 - kEpiWarps * 2048 - 9 * o.cchunks * (int)o.wtile_alloc) / (int)o.patch_alloc);
+    o.stages = (int)((smem - 3072 - kEpiWarps * 2048 - o.taps * o.cchunks * (int)o.wtile_alloc) / (int)o.patch_alloc);
     int cols = 32;
     while (cols < 2 * o.sub * w.cout_pad) cols <<= 1;
     o.tmem_cols = cols;
     ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, w.cout_pad, o.kc * 2, o.f16));
-    ZL_TRY(make_tmap_nhwc(&o.tmap_x, x, o.kc, o.kc * 2, o.f16, kTH * o.sub + 2));
+    ZL_TRY(make_tmap_nhwc(&o.tmap_x, xv, o.kc, o.kc * 2, o.f16, pw, kTH * o.sub + halo2));
     o.y_tma = (y.is16() && (y.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
-    if (o.y_tma) ZL_TRY(make_tmap_out(&o.tmap_y, y, o.f16)); else o.tmap_y = o.tmap_x;
+    if (o.y_tma) ZL_TRY(make_tmap_out(&o.tmap_y, yv, o.f16)); else o.tmap_y = o.tmap_x;
     o.flops = 2.0 * (double)y.pixels() * w.cout * w.ktot;
     o.bytes = (double)x.pixels() * w.cin * 2 + (double)y.pixels() * w.cout * (o.y_f32 ? 4 : 2) + (double)w.cout * w.ktot * 2 +
               (res ? (double)y.pixels() * w.cout * 2 : 0.0);
@@ -462,7 +489,8 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != last_dev) {
-        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         last_dev = dev;
     }
     HaloParams p;
@@ -474,7 +502,8 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc;
     p.tmem_cols = o.tmem_cols;
     const int grid = o.num_tiles < num_sms ? o.num_tiles : num_sms;
-    conv_halo_kernel<<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
+    if (o.taps == 9) conv_halo_kernel<9><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
+    else conv_halo_kernel<1><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }

@@ -373,7 +373,7 @@ int32_t Engine::build_ops(Lane& L, int B)
         if (!bf16) op.kind = Op::CONV_SIMT;
         else if (w.cin == 3) op.kind = Op::CONV0;
         else if (use_halo && conv_halo_supported(w, x, y, nullptr) &&
-                 ceil_div(y.w, 8) * ceil_div(y.h, 16) * y.n >= 4 * num_sms) {
+                 (w.k == 3 ? ceil_div(y.w, 8) * ceil_div(y.h, 16) * y.n : (int)(y.pixels() / 128)) >= 4 * num_sms) {
             // big 3x3 stride-1 layers: persistent halo kernel (input read ~1.4x instead of 9x)
             op.kind = Op::CONV_HALO;
             rc = conv_halo_prepare(w, x, y, res, &op.halo);
