@@ -126,6 +126,10 @@ HALO_CASES = [
     (3, 33, 47, 64, 64, True, True, False, 3),      # fp16, 3 persistent CTAs -> many tiles per CTA, both TMEM buffers
     (2, 64, 64, 32, 48, False, True, True, 5),
     (1, 160, 40, 16, 16, True, True, False, 0),     # four stacked sub-tiles per tile
+    (8, 20, 20, 128, 128, True, True, False, 0),    # weights do not fit: Cout split over CTAs (N-split)
+    (4, 20, 20, 256, 64, False, False, True, 0),    # N-split, four 64-channel chunks
+    (4, 40, 40, 128, 80, False, True, False, 0),    # uneven N-split (48 + 32)
+    (2, 20, 20, 256, 80, False, True, True, 12),    # N-split with few CTAs
     (2, 70, 30, 32, 32, True, False, True, 2),      # two sub-tiles, ragged in both directions
 ]
 
@@ -158,6 +162,8 @@ PERSIST_1X1_CASES = [
     (1, 52, 52, 64, 80, False, True, 0),      # Cout 80
     (4, 26, 26, 192, 128, True, False, 7),
     (1, 24, 24, 16, 16, True, False, 0),      # sub = 4 (36 rows of 8)
+    (8, 20, 20, 384, 256, True, False, 0),    # weights 196 KB: N-split
+    (2, 20, 20, 512, 256, False, False, 0),   # SPPF cv2 shape
 ]
 
 

@@ -269,7 +269,7 @@ static inline uint16_t f2bf_host(float f) {
 }
 static inline float bf2f_host(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; std::memcpy(&f, &u, 4); return f; }
 static inline uint16_t f2h_host(float f) { const __half h = __float2half_rn(f); uint16_t u; std::memcpy(&u, &h, 2); return u; }
-static inline float h2f_host(uint16_t v) { __half h; std::memcpy(&h, &v, 2); return __half2float(h); }
+static inline float h2f_host(uint16_t v) { const __half_raw r{v}; return __half2float(__half(r)); }
 
 int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, int32_t h, int32_t w, int32_t cin,
                      const float* wgt, const float* bias, int32_t cout, int32_t k, int32_t stride, int32_t act_flags,
@@ -331,7 +331,7 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
             ConvHaloOp hop;
             cudaDeviceProp prop;
             cudaGetDeviceProperties(&prop, device);
-            rc = conv_halo_prepare(cw, vx, vy, res ? &vr : nullptr, &hop);
+            rc = conv_halo_prepare(cw, vx, vy, res ? &vr : nullptr, hint > 0 ? hint : prop.multiProcessorCount, &hop);
             if (rc == ZL_OK) rc = conv_halo_launch(st, hop, hint > 0 ? hint : prop.multiProcessorCount);   // hint = CTA count (forces several tiles per CTA)
         } else {
             ConvTcOp op;

@@ -44,7 +44,7 @@ struct HaloParams {
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
-    int32_t kc, cchunks, stages, sub, y_tma;
+    int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, tmem_cols;
 };
@@ -58,8 +58,8 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
                                             uint32_t btap_stride16, uint32_t idesc, bool first_chunk)
 {
     constexpr uint32_t swz16 = (uint32_t)KSTEPS * 2u;        // bytes per pixel row / 16
-#pragma unroll
     constexpr int kPW = Geo<TAPS>::PW;
+#pragma unroll
     for (int tap = 0; tap < TAPS; ++tap) {
         const uint32_t aoff = TAPS == 9 ? (uint32_t)((tap / 3) * kPW + (tap % 3)) * swz16 : 0u;
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)tap * btap_stride16);
@@ -99,6 +99,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const uint32_t obase = pbase + (uint32_t)p.stages * p.patch_alloc;    // per-epilogue-warp output staging: 2 x 1 KB each
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int stages = p.stages;
+    // N-split: CTA c owns output-channel slice (c % nsplit) for good, so its weight slice stays resident
+    const int slice = (int)blockIdx.x % p.nsplit;
+    const int n_off = slice * p.nt;
+    const int ntile = min(p.nt, p.ntile - n_off);            // this CTA's UMMA N (multiple of 16)
+    const int cout_l = p.Cout - n_off;                       // valid output channels left in this slice (may be <= 0)
+    const int tile0 = (int)blockIdx.x / p.nsplit, tile_step = (int)gridDim.x / p.nsplit;
+    const float* bias_g = p.bias + n_off;
+    const size_t esz_y = p.y_f32 ? 4 : 2;
+    void* y_g = reinterpret_cast<char*>(p.y) + (size_t)n_off * esz_y;
+    const __nv_bfloat16* res_g = p.res ? p.res + n_off : nullptr;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -120,7 +130,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         tmem_relinquish();
     }
     float* bias_s = reinterpret_cast<float*>(smem_raw + (base + bias_off - smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < p.ntile; i += kThreads) bias_s[i] = p.bias[i];
+    for (int i = threadIdx.x; i < ntile; i += kThreads) bias_s[i] = bias_g[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -134,10 +144,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             mbar_arrive_expect_tx(bar_wfull, nwt * p.wtile_bytes);
             for (uint32_t t = 0; t < nwt; ++t) {
                 const int tap = (int)t / p.cchunks, cc = (int)t - tap * p.cchunks;
-                tma_load_2d(&tmap_w, bar_wfull, wbase + t * p.wtile_alloc, tap * p.Cin + cc * p.kc, 0);
+                tma_load_2d(&tmap_w, bar_wfull, wbase + t * p.wtile_alloc, tap * p.Cin + cc * p.kc, n_off);
             }
             uint32_t s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 const int n = tile / tiles_per_img;
                 const int rem = tile - n * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -153,7 +163,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         // ===== MMA issuer =====
         const uint32_t swz = (uint32_t)p.kc * 2u;
         const uint32_t fmt = p.f16 ? 0u : 1u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int ksteps = p.kc / 16;
         const uint32_t sbo_a = (uint32_t)kPW * swz;          // one tile row (8 pixels) per 8-row group, groups strided by the patch row
         mbar_wait(bar_wfull, 0u);
@@ -164,7 +174,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const uint32_t patch16 = p.patch_alloc >> 4, wtile16 = p.wtile_alloc >> 4;
         const uint32_t btap16 = wtile16 * (uint32_t)p.cchunks;               // weight tiles are laid out [tap][chunk]
         const int sel = (ksteps == 4 ? 0 : (ksteps == 2 ? 3 : 6)) + (p.sub == 1 ? 0 : (p.sub == 2 ? 1 : 2));
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+        for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             mbar_wait(bar_tempty + 8u * acc, aph ^ 1u);       // epilogue has drained this accumulator
             tc_fence_after();
@@ -175,7 +185,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 if (lane == 0) {
                     const uint64_t ad = adesc_base + (uint64_t)(s * patch16);
                     const uint64_t bd = bdesc_base + (uint64_t)((uint32_t)cc * wtile16);
-                    const uint32_t nt = (uint32_t)p.ntile;
+                    const uint32_t nt = (uint32_t)p.nt;                 // accumulator column stride between sub-tiles
                     const bool first = cc == 0;
                     switch (sel) {
                         case 0: issue_chunk<4, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
@@ -201,12 +211,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int cgp = (int)(warp - 2u) >> 2;               // which share of the (sub-tile, 16-column) work items
         const int row = (int)(q * 32u + lane);               // A row == TMEM lane: h = row / 8, w = row % 8
         const int th = row >> 3, tw = row & 7;
-        const int nchunk = p.ntile >> 4;
+        const int nchunk = ntile >> 4;
         const int items = p.sub * nchunk;
         const uint32_t stage_out = obase + (warp - 2u) * 2048u;     // this warp's two 1 KB staging blocks ([32 px][16 ch], 32-B swizzle)
         uint32_t nstore = 0;
         uint32_t tl = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tl) {
+        for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             const int n = tile / tiles_per_img;
             const int rem = tile - n * tiles_per_img;
@@ -218,7 +228,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             for (int item = cgp; item < items; item += kEpiWarps / 4) {
                 const int j = item / nchunk, c0 = (item - j * nchunk) << 4;
                 uint32_t v[16];
-                tmem_ld16(taddr + (uint32_t)(j * p.ntile + c0), v);
+                tmem_ld16(taddr + (uint32_t)(j * p.nt + c0), v);
                 tmem_ld_wait();
                 const int oy = (ty * p.sub + j) * kTH + th;
                 if (p.y_tma) {
@@ -234,9 +244,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 #pragma unroll
                         for (int i = 0; i < 16; ++i) a[i] = __fdividef(a[i], 1.0f + __expf(-a[i]));
                     }
-                    if (p.res != nullptr && oy < p.H && ox < p.W && c0 < p.Cout) {
-                        const __nv_bfloat16* rp = p.res + (((size_t)n * p.H + oy) * p.W + ox) * p.rpitch + c0;
-                        if (c0 + 16 <= p.Cout && p.r_vec) {
+                    if (res_g != nullptr && oy < p.H && ox < p.W && c0 < cout_l) {
+                        const __nv_bfloat16* rp = res_g + (((size_t)n * p.H + oy) * p.W + ox) * p.rpitch + c0;
+                        if (c0 + 16 <= cout_l && p.r_vec) {
                             const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
                             const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
                             const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -248,7 +258,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                                 a[2 * i + 1] += rb;
                             }
                         } else {
-                            for (int i = 0; i < 16 && c0 + i < p.Cout; ++i) a[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
+                            for (int i = 0; i < 16 && c0 + i < cout_l; ++i) a[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
                         }
                     }
                     uint32_t w[8];
@@ -263,13 +273,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&tmap_y, sbuf, c0, tx * kTW, (ty * p.sub + j) * kTH + (int)q * 4, n);
+                        tma_store_4d(&tmap_y, sbuf, n_off + c0, tx * kTW, (ty * p.sub + j) * kTH + (int)q * 4, n);
                         tma_store_commit();
                     }
                     ++nstore;
                     continue;
                 }
-                if (oy >= p.H || ox >= p.W || c0 >= p.Cout) continue;
+                if (oy >= p.H || ox >= p.W || c0 >= cout_l) continue;
                 const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
                 float f[16];
 #pragma unroll
@@ -284,9 +294,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 16; ++i) f[i] = __fdividef(f[i], 1.0f + __expf(-f[i]));
                 }
-                const bool full = (c0 + 16 <= p.Cout);
-                if (p.res != nullptr) {
-                    const __nv_bfloat16* rp = p.res + m * p.rpitch + c0;
+                const bool full = (c0 + 16 <= cout_l);
+                if (res_g != nullptr) {
+                    const __nv_bfloat16* rp = res_g + m * p.rpitch + c0;
                     if (full && p.r_vec) {
                         const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
                         const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
@@ -299,20 +309,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                             f[2 * i + 1] += b;
                         }
                     } else {
-                        for (int i = 0; i < 16 && c0 + i < p.Cout; ++i) f[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
+                        for (int i = 0; i < 16 && c0 + i < cout_l; ++i) f[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
                     }
                 }
                 if (p.y_f32) {
-                    float* yp = reinterpret_cast<float*>(p.y) + m * p.ypitch + c0;
+                    float* yp = reinterpret_cast<float*>(y_g) + m * p.ypitch + c0;
                     if (full && p.y_vec) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
                     } else {
-                        for (int i = 0; i < 16 && c0 + i < p.Cout; ++i) yp[i] = f[i];
+                        for (int i = 0; i < 16 && c0 + i < cout_l; ++i) yp[i] = f[i];
                     }
                 } else {
-                    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + m * p.ypitch + c0;
+                    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_g) + m * p.ypitch + c0;
                     if (full && p.y_vec) {
                         uint32_t w[8];
 #pragma unroll
@@ -320,7 +330,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                         reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
                         reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     } else {
-                        for (int i = 0; i < 16 && c0 + i < p.Cout; ++i) reinterpret_cast<uint16_t*>(yp)[i] = pack1_16(f[i], p.f16);
+                        for (int i = 0; i < 16 && c0 + i < cout_l; ++i) reinterpret_cast<uint16_t*>(yp)[i] = pack1_16(f[i], p.f16);
                     }
                 }
             }
@@ -410,73 +420,93 @@ static bool persist_views(const ConvWeights& w, const View& x, const View& y, Vi
     return true;
 }
 
-bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int* smem_out)
+struct PersistPlan {
+    int taps, pw, halo2, kc, cchunks, sub, nsplit, nt, stages, smem, tiles;
+    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc;
+    View xv, yv;
+};
+
+// Geometry + shared-memory plan.  The weight slice a CTA owns must stay resident next to >= 2-3 patch
+// stages; when the whole [taps][Cin][Cout] tensor does not fit, Cout is split over `nsplit` CTAs per tile
+// (each re-reads the patch from L2, each owns nt = Cout/nsplit channels for good).
+static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int num_sms, PersistPlan* pl)
 {
-    if (!((w.k == 3 || w.k == 1) && w.stride == 1) || !x.is16() || (w.cin % 16) != 0 || w.cout_pad > 256) return false;
+    if (!((w.k == 3 || w.k == 1) && w.stride == 1) || !x.is16() || (w.cin % 16) != 0) return false;
     if ((x.pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(x.ptr) & 15)) return false;
     if (y.is16() && y.dtype != x.dtype) return false;
-    View xv, yv;
-    if (!persist_views(w, x, y, &xv, &yv)) return false;
-    const int taps = w.k * w.k, pw = w.k == 3 ? kTW + 2 : kTW, halo2 = w.k == 3 ? 2 : 0;
-    const int kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
-    const int cchunks = w.cin / kc;
-    const int sub = halo_sub(w, xv.h);
-    if (2 * sub * w.cout_pad > 512) return false;                 // two accumulator buffers must fit TMEM
-    const uint32_t wtile_alloc = ((uint32_t)w.cout_pad * kc * 2 + 1023u) & ~1023u;
-    const uint32_t patch_alloc = ((uint32_t)pw * (kTH * sub + halo2) * kc * 2 + 1023u) & ~1023u;
-    const uint32_t fixed = 3072u + (uint32_t)taps * cchunks * wtile_alloc + (uint32_t)kEpiWarps * 2048u;   // barriers + bias + weights + output staging
+    if (!persist_views(w, x, y, &pl->xv, &pl->yv)) return false;
+    pl->taps = w.k * w.k; pl->pw = w.k == 3 ? kTW + 2 : kTW; pl->halo2 = w.k == 3 ? 2 : 0;
+    pl->kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
+    pl->cchunks = w.cin / pl->kc;
+    pl->sub = halo_sub(w, pl->xv.h);
+    pl->tiles = ceil_div(pl->xv.w, kTW) * ceil_div(pl->xv.h, kTH * pl->sub) * pl->xv.n;
+    pl->patch_bytes = (uint32_t)pl->pw * (kTH * pl->sub + pl->halo2) * pl->kc * 2;
+    pl->patch_alloc = (pl->patch_bytes + 1023u) & ~1023u;
     const uint32_t budget = 227u * 1024u;
-    const int min_stages = cchunks + 1 < 3 ? cchunks + 1 : 3;
-    if (fixed + (uint32_t)min_stages * patch_alloc > budget) return false;
-    if (smem_out) {
-        int stages = (int)((budget - fixed) / patch_alloc);
+    const int min_stages = pl->cchunks + 1 < 3 ? pl->cchunks + 1 : 3;
+    for (int nsplit = 1; nsplit <= 16; ++nsplit) {
+        const int nt = round_up(ceil_div(w.cout_pad, nsplit), 16);
+        if (nsplit > 1 && nt * (nsplit - 1) >= w.cout_pad) continue;          // this split count adds nothing
+        if (nt > 256 || 2 * pl->sub * nt > 512) continue;                     // UMMA N limit, two accumulators in TMEM
+        const uint32_t wtile_bytes = (uint32_t)nt * pl->kc * 2;
+        const uint32_t wtile_alloc = (wtile_bytes + 1023u) & ~1023u;
+        const uint32_t fixed = 3072u + (uint32_t)pl->taps * pl->cchunks * wtile_alloc + (uint32_t)kEpiWarps * 2048u;
+        if (fixed + (uint32_t)min_stages * pl->patch_alloc > budget) continue;
+        // fits.  Small problems: keep splitting (down to N = 64, the width below which an MMA gets no cheaper)
+        // until every SM has work.
+        if (pl->tiles * nsplit < num_sms && nt > 64) continue;
+        int stages = (int)((budget - fixed) / pl->patch_alloc);
         if (stages > kMaxPatchStages) stages = kMaxPatchStages;
-        if (stages > 3 * cchunks) stages = 3 * cchunks;
+        if (stages > 3 * pl->cchunks) stages = 3 * pl->cchunks;
         if (stages < 2) stages = 2;
-        *smem_out = (int)(fixed + (uint32_t)stages * patch_alloc);
+        pl->nsplit = nsplit; pl->nt = nt; pl->stages = stages;
+        pl->wtile_bytes = wtile_bytes; pl->wtile_alloc = wtile_alloc;
+        pl->smem = (int)(fixed + (uint32_t)stages * pl->patch_alloc);
+        return true;
     }
+    return false;
+}
+
+bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int num_sms, int* work_units)
+{
+    PersistPlan pl;
+    if (!persist_plan(w, x, y, num_sms, &pl)) return false;
+    if (work_units) *work_units = pl.tiles * pl.nsplit;
     return true;
 }
 
-int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, ConvHaloOp* op)
+int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, int num_sms, ConvHaloOp* op)
 {
-    int smem = 0;
-    if (!conv_halo_supported(w, x, y, &smem)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: layer not supported (" + w.name + ")");
+    PersistPlan pl;
+    if (!persist_plan(w, x, y, num_sms, &pl)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: layer not supported (" + w.name + ")");
     if (y.h != x.h || y.w != x.w || y.n != x.n || y.c != w.cout || x.c != w.cin) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: view mismatch (" + w.name + ")");
     if (res && (res->dtype != x.dtype || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: residual view mismatch");
-    View xv, yv;
-    persist_views(w, x, y, &xv, &yv);
-    const int pw = w.k == 3 ? kTW + 2 : kTW, halo2 = w.k == 3 ? 2 : 0;
     ConvHaloOp& o = *op;
-    o.taps = w.k * w.k;
+    o.taps = pl.taps;
     o.y = y.ptr;
     o.res = res ? reinterpret_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
     o.bias = w.bias;
-    o.N = xv.n; o.H = xv.h; o.W = xv.w; o.Cin = w.cin; o.Cout = w.cout; o.ntile = w.cout_pad;
+    o.N = pl.xv.n; o.H = pl.xv.h; o.W = pl.xv.w; o.Cin = w.cin; o.Cout = w.cout; o.ntile = w.cout_pad;
     o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
     o.f16 = x.dtype == DT_F16 ? 1 : 0;
     o.act = w.act;
     o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
-    o.kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
-    o.cchunks = w.cin / o.kc;
-    o.sub = halo_sub(w, xv.h);
-    o.tiles_x = ceil_div(xv.w, kTW); o.tiles_y = ceil_div(xv.h, kTH * o.sub);
-    o.num_tiles = o.tiles_x * o.tiles_y * xv.n;
-    o.wtile_bytes = (uint32_t)w.cout_pad * o.kc * 2;
-    o.wtile_alloc = (o.wtile_bytes + 1023u) & ~1023u;
-    o.patch_bytes = (uint32_t)pw * (kTH * o.sub + halo2) * o.kc * 2;
-    o.patch_alloc = (o.patch_bytes + 1023u) & ~1023u;
-    o.smem_bytes = smem;
-    o.stages = (int)((smem - 3072 - kEpiWarps * 2048 - o.taps * o.cchunks * (int)o.wtile_alloc) / (int)o.patch_alloc);
+    o.kc = pl.kc; o.cchunks = pl.cchunks; o.sub = pl.sub; o.nsplit = pl.nsplit; o.nt = pl.nt;
+    o.tiles_x = ceil_div(pl.xv.w, kTW); o.tiles_y = ceil_div(pl.xv.h, kTH * o.sub);
+    o.num_tiles = pl.tiles;
+    o.wtile_bytes = pl.wtile_bytes; o.wtile_alloc = pl.wtile_alloc;
+    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc;
+    o.smem_bytes = pl.smem; o.stages = pl.stages;
     int cols = 32;
-    while (cols < 2 * o.sub * w.cout_pad) cols <<= 1;
+    while (cols < 2 * o.sub * o.nt) cols <<= 1;
     o.tmem_cols = cols;
-    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, w.cout_pad, o.kc * 2, o.f16));
-    ZL_TRY(make_tmap_nhwc(&o.tmap_x, xv, o.kc, o.kc * 2, o.f16, pw, kTH * o.sub + halo2));
+    // weight box = one slice of nt output channels (rows past Cout_pad are zero-filled by TMA)
+    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, o.nt, o.kc * 2, o.f16));
+    ZL_TRY(make_tmap_nhwc(&o.tmap_x, pl.xv, o.kc, o.kc * 2, o.f16, pl.pw, kTH * o.sub + pl.halo2));
     o.y_tma = (y.is16() && (y.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
-    if (o.y_tma) ZL_TRY(make_tmap_out(&o.tmap_y, yv, o.f16)); else o.tmap_y = o.tmap_x;
+    if (o.y_tma) ZL_TRY(make_tmap_out(&o.tmap_y, pl.yv, o.f16)); else o.tmap_y = o.tmap_x;
     o.flops = 2.0 * (double)y.pixels() * w.cout * w.ktot;
     o.bytes = (double)x.pixels() * w.cin * 2 + (double)y.pixels() * w.cout * (o.y_f32 ? 4 : 2) + (double)w.cout * w.ktot * 2 +
               (res ? (double)y.pixels() * w.cout * 2 : 0.0);
@@ -497,11 +527,12 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.y = o.y; p.res = o.res; p.bias = o.bias;
     p.N = o.N; p.H = o.H; p.W = o.W; p.Cin = o.Cin; p.Cout = o.Cout; p.ntile = o.ntile;
     p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16; p.act = o.act;
-    p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma;
+    p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma; p.nsplit = o.nsplit; p.nt = o.nt;
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
     p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc;
     p.tmem_cols = o.tmem_cols;
-    const int grid = o.num_tiles < num_sms ? o.num_tiles : num_sms;
+    int grid = o.num_tiles * o.nsplit;
+    if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
     if (o.taps == 9) conv_halo_kernel<9><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
     else conv_halo_kernel<1><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
     ZL_CUDA(cudaGetLastError());

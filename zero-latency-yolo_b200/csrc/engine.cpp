@@ -372,11 +372,11 @@ int32_t Engine::build_ops(Lane& L, int B)
                    (double)w.cout * w.ktot * (bf16 ? 2 : 4) + (res ? (double)y.pixels() * w.cout * res->esize() : 0.0);
         if (!bf16) op.kind = Op::CONV_SIMT;
         else if (w.cin == 3) op.kind = Op::CONV0;
-        else if (use_halo && conv_halo_supported(w, x, y, nullptr) &&
-                 (w.k == 3 ? ceil_div(y.w, 8) * ceil_div(y.h, 16) * y.n : (int)(y.pixels() / 128)) >= 4 * num_sms) {
-            // big 3x3 stride-1 layers: persistent halo kernel (input read ~1.4x instead of 9x)
+        else if (int units = 0; use_halo && conv_halo_supported(w, x, y, num_sms, &units) && units >= num_sms) {
+            // stride-1 layers with at least one work unit per SM: persistent weights-resident kernel
+            // (3x3: input read ~1.4x instead of 9x; 1x1: flattened pixel tiles)
             op.kind = Op::CONV_HALO;
-            rc = conv_halo_prepare(w, x, y, res, &op.halo);
+            rc = conv_halo_prepare(w, x, y, res, num_sms, &op.halo);
         } else {
             op.kind = Op::CONV_TC;
             // small problems (latency path): split Cout over more CTAs so more than a handful of SMs work

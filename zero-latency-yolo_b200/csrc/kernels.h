@@ -69,14 +69,14 @@ struct ConvHaloOp {
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
-    int32_t kc, cchunks, stages, sub, y_tma, taps;
+    int32_t kc, cchunks, stages, sub, y_tma, taps, nsplit, nt;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, tmem_cols;
     int32_t smem_bytes;
     double flops, bytes;
 };
-bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int* smem_out);
-int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, ConvHaloOp* op);
+bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int num_sms, int* work_units);
+int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, int num_sms, ConvHaloOp* op);
 int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms);
 
 // ---------------------------------------------------------------- pool / upsample

@@ -140,6 +140,7 @@ filter_kernel(const float* __restrict__ raw, int nc, int A, const FrameDesc* __r
 
 // ============================================================= N1: NMS
 constexpr int kNmsThreads = 1024;
+constexpr int kMaxLargeSeg = 512;     // queue slots for class segments with more than 32 candidates
 
 // calculateIoU (onnx_engine.cpp:881-909) with IEEE single ops in the reference's order.
 __device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
@@ -158,13 +159,15 @@ __device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
 
 // One CTA per frame.  Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | scan scratch.
 __global__ void __launch_bounds__(kNmsThreads)
-nms_kernel(int A, float iou_thr, int key_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
+nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
            float4* __restrict__ sorted_box, const uint32_t* __restrict__ cand_count, uint32_t* __restrict__ header,
            DevDet* __restrict__ dets, int maxn, uint32_t cap)
 {
     extern __shared__ __align__(16) uint8_t nms_smem[];
     __shared__ uint32_t s_warp_tot[32];
     __shared__ uint32_t s_base;
+    __shared__ int s_nlarge, s_qhead, s_gq[8];
+    __shared__ int s_large[2 * kMaxLargeSeg];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = (int)min(cand_count[f], (uint32_t)A);
@@ -213,41 +216,118 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int key_pitch, uint64_t* __re
     }
     const uint64_t* K = in_smem ? skeys : gkeys;
 
-    // ---- gather boxes into sorted order
-    float4* sb = sorted_box + (size_t)f * A;
+    // ---- gather boxes into sorted order: shared memory when they fit (the greedy sweep below is a chain of
+    // dependent box reads, so its latency is the box read latency), else the global scratch
+    float4* sb = (n <= box_cap_smem)
+                     ? reinterpret_cast<float4*>(nms_smem + (size_t)key_cap_smem * 8 + (size_t)(((((A + 31) >> 5) * 4) + 15) & ~15))
+                     : sorted_box + (size_t)f * A;
     for (int i = tid; i < n; i += kNmsThreads) sb[i] = box_by_anchor[(size_t)f * A + key_anchor(K[i])];
     __syncthreads();
 
-    // ---- greedy sweep, one warp per class segment (segments found by their head element)
+    // ---- greedy per-class suppression (applyNMS, onnx_engine.cpp:856-875), exact, in two phases.
+    // A class segment is a run of equal class ids in the sorted list.  The reference's loop is a serial chain over the
+    // KEPT candidates of a segment; each link tests the still-alive later candidates, which is the parallel part.
+    //  phase 1: segments of <= 32 candidates — one warp each, boxes in registers, links cost one shuffle + one IoU;
+    //  phase 2: larger segments — groups of 4 warps pull segments from a queue; per link the 128 threads sweep the
+    //           remaining candidates and meet on a named barrier.
     if (n > 1) {
+        if (tid == 0) { s_nlarge = 0; s_qhead = 0; }
+        __syncthreads();
         for (int head = warp; head < n; head += kNmsThreads / 32) {
-            // every warp scans candidate heads strided by warp id; a head is an index whose class differs from its predecessor
-            // (cheap test, the heavy work only starts on real heads)
-            bool is_head = head == 0 || key_class(K[head]) != key_class(K[head - 1]);
+            const bool is_head = head == 0 || key_class(K[head]) != key_class(K[head - 1]);
             if (!is_head) continue;
             const int cls = key_class(K[head]);
-            // segment end = first index with a larger class (binary search on the sorted keys)
-            int lo = head + 1, hi = n;
+            int lo = head + 1, hi = n;                       // segment end: first index with a larger class
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (key_class(K[mid]) > cls) hi = mid; else lo = mid + 1;
             }
-            const int end = lo;
-            for (int i = head; i < end - 1; ++i) {
-                const uint32_t wi = removed[i >> 5];
-                if ((wi >> (i & 31)) & 1u) continue;        // is_removed[i]  (onnx_engine.cpp:857)
+            const int end = lo, m = end - head;
+            if (m == 1) continue;
+            if (m > 32) {
+                if (lane == 0) { const int q = atomicAdd(&s_nlarge, 1); if (q < kMaxLargeSeg) { s_large[2 * q] = head; s_large[2 * q + 1] = end; } }
+                continue;
+            }
+            const int i = head + lane;
+            const bool valid = lane < m;
+            const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t cur = m == 32 ? 0xffffffffu : ((1u << m) - 1u);      // alive, not yet decided
+            uint32_t kept = 0u;
+            while (cur != 0u) {
+                const int t = __ffs(cur) - 1;                              // next candidate in sorted order that is not removed
+                kept |= 1u << t;
+                cur &= ~(1u << t);
+                float4 bt;
+                bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
+                bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
+                const bool sup = ((cur >> lane) & 1u) && iou_ref(bt, bi) > iou_thr;     // strict '>' (onnx_engine.cpp:871)
+                cur &= ~__ballot_sync(0xffffffffu, sup);
+            }
+            if (valid && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
+        }
+        __syncthreads();
+        const int nlarge = min(s_nlarge, kMaxLargeSeg);
+        const bool overflow = s_nlarge > kMaxLargeSeg;                      // more large segments than queue slots: handled below
+        const int grp = warp >> 2, gtid = tid & 127;                        // 8 groups of 128 threads
+        for (;;) {
+            int q = 0;
+            if (gtid == 0) q = atomicAdd(&s_qhead, 1);
+            // broadcast q inside the group through the named barrier + smem
+            if (gtid == 0) s_gq[grp] = q;
+            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            q = s_gq[grp];
+            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            if (q >= nlarge) break;
+            const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
+            int i = s0;
+            while (i < e0) {
                 const float4 bi = sb[i];
-                for (int j0 = (i + 1) & ~31; j0 < end; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool sup = false;
-                    if (j > i && j < end) {
-                        const bool gone = (removed[j >> 5] >> (j & 31)) & 1u;
-                        if (!gone) sup = iou_ref(bi, sb[j]) > iou_thr;     // strict '>' (onnx_engine.cpp:871)
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                    if (bal != 0u && lane == 0) atomicOr(const_cast<uint32_t*>(&removed[j0 >> 5]), bal);
+                for (int j = i + 1 + gtid; j < e0; j += 128) {
+                    if (((removed[j >> 5] >> (j & 31)) & 1u) == 0u && iou_ref(bi, sb[j]) > iou_thr)
+                        atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31));
                 }
-                __syncwarp();
+                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+                // next candidate that survived everything before it (uniform across the group)
+                ++i;
+                while (i < e0) {
+                    const uint32_t wv = removed[i >> 5] >> (i & 31);
+                    const uint32_t alive = ~wv;
+                    if (alive == 0u) { i = (i | 31) + 1; continue; }
+                    const int skip = __ffs(alive) - 1;
+                    if ((i & 31) + skip > 31) { i = (i | 31) + 1; continue; }
+                    i += skip;
+                    break;
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");   // everyone has read the flags before the next sweep writes
+            }
+        }
+        if (overflow) {
+            // pathological: > kMaxLargeSeg large segments (needs > 64 classes with > 32 candidates each AND queue overflow);
+            // fall back to the plain sequential sweep for the segments that did not get a slot
+            __syncthreads();
+            for (int head = warp; head < n; head += kNmsThreads / 32) {
+                const bool is_head = head == 0 || key_class(K[head]) != key_class(K[head - 1]);
+                if (!is_head) continue;
+                const int cls = key_class(K[head]);
+                int lo = head + 1, hi = n;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (key_class(K[mid]) > cls) hi = mid; else lo = mid + 1; }
+                const int end = lo;
+                if (end - head <= 32) continue;
+                bool queued = false;
+                for (int q = 0; q < kMaxLargeSeg; ++q) if (s_large[2 * q] == head) { queued = true; break; }
+                if (queued) continue;
+                for (int i = head; i < end - 1; ++i) {
+                    if ((removed[i >> 5] >> (i & 31)) & 1u) continue;
+                    const float4 bi = sb[i];
+                    for (int j0 = (i + 1) & ~31; j0 < end; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool sup = false;
+                        if (j > i && j < end && !((removed[j >> 5] >> (j & 31)) & 1u)) sup = iou_ref(bi, sb[j]) > iou_thr;
+                        const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                        if (bal != 0u && lane == 0) atomicOr(const_cast<uint32_t*>(&removed[j0 >> 5]), bal);
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
@@ -338,14 +418,17 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
     int key_cap = 1;
     while (key_cap < A) key_cap <<= 1;
     if (key_cap > 16384) key_cap = 0;              // too many to sort in smem -> sort in global memory
-    const size_t mask_bytes = (size_t)ceil_div(A, 32) * 4;
-    const size_t smem = (size_t)key_cap * 8 + mask_bytes;
+    const size_t mask_bytes = ((size_t)ceil_div(A, 32) * 4 + 15) & ~(size_t)15;
+    size_t smem = (size_t)key_cap * 8 + mask_bytes;
     if (smem > 200 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "nms: anchor count too large for the suppression bitmask");
+    int box_cap = (int)((200 * 1024 - smem) / 16);
+    if (box_cap > A) box_cap = A;
+    smem += (size_t)box_cap * 16;
     static thread_local int last_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != last_dev) { ZL_TRY(nms_configure()); last_dev = dev; }
-    nms_kernel<<<n, kNmsThreads, smem, st>>>(A, iou_thr, key_cap, pb.key_pitch, pb.keys, pb.box_by_anchor, pb.sorted_box, pb.cand_count,
+    nms_kernel<<<n, kNmsThreads, smem, st>>>(A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, pb.box_by_anchor, pb.sorted_box, pb.cand_count,
                                             pb.header, pb.dets, pb.maxn, pb.cap);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
