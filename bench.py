@@ -47,47 +47,78 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread
+    (nvidia-smi -lms cannot start fast enough for a region of tens of milliseconds); nvidia-smi as a fallback."""
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.samples, self.reasons, self.max_mhz = gpu_index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        self.src = "none"
+
+    def _phys_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._phys_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.src = "nvml"
+        except Exception:
+            self._nvml = None
+            self.src = "nvidia-smi"
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        time.sleep(0.02)          # first samples land before the timed region opens
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _run(self):
+        if self._nvml is not None:
+            n = self._nvml
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                    try:
+                        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            return
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self._phys_index()), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                time.sleep(0.05)
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0, "source": self.src}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "source": self.src}
 
 
 def shard_frames(n_total, rank, world):

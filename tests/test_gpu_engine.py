@@ -111,7 +111,7 @@ def test_fp32_mode_other_scales(built_lib, scale):
 #   bf16: 3 fewer mantissa bits -> median IoU 0.986-0.993 but only 36-66 % reach 0.99
 GATES = {
     "fp16": dict(score_max=0.03, score_med=1e-4, frac99=0.95, frac90=0.97, kept_slack=2),
-    "bf16": dict(score_max=0.25, score_med=5e-3, frac99=0.25, frac90=0.85, kept_slack=8),
+    "bf16": dict(score_max=0.25, score_med=5e-3, frac99=0.25, frac90=0.80, kept_slack=8),
 }
 
 
@@ -155,6 +155,25 @@ def test_16bit_modes_close_to_oracle_640_nc80(built_lib, model_n80, mode):
     e.load_weights_blob(blob)
     e.warmup(1)
     _check_16bit(e, tensors, "n", 80, frames, 640, 640, mode)
+    e.close()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_16bit_results_do_not_depend_on_batch(built_lib, model_n80, prec):
+    """Frames never share state: a frame's detections are bit-identical whether it runs alone, in a batch of 3
+    (padded to 4) or of 32 — the kernel chosen per layer changes with the batch, the accumulation order does not."""
+    import zlb200
+    tensors, blob = model_n80
+    frames = list(synth.frames_structured(32, 640, 640, seed=123))
+    e = zlb200.Engine(640, 640, 80, "n", precision=zlb200.FP16 if prec == "fp16" else zlb200.BF16, max_batch=32)
+    e.load_weights_blob(blob)
+    big = e.infer(frames)
+    three = e.infer(frames[:3])
+    one = e.infer(frames[:1])
+    assert sum(len(d) for d in big) > 100
+    for a, b in zip(three, big[:3]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    assert np.array_equal(one[0].view(np.uint8), big[0].view(np.uint8))
     e.close()
 
 

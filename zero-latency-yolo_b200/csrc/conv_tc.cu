@@ -93,18 +93,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
     if (warp == 0) {
         // ===== TMA producer =====
+        // K-blocks run channel-chunk-major, tap-minor — the same accumulation order as the persistent kernel
+        // (conv_halo.cu), so a layer gives bit-identical results whichever kernel the batch size selects.
         if (lane == 0) {
             const uint32_t tx = p.b_bytes + (p.a_tma ? p.a_bytes : 0u);
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                const uint32_t sa = tiles + (uint32_t)s * p.stage_bytes;
-                const uint32_t sb = sa + p.a_bytes;
-                mbar_arrive_expect_tx(bar_full + 8u * s, tx);
-                const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-                tma_load_2d(&tmap_w, bar_full + 8u * s, sb, tap * p.Cin + cc * p.kc, n0);
-                if (p.a_tma) tma_load_2d(&tmap_a, bar_full + 8u * s, sa, cc * p.kc, m0);
+            const int taps = p.k * p.k;
+            uint32_t s = 0, ph = 0;
+            for (int cc = 0; cc < p.cchunks; ++cc) {
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    const uint32_t sa = tiles + s * p.stage_bytes;
+                    const uint32_t sb = sa + p.a_bytes;
+                    mbar_arrive_expect_tx(bar_full + 8u * s, tx);
+                    tma_load_2d(&tmap_w, bar_full + 8u * s, sb, tap * p.Cin + cc * p.kc, n0);
+                    if (p.a_tma) tma_load_2d(&tmap_a, bar_full + 8u * s, sa, cc * p.kc, m0);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -114,24 +118,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const uint32_t fmt = p.f16 ? 0u : 1u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.ntile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
         const int ksteps = p.kc / 16;
+        const uint64_t adesc0 = make_smem_desc(tiles, swz);
+        const uint64_t bdesc0 = make_smem_desc(tiles + p.a_bytes, swz);
+        const uint32_t stage16 = p.stage_bytes >> 4;
+        uint32_t s = 0, ph = 0;
         for (int kb = 0; kb < p.nkb; ++kb) {
-            const int s = kb % stages;
-            const uint32_t ph = (uint32_t)(kb / stages) & 1u;
             mbar_wait(bar_full + 8u * s, ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t sa = tiles + (uint32_t)s * p.stage_bytes;
-                const uint32_t sb = sa + p.a_bytes;
-                const uint64_t adesc = make_smem_desc(sa, swz);
-                const uint64_t bdesc = make_smem_desc(sb, swz);
-                for (int k = 0; k < ksteps; ++k) {
-                    // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-B units
-                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                const uint64_t adesc = adesc0 + (uint64_t)(s * stage16);
+                const uint64_t bdesc = bdesc0 + (uint64_t)(s * stage16);
+                // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-B units
+                if (ksteps == 4) {
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+                    umma_bf16(tmem_base, adesc + 4, bdesc + 4, idesc, 1u);
+                    umma_bf16(tmem_base, adesc + 6, bdesc + 6, idesc, 1u);
+                } else if (ksteps == 2) {
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+                    umma_bf16(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+                } else {
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
                 }
                 umma_commit(bar_empty + 8u * s);
                 if (kb == p.nkb - 1) umma_commit(bar_accum);
             }
             __syncwarp();
+            if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
         }
     } else {
         // ===== warps 2..5: A gather (3x3 / strided) then epilogue =====
@@ -151,32 +164,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const uint32_t rowbytes = (uint32_t)p.kc * 2u;
             // software image of the hardware swizzle (Swizzle<B,4,3> on byte addresses, tiles 1 KB aligned)
             const uint32_t xr = nchunk == 8 ? ((uint32_t)t & 7u) : (nchunk == 4 ? (((uint32_t)t >> 1) & 3u) : (((uint32_t)t >> 2) & 1u));
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
-                const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-                const int r = tap / p.k, sft = tap - r * p.k;
-                const int iy = iy0 + r, ix = ix0 + sft;
-                const bool ok = row_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                const uint4* src = reinterpret_cast<const uint4*>(
-                    p.x + ((size_t)(n_img * p.H + iy) * p.W + ix) * p.xpitch + cc * p.kc);
-                uint4 v[8];
+            const int taps = p.k * p.k;
+            uint32_t s = 0, ph = 0;
+            for (int cc = 0; cc < p.cchunks; ++cc) {
+                int r = 0, sft = 0;
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int iy = iy0 + r, ix = ix0 + sft;
+                    const bool ok = row_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                    uint4 v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[j] = make_uint4(0u, 0u, 0u, 0u);
-                    if (j < nchunk && ok) v[j] = __ldg(src + j);
-                }
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                const uint32_t rowbase = tiles + (uint32_t)s * p.stage_bytes + (uint32_t)t * rowbytes;
+                    for (int j = 0; j < 8; ++j) v[j] = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok) {
+                        const uint4* src = reinterpret_cast<const uint4*>(p.x + ((size_t)(n_img * p.H + iy) * p.W + ix) * p.xpitch + cc * p.kc);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j < nchunk) {
-                        const uint32_t dst = rowbase + ((((uint32_t)j) ^ xr) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w) : "memory");
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nchunk) v[j] = __ldg(src + j);
                     }
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    const uint32_t rowbase = tiles + s * p.stage_bytes + (uint32_t)t * rowbytes;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < nchunk) {
+                            const uint32_t dst = rowbase + ((((uint32_t)j) ^ xr) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w) : "memory");
+                        }
+                    }
+                    fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+                    mbar_arrive(bar_full + 8u * s);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+                    if (++sft == p.k) { sft = 0; ++r; }
                 }
-                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
-                mbar_arrive(bar_full + 8u * s);
             }
         }
         // ----- epilogue -----
@@ -198,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 float a = __uint_as_float(v[i]) + __ldg(p.bias + cg + i);
-                f[i] = p.act ? silu(a) : a;
+                f[i] = p.act ? __fdividef(a, 1.0f + __expf(-a)) : a;      // same formula as conv_halo.cu: results do not depend on the kernel chosen
             }
             const bool full = (cg + 16 <= p.Cout);
             if (p.res != nullptr) {
