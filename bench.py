@@ -223,7 +223,8 @@ def run_ours(args, rank, local_rank, world):
     n_sets = 4
     sets = make_inputs(n_sets, seed0=5678 + 100 * rank)
     prec = zlb200.FP16 if args.dtype == "fp16" else zlb200.BF16
-    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=prec, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank)
+    E2E_THREADS = 2        # host threads in the end-to-end leg: each owns a lane, so H2D of one batch overlaps compute of the other
+    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=prec, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank, num_lanes=E2E_THREADS)
     eng.load_weights_blob(blob)
     eng.warmup(1)
     for s in range(n_sets):
@@ -243,19 +244,34 @@ def run_ours(args, rank, local_rank, world):
     max_ms = reduce_max(ms, dist, "cuda")
     value = world * BATCH * args.steps / (max_ms / 1e3)
 
-    # ---- end to end through the public C-ABI call with pinned HOST frames
-    pinned = zlb200.pinned_array((BATCH, HW, HW, 3))
-    pinned[:] = sets[0]
-    pframes = [pinned[i] for i in range(BATCH)]
-    for _ in range(3):
-        dets = eng.infer(pframes)
+    # ---- end to end through the public C-ABI call with pinned HOST frames: every step copies its 64 frames
+    # host->device and reads the detections back; E2E_THREADS host threads keep one batch each in flight
+    pinned = [zlb200.pinned_array((BATCH, HW, HW, 3)) for _ in range(E2E_THREADS)]
+    for t, buf in enumerate(pinned):
+        buf[:] = sets[t % n_sets]
+    pframes = [[buf[i] for i in range(BATCH)] for buf in pinned]
+    last = [None] * E2E_THREADS
+
+    def e2e_worker(t, nsteps):
+        for _ in range(nsteps):
+            last[t] = eng.infer(pframes[t])
+
+    def run_e2e(total_steps):
+        share = [total_steps // E2E_THREADS + (1 if t < total_steps % E2E_THREADS else 0) for t in range(E2E_THREADS)]
+        th = [threading.Thread(target=e2e_worker, args=(t, share[t])) for t in range(E2E_THREADS)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    run_e2e(2 * E2E_THREADS)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        dets = eng.infer(pframes)
-    e2e_s = time.perf_counter() - t0
+    e2e_s = run_e2e(args.steps)
     barrier()
     e2e_fps = world * BATCH * args.steps / reduce_max(e2e_s, dist, "cuda")
+    dets = next(x for x in last if x is not None)
     n_det = sum(len(d) for d in dets)
     d2h = (4 + 2 * BATCH) * 4 + min(BATCH * 64, BATCH * eng.A) * 24
 
@@ -336,7 +352,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": WORKLOAD.replace("bf16", args.dtype), "inputs": f"{n_sets} rotating resident input sets of {BATCH} frames ({n_sets * BATCH * HW * HW * 3 / 1e6:.0f} MB > 126 MB L2)",
                    "frames_per_step_per_gpu": BATCH, "parallelism": f"frame-sharded replicas x{world}, no collective"},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * HW * HW * 3, "d2h_bytes_per_step": d2h,
-                "api": "zl_infer_batch (C-ABI) on pinned host frames, synchronous", "detections_last_step": n_det},
+                "api": f"zl_infer_batch (C-ABI) on pinned host frames from {E2E_THREADS} host threads (one lane each)", "detections_last_step": n_det},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

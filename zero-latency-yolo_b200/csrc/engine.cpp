@@ -595,8 +595,18 @@ int32_t Engine::infer_batch(const uint8_t* const* frames, const int32_t* ws, con
 {
     if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
     if (n < 0 || (n > 0 && (!frames || !ws || !hs))) ZL_FAIL(ZL_INVALID_ARGUMENT, "null argument");
-    Lane& L = *lanes[0];
-    std::lock_guard<std::mutex> g(L.mu);
+    // concurrent callers get different lanes (stream + buffers), so one caller's H2D copies overlap another's kernels
+    Lane* Lp = nullptr;
+    std::unique_lock<std::mutex> g;
+    for (auto& cand : lanes) {
+        std::unique_lock<std::mutex> t(cand->mu, std::try_to_lock);
+        if (t.owns_lock()) { Lp = cand.get(); g = std::move(t); break; }
+    }
+    if (!Lp) {
+        Lp = lanes[sync_rr.fetch_add(1) % lanes.size()].get();
+        g = std::unique_lock<std::mutex>(Lp->mu);
+    }
+    Lane& L = *Lp;
     std::vector<zl_det> dets;
     int total = 0;
     bool overflow = false;

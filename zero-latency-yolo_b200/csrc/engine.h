@@ -153,6 +153,7 @@ private:
     std::deque<double> lat_ms;
     double dev_ms_sum = 0; uint64_t dev_ms_n = 0;
     int graph_captured = 0;
+    std::atomic<uint32_t> sync_rr{0};
 };
 
 }  // namespace zl
