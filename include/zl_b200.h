@@ -212,6 +212,12 @@ ZL_API int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_
 ZL_API int32_t zl_probe_umma(int32_t device, int32_t N, int32_t swz, int32_t sbo_a, int32_t nacc, int32_t count,
                              int32_t shift_rows, int32_t ksteps, int32_t grid, int64_t* issue_cycles, int64_t* total_cycles);
 
+/* Measurement hook: one 4-D tiled TMA load (optional element stride) dumped from shared memory. */
+ZL_API int32_t zl_probe_tma(int32_t device, const uint16_t* x, int32_t n, int32_t h, int32_t w, int32_t c,
+                            int32_t box_c, int32_t box_w, int32_t box_h, int32_t estride, int32_t swizzle_bytes,
+                            int32_t c0, int32_t c1, int32_t c2, int32_t c3, uint32_t expect_bytes,
+                            uint8_t* dump, uint32_t dump_bytes, int32_t* completed);
+
 /* ---- host memory + errors ---- */
 ZL_API void*   zl_host_alloc(size_t bytes);   /* pinned */
 ZL_API void    zl_host_free(void* p);

@@ -151,6 +151,34 @@ def test_conv_halo(built_lib, case):
     assert err.max() < tol * max(1.0, np.abs(ref).max()), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
 
 
+PERSIST_S2_CASES = [
+    # n, h, w, cin, cout, fp16, out_f32, ctas   (3x3 stride 2, pad 1)
+    (1, 32, 16, 32, 64, False, True, 0),       # exactly one output tile
+    (2, 160, 160, 32, 64, False, False, 0),    # layer 3 shape
+    (1, 320, 320, 16, 32, True, False, 0),     # layer 1 shape: sub = 2, 32-B swizzle
+    (2, 80, 80, 64, 128, True, False, 0),      # layer 5: two 32-channel chunks
+    (4, 40, 40, 128, 256, False, False, 0),    # layer 7: N-split
+    (3, 38, 54, 64, 64, True, True, 5),        # ragged output tiles (19 x 27), few CTAs
+    (2, 80, 80, 64, 64, False, False, 0),      # layer 16
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_S2_CASES)
+def test_conv_persistent_stride2(built_lib, case):
+    import zlb200
+    n, h, w, cin, cout, fp16, out_f32, ctas = case
+    cvt = _h if fp16 else _bf
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = cvt(rng.normal(size=(n, h, w, cin)).astype(np.float32))
+    wt = cvt((rng.normal(size=(cout, 3, 3, cin)) / np.sqrt(cin * 9)).astype(np.float32))
+    b = rng.normal(size=cout).astype(np.float32)
+    ref = _torch_conv(x, wt, b, 2, True, None)
+    y = zlb200.test_conv(x, wt, b, stride=2, act=True, impl=3, out_f32=out_f32, fp16=fp16, ntile_hint=ctas)
+    tol = 2e-3 if (out_f32 or fp16) else 1.2e-2
+    err = np.abs(y - ref)
+    assert err.max() < tol * max(1.0, np.abs(ref).max()), f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
 PERSIST_1X1_CASES = [
     # n, h, w, cin, cout, fp16, out_f32, ctas
     (1, 16, 8, 64, 64, False, True, 0),       # one tile

@@ -33,7 +33,15 @@ using namespace tc;
 constexpr int kTW = 8, kTH = 16;            // one MMA sub-tile: 8 (w) x 16 (h) output pixels = 128 GEMM rows
 // TAPS == 9: 3x3 conv, patch = tile + 1-pixel halo (width 10, height 16*sub + 2)
 // TAPS == 1: 1x1 conv, patch = tile (width 8, height 16*sub); the pixel list is viewed as an 8-wide image
-template <int TAPS> struct Geo { static constexpr int PW = TAPS == 9 ? kTW + 2 : kTW, HALO = TAPS == 9 ? 1 : 0; };
+// MODE == 2: 3x3 stride-2 conv.  The input region of a tile is fetched as FOUR parity sub-patches (even/odd rows x
+//            even/odd columns) by TMA loads with element stride 2; tap (r,s) then reads sub-patch
+//            (r != 1, s != 1) shifted by (r >= 1, s >= 1) — the same shifted-view trick, patch width 9.
+template <int MODE> struct Geo {
+    static constexpr int TAPS = MODE == 1 ? 1 : 9;
+    static constexpr int PW = MODE == 9 ? kTW + 2 : (MODE == 2 ? kTW + 1 : kTW);
+    static constexpr int HALO = MODE == 9 ? 1 : 0;
+    static constexpr int NPATCH = MODE == 2 ? 4 : 1;
+};
 constexpr int kEpiWarps = 16;                // 4 per TMEM lane quarter, each owning a share of the accumulator columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxPatchStages = 12;
@@ -46,24 +54,26 @@ struct HaloParams {
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt;
     int32_t tiles_x, tiles_y, num_tiles;
-    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, tmem_cols;
+    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
 };
 
 // Issue all MMAs of one (tile, channel chunk): 9 taps x SUB sub-tiles x KSTEPS k-steps, fully unrolled.
 // Measured on B200 (umma_probe.cu): a tcgen05.mma with N <= 64 occupies the tensor pipe for ~48 cycles, so
 // the single issuing thread must spend far less than that per instruction: both descriptors are the
 // stage's base descriptor plus a compile-time constant in the 14-bit address field.
-template <int KSTEPS, int SUB, int TAPS>
-__device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uint64_t adesc0, uint64_t bdesc0, uint32_t wtile16,
+template <int KSTEPS, int SUB, int MODE>
+__device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uint64_t adesc0, uint64_t bdesc0, uint32_t subpatch16,
                                             uint32_t btap_stride16, uint32_t idesc, bool first_chunk)
 {
     constexpr uint32_t swz16 = (uint32_t)KSTEPS * 2u;        // bytes per pixel row / 16
-    constexpr int kPW = Geo<TAPS>::PW;
+    constexpr int kPW = Geo<MODE>::PW, TAPS = Geo<MODE>::TAPS;
 #pragma unroll
     for (int tap = 0; tap < TAPS; ++tap) {
-        const uint32_t aoff = TAPS == 9 ? (uint32_t)((tap / 3) * kPW + (tap % 3)) * swz16 : 0u;
+        const int r = tap / 3, sf = tap % 3;
+        uint32_t aoff = 0u;
+        if (MODE == 9) aoff = (uint32_t)(r * kPW + sf) * swz16;
+        if (MODE == 2) aoff = (uint32_t)((r != 1 ? 2 : 0) + (sf != 1 ? 1 : 0)) * subpatch16 + (uint32_t)((r >= 1 ? kPW : 0) + (sf >= 1 ? 1 : 0)) * swz16;
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)tap * btap_stride16);
-        (void)wtile16;
 #pragma unroll
         for (int j = 0; j < SUB; ++j) {
 #pragma unroll
@@ -75,13 +85,13 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
     }
 }
 
-template <int TAPS>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const __grid_constant__ CUtensorMap tmap_y, const HaloParams p)
 {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int kPW = Geo<TAPS>::PW, kHalo = Geo<TAPS>::HALO;
+    constexpr int kPW = Geo<MODE>::PW, kHalo = Geo<MODE>::HALO, TAPS = Geo<MODE>::TAPS, NPATCH = Geo<MODE>::NPATCH;
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
 
@@ -152,9 +162,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 const int rem = tile - n * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 for (int cc = 0; cc < p.cchunks; ++cc) {
-                    mbar_wait(bar_pempty + 8u * s, ph ^ 1u);
-                    mbar_arrive_expect_tx(bar_pfull + 8u * s, p.patch_bytes);
-                    tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
+                    mbar_wait(bar_pempty + 8u * s, ph ^ 1u, 1);
+                    mbar_arrive_expect_tx(bar_pfull + 8u * s, p.patch_bytes * (uint32_t)NPATCH);
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int pp = 0; pp < 4; ++pp)       // parity sub-patch pp = 2*(row parity) + (column parity)
+                            tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc + (uint32_t)pp * p.subpatch_alloc, cc * p.kc,
+                                        2 * (tx * kTW - 1) + (pp & 1), 2 * (ty * kTH * p.sub - 1) + (pp >> 1), n);
+                    } else {
+                        tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
+                    }
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
                 }
             }
@@ -166,21 +183,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int ksteps = p.kc / 16;
         const uint32_t sbo_a = (uint32_t)kPW * swz;          // one tile row (8 pixels) per 8-row group, groups strided by the patch row
-        mbar_wait(bar_wfull, 0u);
+        mbar_wait(bar_wfull, 0u, 2);
         tc_fence_after();
         uint32_t s = 0, ph = 0, tl = 0;
         const uint64_t adesc_base = make_smem_desc_sbo(pbase, swz, sbo_a);
         const uint64_t bdesc_base = make_smem_desc_sbo(wbase, swz, 8u * swz);
-        const uint32_t patch16 = p.patch_alloc >> 4, wtile16 = p.wtile_alloc >> 4;
+        const uint32_t patch16 = p.patch_alloc >> 4, wtile16 = p.wtile_alloc >> 4, subpatch16 = p.subpatch_alloc >> 4;
         const uint32_t btap16 = wtile16 * (uint32_t)p.cchunks;               // weight tiles are laid out [tap][chunk]
         const int sel = (ksteps == 4 ? 0 : (ksteps == 2 ? 3 : 6)) + (p.sub == 1 ? 0 : (p.sub == 2 ? 1 : 2));
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-            mbar_wait(bar_tempty + 8u * acc, aph ^ 1u);       // epilogue has drained this accumulator
+            mbar_wait(bar_tempty + 8u * acc, aph ^ 1u, 3);    // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
             for (int cc = 0; cc < p.cchunks; ++cc) {
-                mbar_wait(bar_pfull + 8u * s, ph);
+                mbar_wait(bar_pfull + 8u * s, ph, 4);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint64_t ad = adesc_base + (uint64_t)(s * patch16);
@@ -188,15 +205,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     const uint32_t nt = (uint32_t)p.nt;                 // accumulator column stride between sub-tiles
                     const bool first = cc == 0;
                     switch (sel) {
-                        case 0: issue_chunk<4, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 1: issue_chunk<4, 2, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 2: issue_chunk<4, 4, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 3: issue_chunk<2, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 4: issue_chunk<2, 2, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 5: issue_chunk<2, 4, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 6: issue_chunk<1, 1, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        case 7: issue_chunk<1, 2, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
-                        default: issue_chunk<1, 4, TAPS>(tmem_d, nt, ad, bd, wtile16, btap16, idesc, first); break;
+                        case 0: issue_chunk<4, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 1: issue_chunk<4, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 2: issue_chunk<4, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 3: issue_chunk<2, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 4: issue_chunk<2, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 5: issue_chunk<2, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 6: issue_chunk<1, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        case 7: issue_chunk<1, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        default: issue_chunk<1, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
                     }
                     umma_commit(bar_pempty + 8u * s);
                     if (cc == p.cchunks - 1) umma_commit(bar_tfull + 8u * acc);
@@ -222,7 +239,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int ox = tx * kTW + tw;
-            mbar_wait(bar_tfull + 8u * acc, aph);
+            mbar_wait(bar_tfull + 8u * acc, aph, 5);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (p.tmem_cols >> 1);
             for (int item = cgp; item < items; item += kEpiWarps / 4) {
@@ -351,7 +368,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f16, int patch_w, int patch_h)
+int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f16, int patch_w, int patch_h, int estride)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -363,8 +380,9 @@ int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f1
     }
     cuuint64_t dims[4] = {(cuuint64_t)x.c, (cuuint64_t)x.w, (cuuint64_t)x.h, (cuuint64_t)x.n};
     cuuint64_t strides[3] = {(cuuint64_t)x.pitch * 2, (cuuint64_t)x.w * x.pitch * 2, (cuuint64_t)x.h * x.w * x.pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)patch_w, (cuuint32_t)patch_h, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // with a traversal stride the box spans patch*stride source elements and ceil(box/stride) of them are loaded
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(patch_w * estride), (cuuint32_t)(patch_h * estride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x.ptr, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -421,8 +439,8 @@ static bool persist_views(const ConvWeights& w, const View& x, const View& y, Vi
 }
 
 struct PersistPlan {
-    int taps, pw, halo2, kc, cchunks, sub, nsplit, nt, stages, smem, tiles;
-    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc;
+    int taps, pw, prow_extra, npatch, kc, cchunks, sub, nsplit, nt, stages, smem, tiles;
+    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc;
     View xv, yv;
 };
 
@@ -431,17 +449,24 @@ struct PersistPlan {
 // (each re-reads the patch from L2, each owns nt = Cout/nsplit channels for good).
 static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int num_sms, PersistPlan* pl)
 {
-    if (!((w.k == 3 || w.k == 1) && w.stride == 1) || !x.is16() || (w.cin % 16) != 0) return false;
+    const bool s2 = w.k == 3 && w.stride == 2;
+    if (!(((w.k == 3 || w.k == 1) && w.stride == 1) || s2) || !x.is16() || (w.cin % 16) != 0) return false;
+    if (s2 && ((x.h & 1) || (x.w & 1))) return false;
     if ((x.pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(x.ptr) & 15)) return false;
     if (y.is16() && y.dtype != x.dtype) return false;
     if (!persist_views(w, x, y, &pl->xv, &pl->yv)) return false;
-    pl->taps = w.k * w.k; pl->pw = w.k == 3 ? kTW + 2 : kTW; pl->halo2 = w.k == 3 ? 2 : 0;
+    pl->taps = w.k * w.k;
+    pl->pw = s2 ? kTW + 1 : (w.k == 3 ? kTW + 2 : kTW);
+    pl->prow_extra = s2 ? 1 : (w.k == 3 ? 2 : 0);
+    pl->npatch = s2 ? 4 : 1;
     pl->kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
+    if (s2 && pl->kc == 64) pl->kc = 32;                 // four sub-patches per stage: keep a stage under ~40 KB
     pl->cchunks = w.cin / pl->kc;
-    pl->sub = halo_sub(w, pl->xv.h);
-    pl->tiles = ceil_div(pl->xv.w, kTW) * ceil_div(pl->xv.h, kTH * pl->sub) * pl->xv.n;
-    pl->patch_bytes = (uint32_t)pl->pw * (kTH * pl->sub + pl->halo2) * pl->kc * 2;
-    pl->patch_alloc = (pl->patch_bytes + 1023u) & ~1023u;
+    pl->sub = halo_sub(w, pl->yv.h);
+    pl->tiles = ceil_div(pl->yv.w, kTW) * ceil_div(pl->yv.h, kTH * pl->sub) * pl->yv.n;
+    pl->patch_bytes = (uint32_t)pl->pw * (kTH * pl->sub + pl->prow_extra) * pl->kc * 2;      // one (sub-)patch
+    pl->subpatch_alloc = (pl->patch_bytes + 1023u) & ~1023u;
+    pl->patch_alloc = pl->subpatch_alloc * (uint32_t)pl->npatch;                              // one pipeline stage
     const uint32_t budget = 227u * 1024u;
     const int min_stages = pl->cchunks + 1 < 3 ? pl->cchunks + 1 : 3;
     for (int nsplit = 1; nsplit <= 16; ++nsplit) {
@@ -479,14 +504,16 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
 {
     PersistPlan pl;
     if (!persist_plan(w, x, y, num_sms, &pl)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: layer not supported (" + w.name + ")");
-    if (y.h != x.h || y.w != x.w || y.n != x.n || y.c != w.cout || x.c != w.cin) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: view mismatch (" + w.name + ")");
+    if (y.h != x.h / w.stride || y.w != x.w / w.stride || y.n != x.n || y.c != w.cout || x.c != w.cin) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: view mismatch (" + w.name + ")");
     if (res && (res->dtype != x.dtype || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: residual view mismatch");
     ConvHaloOp& o = *op;
     o.taps = pl.taps;
+    o.mode = (w.k == 1) ? 1 : (w.stride == 2 ? 2 : 9);
     o.y = y.ptr;
     o.res = res ? reinterpret_cast<const __nv_bfloat16*>(res->ptr) : nullptr;
     o.bias = w.bias;
-    o.N = pl.xv.n; o.H = pl.xv.h; o.W = pl.xv.w; o.Cin = w.cin; o.Cout = w.cout; o.ntile = w.cout_pad;
+    o.N = pl.yv.n; o.H = pl.yv.h; o.W = pl.yv.w;      // output geometry (tiles, clipping)
+    o.Cin = w.cin; o.Cout = w.cout; o.ntile = w.cout_pad;
     o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
     o.f16 = x.dtype == DT_F16 ? 1 : 0;
@@ -494,17 +521,17 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
     o.kc = pl.kc; o.cchunks = pl.cchunks; o.sub = pl.sub; o.nsplit = pl.nsplit; o.nt = pl.nt;
-    o.tiles_x = ceil_div(pl.xv.w, kTW); o.tiles_y = ceil_div(pl.xv.h, kTH * o.sub);
+    o.tiles_x = ceil_div(pl.yv.w, kTW); o.tiles_y = ceil_div(pl.yv.h, kTH * o.sub);
     o.num_tiles = pl.tiles;
     o.wtile_bytes = pl.wtile_bytes; o.wtile_alloc = pl.wtile_alloc;
-    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc;
+    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc; o.subpatch_alloc = pl.subpatch_alloc;
     o.smem_bytes = pl.smem; o.stages = pl.stages;
     int cols = 32;
     while (cols < 2 * o.sub * o.nt) cols <<= 1;
     o.tmem_cols = cols;
     // weight box = one slice of nt output channels (rows past Cout_pad are zero-filled by TMA)
     ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, o.nt, o.kc * 2, o.f16));
-    ZL_TRY(make_tmap_nhwc(&o.tmap_x, pl.xv, o.kc, o.kc * 2, o.f16, pl.pw, kTH * o.sub + pl.halo2));
+    ZL_TRY(make_tmap_nhwc(&o.tmap_x, pl.xv, o.kc, o.kc * 2, o.f16, pl.pw, kTH * o.sub + pl.prow_extra, w.stride));
     o.y_tma = (y.is16() && (y.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     if (o.y_tma) ZL_TRY(make_tmap_out(&o.tmap_y, pl.yv, o.f16)); else o.tmap_y = o.tmap_x;
     o.flops = 2.0 * (double)y.pixels() * w.cout * w.ktot;
@@ -521,6 +548,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     if (dev != last_dev) {
         ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         last_dev = dev;
     }
     HaloParams p;
@@ -529,11 +557,12 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16; p.act = o.act;
     p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma; p.nsplit = o.nsplit; p.nt = o.nt;
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
-    p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc;
+    p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc;
     p.tmem_cols = o.tmem_cols;
     int grid = o.num_tiles * o.nsplit;
     if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
-    if (o.taps == 9) conv_halo_kernel<9><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
+    if (o.mode == 9) conv_halo_kernel<9><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
+    else if (o.mode == 2) conv_halo_kernel<2><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
     else conv_halo_kernel<1><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;

@@ -56,7 +56,7 @@ EXPORTS = [
     "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
     "zl_engine_run_resident", "zl_engine_profile", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
-    "zl_test_conv", "zl_probe_umma", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
+    "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
 
 
@@ -102,6 +102,7 @@ def lib():
             "zl_bench_decode_nms": (i32, [vp, vp, i32, i32, i32, f32, f32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int64)]),
             "zl_test_conv": (i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
             "zl_probe_umma": (i32, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+            "zl_probe_tma": (i32, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, u32, vp, u32, C.POINTER(i32)]),
             "zl_host_alloc": (vp, [sz]),
             "zl_host_free": (None, [vp]),
             "zl_last_error": (C.c_char_p, []),
@@ -304,3 +305,14 @@ def probe_umma(N, swz=128, sbo=None, nacc=1, count=512, shift_rows=0, ksteps=4, 
     a, b = C.c_int64(), C.c_int64()
     _check(lib().zl_probe_umma(device, N, swz, sbo if sbo is not None else 8 * swz, nacc, count, shift_rows, ksteps, grid, C.byref(a), C.byref(b)))
     return a.value / count, b.value / count
+
+
+def probe_tma(x_f16, box, estride, swizzle, coords, expect_bytes, dump_bytes, device=0):
+    """x_f16: [n,h,w,c] float16 array. Returns (completed, uint16 dump)."""
+    x = np.ascontiguousarray(x_f16, np.float16)
+    n, h, w, c = x.shape
+    dump = np.zeros(dump_bytes, np.uint8)
+    done = C.c_int32()
+    _check(lib().zl_probe_tma(device, _ptr(x), n, h, w, c, box[0], box[1], box[2], estride, swizzle,
+                              coords[0], coords[1], coords[2], coords[3], expect_bytes, _ptr(dump), dump_bytes, C.byref(done)))
+    return done.value, dump.view(np.float16)
