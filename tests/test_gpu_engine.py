@@ -177,6 +177,45 @@ def test_16bit_results_do_not_depend_on_batch(built_lib, model_n80, prec):
     e.close()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_fused_decode_filter_equals_raw_path(built_lib, model_n80, prec):
+    """The hot path decodes and filters in one kernel without writing the raw head tensor; it must give exactly
+    the detections of the two-step path (raw head via zl_forward_raw -> zl_decode_nms)."""
+    import zlb200
+    tensors, blob = model_n80
+    frames = list(synth.frames_structured(3, 640, 640, seed=77))
+    e = zlb200.Engine(640, 640, 80, "n", precision=zlb200.FP32 if prec == "fp32" else zlb200.FP16, max_batch=4, conf=0.25)
+    e.load_weights_blob(blob)
+    fused = e.infer(frames)
+    two_step = e.decode_nms(e.forward_raw(frames), 640, 640, 0.25, 0.45)
+    assert sum(len(d) for d in fused) > 100
+    for a, b in zip(fused, two_step):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    e.close()
+
+
+def test_fused_preprocess_layer0_equals_unfused(built_lib, model_n4):
+    """The optional fused P1+layer-0 kernel (ZL_FUSE_PRE=1) must reproduce the two-kernel path bit for bit
+    (same sampled bytes, same 16-bit rounding of x/255, same FMA order), including on stretched 800x600 frames."""
+    import os
+    import zlb200
+    tensors, blob = model_n4
+    frames = list(synth.frames_structured(3, 416, 416, seed=41)) + [synth.frames_noise(1, 600, 800, seed=42)[0]]
+    outs = []
+    for flag in ("0", "1"):
+        os.environ["ZL_FUSE_PRE"] = flag
+        try:
+            e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP16, max_batch=4, max_frame=(800, 600))
+        finally:
+            os.environ.pop("ZL_FUSE_PRE", None)
+        e.load_weights_blob(blob)
+        outs.append((e.forward_raw(frames), e.infer(frames)))
+        e.close()
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_bf16_graph_equals_direct_launch(built_lib, model_n4):
     import zlb200
     tensors, blob = model_n4

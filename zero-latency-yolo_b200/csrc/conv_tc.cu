@@ -339,6 +339,7 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
     o.k = w.k; o.stride = w.stride; o.pad = pad; o.act = w.act;
     o.kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
+    if (w.k == 3 && w.stride == 2 && o.kc == 64) o.kc = 32;     // same K chunking as the persistent kernel's stride-2 mode: identical accumulation order
     o.swz = o.kc * 2;
     o.cchunks = w.cin / o.kc;
     o.nkb = w.k * w.k * o.cchunks;

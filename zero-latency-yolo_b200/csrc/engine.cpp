@@ -86,6 +86,7 @@ int32_t Engine::init()
     if (prop.major != 10) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", this build is sm_100a only");
     num_sms = prop.multiProcessorCount;
     if (const char* ev = getenv("ZL_DISABLE_HALO")) use_halo = !(ev[0] == '1');
+    if (const char* ev = getenv("ZL_FUSE_PRE")) fuse_pre = (ev[0] == '1');
     ZL_TRY(build_model_def());
     num_anchors = 0;
     for (int s : {8, 16, 32}) num_anchors += (cfg.model_h / s) * (cfg.model_w / s);
@@ -401,9 +402,19 @@ int32_t Engine::build_ops(Lane& L, int B)
     };
     const int* c = md.c;
 
-    { Op op; op.kind = Op::PRE; op.name = "preprocess"; op.y = buf("X0");
-      op.bytes = (double)B * cfg.model_w * cfg.model_h * (3 + 4 * (bf16 ? 2 : 4)); ops.push_back(op); }
-    conv("model.0.conv", buf("X0"), buf("A0"), nullptr);
+    if (bf16 && fuse_pre) {
+        // 16-bit modes: preprocessing is fused into layer 0 (the preprocessed image is never written)
+        auto it0 = conv_by_name.find("model.0.conv");
+        if (it0 == conv_by_name.end()) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "no weights for model.0.conv");
+        Op op; op.kind = Op::PRE_CONV0; op.name = "preprocess+model.0.conv"; op.w = it0->second; op.y = buf("A0");
+        op.flops = 2.0 * (double)op.y.pixels() * op.w->cout * 27;
+        op.bytes = (double)B * cfg.model_w * cfg.model_h * 3 + (double)op.y.pixels() * op.w->cout * 2;
+        ops.push_back(op);
+    } else {
+        Op op; op.kind = Op::PRE; op.name = "preprocess"; op.y = buf("X0");
+        op.bytes = (double)B * cfg.model_w * cfg.model_h * (3 + 4 * (bf16 ? 2 : 4)); ops.push_back(op);
+        conv("model.0.conv", buf("X0"), buf("A0"), nullptr);
+    }
     conv("model.1.conv", buf("A0"), buf("A1"), nullptr);
     c2f(2, buf("A1"), "CAT2", "T2", buf("A2"), md.n[0], true);
     conv("model.3.conv", buf("A2"), buf("A3"), nullptr);
@@ -455,38 +466,49 @@ int32_t Engine::build_ops(Lane& L, int B)
     const double rawb = (double)B * (4 + md.nc) * num_anchors * 4;
     { Op op; op.kind = Op::DECODE; op.name = "dfl_decode"; op.bytes = (double)B * num_anchors * (64 + md.nc) * 4 + rawb; ops.push_back(op); }
     { Op op; op.kind = Op::FILTER; op.name = "filter"; op.bytes = rawb; ops.push_back(op); }
+    { Op op; op.kind = Op::DECODE_FILTER; op.name = "decode+filter"; op.bytes = (double)B * num_anchors * md.nc * 4; ops.push_back(op); }
     { Op op; op.kind = Op::NMS; op.name = "nms"; op.bytes = 0; ops.push_back(op); }
     L.ops[B] = std::move(ops);
     return ZL_OK;
 }
 
 // ------------------------------------------------------------------ execution
-int32_t Engine::run_ops(Lane& L, int B, bool with_d2h)
+int32_t Engine::launch_op(Lane& L, int B, const Op& op)
 {
     cudaStream_t st = L.stream;
-    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
-    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
+    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // any 16-bit tensor-core mode
+    const bool f16 = cfg.precision == ZL_PRECISION_FP16;
+    switch (op.kind) {
+        case Op::PRE:
+            return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr);
+        case Op::CONV_TC: return conv_tc_launch(st, op.tc);
+        case Op::CONV_HALO: return conv_halo_launch(st, op.halo, num_sms);
+        case Op::CONV_SIMT: return launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr);
+        case Op::CONV0: return launch_conv0_direct(st, *op.w, op.x, op.y);
+        case Op::PRE_CONV0: return launch_pre_conv0(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, *op.w, op.y);
+        case Op::POOL: return launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3);
+        case Op::UPSAMPLE: return launch_upsample2x(st, op.x, op.y);
+        case Op::DECODE: return launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw, !bf16);
+        case Op::FILTER: return launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb);
+        case Op::DECODE_FILTER:
+            return launch_decode_filter(st, L.levels, B, md.nc, num_anchors, L.d_descs, cfg.conf_threshold, d_class_weights, L.pb, !bf16);
+        case Op::NMS: return launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb);
+    }
+    return ZL_OK;
+}
+
+// want_raw: materialise the raw head tensor (zl_forward_raw) with the two-kernel D1, F1 path; otherwise the fused
+// decode+filter kernel runs and L.raw is not written.  Both produce the same candidates bit for bit.
+int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
+{
+    cudaStream_t st = L.stream;
     auto it = L.ops.find(B);
     if (it == L.ops.end()) { ZL_TRY(build_ops(L, B)); it = L.ops.find(B); }
     ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st));
     ZL_CUDA(cudaMemsetAsync(L.pb.header, 0, sizeof(uint32_t) * 4, st));
     for (const Op& op : it->second) {
-        switch (op.kind) {
-            case Op::PRE:
-                ZL_TRY(launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr));
-                break;
-            case Op::CONV_TC: ZL_TRY(conv_tc_launch(st, op.tc)); break;
-            case Op::CONV_HALO: ZL_TRY(conv_halo_launch(st, op.halo, num_sms)); break;
-            case Op::CONV_SIMT: ZL_TRY(launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr)); break;
-            case Op::CONV0: ZL_TRY(launch_conv0_direct(st, *op.w, op.x, op.y)); break;
-            case Op::POOL: ZL_TRY(launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3)); break;
-            case Op::UPSAMPLE: ZL_TRY(launch_upsample2x(st, op.x, op.y)); break;
-            case Op::DECODE: ZL_TRY(launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw, !bf16)); break;
-            case Op::FILTER:
-                ZL_TRY(launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb));
-                break;
-            case Op::NMS: ZL_TRY(launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb)); break;
-        }
+        if (want_raw ? op.kind == Op::DECODE_FILTER : (op.kind == Op::DECODE || op.kind == Op::FILTER)) continue;
+        ZL_TRY(launch_op(L, B, op));
     }
     if (with_d2h) {
         // header (total, cnt[], off[]) and the first inline_dets records in two fixed-size copies
@@ -525,8 +547,9 @@ int32_t Engine::ensure_graph(Lane& L, int B)
     return ZL_OK;
 }
 
-int32_t Engine::launch_batch(Lane& L, int B)
+int32_t Engine::launch_batch(Lane& L, int B, bool want_raw)
 {
+    if (want_raw) return run_ops(L, B, true, true);
     if (cfg.use_graph) {
         ZL_TRY(ensure_graph(L, B));
         ZL_CUDA(cudaGraphLaunch(L.graphs[B], L.stream));
@@ -537,7 +560,7 @@ int32_t Engine::launch_batch(Lane& L, int B)
 
 // Runs n (<= max_batch) frames on lane L.  Caller holds L.mu.
 int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
-                               bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts)
+                               bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts, bool want_raw)
 {
     ZL_CUDA(cudaSetDevice(cfg.device));
     const int B = graph_batch_for(n);
@@ -556,7 +579,7 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
     for (int i = n; i < B; ++i) L.h_descs[i] = L.h_descs[0];     // padding frames repeat frame 0; their results are ignored
     ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.h_descs, sizeof(FrameDesc) * B, cudaMemcpyHostToDevice, L.stream));
     ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
-    ZL_TRY(launch_batch(L, B));
+    ZL_TRY(launch_batch(L, B, want_raw));
     ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
     ZL_CUDA(cudaStreamSynchronize(L.stream));
     float ms = 0;
@@ -615,7 +638,7 @@ int32_t Engine::infer_batch(const uint8_t* const* frames, const int32_t* ws, con
         bool pinned = true;
         for (int i = 0; i < nb; ++i) pinned = pinned && is_pinned(frames[i0 + i]);
         std::vector<int32_t> cnt(nb);
-        ZL_TRY(run_lane_batch(L, frames + i0, ws + i0, hs + i0, nb, pinned, &dets, cnt.data()));
+        ZL_TRY(run_lane_batch(L, frames + i0, ws + i0, hs + i0, nb, pinned, &dets, cnt.data(), raw_out != nullptr));
         if (raw_out) {
             const size_t per = (size_t)(4 + md.nc) * num_anchors;
             ZL_CUDA(cudaMemcpy(raw_out + (size_t)i0 * per, L.raw, per * nb * 4, cudaMemcpyDeviceToHost));
@@ -785,7 +808,7 @@ int32_t Engine::run_resident(int n_sets, int steps, float* total_ms, int64_t* la
     ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
     for (int s = 0; s < steps; ++s) {
         ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)(s % n_sets) * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
-        ZL_TRY(launch_batch(L, B));
+        ZL_TRY(launch_batch(L, B, false));
     }
     ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
     ZL_CUDA(cudaStreamSynchronize(L.stream));
@@ -793,7 +816,7 @@ int32_t Engine::run_resident(int n_sets, int steps, float* total_ms, int64_t* la
     ZL_CUDA(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
     dets = ((const uint32_t*)L.h_result)[0];
     if (total_ms) *total_ms = ms;
-    if (launches) *launches = (int64_t)steps * (int64_t)L.ops[B].size();
+    if (launches) *launches = (int64_t)steps * ((int64_t)L.ops[B].size() - 2);     // DECODE + FILTER ops are the raw-mode alternates
     if (total_dets) *total_dets = dets;
     return ZL_OK;
 }
@@ -811,9 +834,8 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
     ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)set * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
     ZL_TRY(run_ops(L, B, false));                         // warm
     ZL_CUDA(cudaStreamSynchronize(L.stream));
-    const std::vector<Op>& ops = L.ops[B];
-    const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
-    const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
+    std::vector<Op> ops;
+    for (const Op& op : L.ops[B]) if (op.kind != Op::DECODE && op.kind != Op::FILTER) ops.push_back(op);
     std::vector<cudaEvent_t> ev(ops.size() + 1);
     for (auto& e : ev) cudaEventCreate(&e);
     std::vector<double> acc(ops.size(), 0.0);
@@ -824,20 +846,8 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
         cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st);
         cudaMemsetAsync(L.pb.header, 0, 16, st);
         for (size_t i = 0; i < ops.size() && rc == ZL_OK; ++i) {
-            const Op& op = ops[i];
             cudaEventRecord(ev[i], st);
-            switch (op.kind) {
-                case Op::PRE: rc = launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr); break;
-                case Op::CONV_TC: rc = conv_tc_launch(st, op.tc); break;
-                case Op::CONV_HALO: rc = conv_halo_launch(st, op.halo, num_sms); break;
-                case Op::CONV_SIMT: rc = launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr); break;
-                case Op::CONV0: rc = launch_conv0_direct(st, *op.w, op.x, op.y); break;
-                case Op::POOL: rc = launch_sppf_pool(st, op.x, op.p1, op.p2, op.p3); break;
-                case Op::UPSAMPLE: rc = launch_upsample2x(st, op.x, op.y); break;
-                case Op::DECODE: rc = launch_dfl_decode(st, L.levels, B, md.nc, num_anchors, L.raw, !bf16); break;
-                case Op::FILTER: rc = launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb); break;
-                case Op::NMS: rc = launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb); break;
-            }
+            rc = launch_op(L, B, ops[i]);
         }
         cudaEventRecord(ev[ops.size()], st);
         if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("profile: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; }

@@ -34,7 +34,7 @@ struct ModelDef {
 };
 
 struct Op {
-    enum Kind : int32_t { PRE = 0, CONV_TC = 1, CONV_SIMT = 2, CONV0 = 3, POOL = 4, UPSAMPLE = 5, DECODE = 6, FILTER = 7, NMS = 8, CONV_HALO = 9 };
+    enum Kind : int32_t { PRE = 0, CONV_TC = 1, CONV_SIMT = 2, CONV0 = 3, POOL = 4, UPSAMPLE = 5, DECODE = 6, FILTER = 7, NMS = 8, CONV_HALO = 9, PRE_CONV0 = 10, DECODE_FILTER = 11 };
     int32_t kind = PRE;
     std::string name;
     const ConvWeights* w = nullptr;
@@ -111,6 +111,7 @@ public:
     int num_anchors = 0;
     int num_sms = 148;
     bool use_halo = true;
+    bool fuse_pre = false;     // P1 fused into layer 0 (bit-identical, measured slower than the two-kernel path: scattered byte loads)
     bool weights_loaded = false;
 
 private:
@@ -118,12 +119,13 @@ private:
     int32_t alloc_lane(Lane& L);
     void free_lane(Lane& L);
     int32_t build_ops(Lane& L, int B);
-    int32_t run_ops(Lane& L, int B, bool with_d2h);
+    int32_t run_ops(Lane& L, int B, bool with_d2h, bool want_raw = false);
+    int32_t launch_op(Lane& L, int B, const Op& op);
     int32_t ensure_graph(Lane& L, int B);
-    int32_t launch_batch(Lane& L, int B);         // graph if enabled, else direct
+    int32_t launch_batch(Lane& L, int B, bool want_raw = false);   // graph if enabled, else direct
     int graph_batch_for(int n) const;
     int32_t run_lane_batch(Lane& L, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
-                           bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts);
+                           bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts, bool want_raw = false);
     void worker_main(int lane_id);
     size_t slot_bytes() const { return (size_t)cfg.max_frame_w * cfg.max_frame_h * 3; }
     int inline_dets(int B) const;

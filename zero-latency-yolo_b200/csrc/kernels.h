@@ -34,6 +34,9 @@ int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDe
 int32_t launch_conv_simt(cudaStream_t st, const ConvWeights& w, const View& x, const View& y, const View* res);
 // bf16 first layer (cin=3 padded to 4): direct conv on CUDA cores, bf16 NHWC out.
 int32_t launch_conv0_direct(cudaStream_t st, const ConvWeights& w, const View& x, const View& y);
+// P1 + layer 0 fused for the 16-bit modes: u8 frames in, 16-bit NHWC activations out (conv_simt.cu).
+int32_t launch_pre_conv0(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n, int32_t mw, int32_t mh,
+                         const ConvWeights& w, const View& y);
 
 // tcgen05 implicit GEMM.  A operand staged either by TMA (1x1 convs: plain 2-D
 // tiled map over [pixels][cin]) or by producer warps gathering NHWC rows into
@@ -108,6 +111,9 @@ struct PostBuffers {
 int32_t launch_filter(cudaStream_t st, const float* raw, int32_t n, int32_t nc, int32_t A,
                       const FrameDesc* descs, const int32_t* img_wh, float conf_thr,
                       const float* class_weights, const PostBuffers& pb);
+// D1 + F1 fused: head maps -> candidates without materialising the raw head tensor (engine hot path).
+int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, const FrameDesc* descs,
+                             float conf_thr, const float* class_weights, const PostBuffers& pb, bool precise);
 // applyNMS (onnx_engine.cpp:837-878): per-frame key sort + per-class greedy bitmask suppression.
 int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb);
 int32_t nms_configure();   // one-time cudaFuncSetAttribute calls

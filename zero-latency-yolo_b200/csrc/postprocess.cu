@@ -24,6 +24,47 @@ namespace {
 constexpr int kDflAnchors = 32;    // anchors per CTA
 constexpr int kDflThreads = 256;   // 8 warps, 4 anchors each
 
+// Detect tail for ONE anchor, computed by a whole warp: DFL softmax expectation per side (lane owns bin lane&15 of
+// sides lane>>4 and 2+(lane>>4)), dist2bbox, x stride.  Returns (cx, cy, w, h) in model-input pixels on every lane.
+template <bool PRECISE>
+__device__ __forceinline__ float4 dfl_box(const HeadLevel& lv, size_t pix, int x, int y, int lane)
+{
+    const float* bp = lv.box + pix * 64;
+    const float va = __ldg(bp + lane), vb = __ldg(bp + 32 + lane);
+    float ma = va, mb = vb;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+    }
+    using T = typename std::conditional<PRECISE, double, float>::type;
+    T ea, eb;
+    if (PRECISE) { ea = (T)exp((double)va - (double)ma); eb = (T)exp((double)vb - (double)mb); }
+    else { ea = (T)__expf(va - ma); eb = (T)__expf(vb - mb); }
+    const T bin = (T)(lane & 15);
+    T sa = ea, sb = eb, wa = ea * bin, wb = eb * bin;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        wa += __shfl_xor_sync(0xffffffffu, wa, o);
+        wb += __shfl_xor_sync(0xffffffffu, wb, o);
+    }
+    const T da = PRECISE ? wa / sa : (T)__fdividef((float)wa, (float)sa);      // lanes 0-15: left,right ; lanes 16-31: top,bottom
+    const T db = PRECISE ? wb / sb : (T)__fdividef((float)wb, (float)sb);
+    const T dl = __shfl_sync(0xffffffffu, da, 0), dt = __shfl_sync(0xffffffffu, da, 16);
+    const T dr = __shfl_sync(0xffffffffu, db, 0), dbm = __shfl_sync(0xffffffffu, db, 16);
+    const T ax = (T)x + (T)0.5, ay = (T)y + (T)0.5, s = (T)lv.stride;
+    const T x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + dbm;
+    return make_float4((float)((x1 + x2) * (T)0.5 * s), (float)((y1 + y2) * (T)0.5 * s), (float)((x2 - x1) * s), (float)((y2 - y1) * s));
+}
+
+template <bool PRECISE>
+__device__ __forceinline__ float cls_score(float z)
+{
+    return PRECISE ? (float)(1.0 / (1.0 + exp(-(double)z))) : __fdividef(1.0f, 1.0f + __expf(-z));
+}
+
 // PRECISE = fp64 softmax / sigmoid / box arithmetic (exact mode); otherwise fp32 (bf16 mode).
 template <bool PRECISE>
 __global__ void __launch_bounds__(kDflThreads)
@@ -43,44 +84,16 @@ dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, in
         const int idx = a - lv.a0;
         const int y = idx / lv.w, x = idx - y * lv.w;
         const size_t pix = (size_t)(f * lv.h + y) * lv.w + x;
-        // ---- box: 4 sides x 16 bins; lane owns bins (lane&15) of sides (lane>>4) and 2+(lane>>4)
-        const float* bp = lv.box + pix * 64;
-        const float va = __ldg(bp + lane), vb = __ldg(bp + 32 + lane);
-        float ma = va, mb = vb;
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) {
-            ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
-            mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
-        }
-        using T = typename std::conditional<PRECISE, double, float>::type;
-        T ea, eb;
-        if (PRECISE) { ea = (T)exp((double)va - (double)ma); eb = (T)exp((double)vb - (double)mb); }
-        else { ea = (T)expf(va - ma); eb = (T)expf(vb - mb); }
-        const T bin = (T)(lane & 15);
-        T sa = ea, sb = eb, wa = ea * bin, wb = eb * bin;
-#pragma unroll
-        for (int o = 8; o >= 1; o >>= 1) {
-            sa += __shfl_xor_sync(0xffffffffu, sa, o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
-            wa += __shfl_xor_sync(0xffffffffu, wa, o);
-            wb += __shfl_xor_sync(0xffffffffu, wb, o);
-        }
-        const T da = wa / sa, db = wb / sb;           // lanes 0-15: left,right ; lanes 16-31: top,bottom
-        const T dl = __shfl_sync(0xffffffffu, da, 0), dt = __shfl_sync(0xffffffffu, da, 16);
-        const T dr = __shfl_sync(0xffffffffu, db, 0), dbm = __shfl_sync(0xffffffffu, db, 16);
+        // ---- box: 4 sides x 16 bins, 16-lane shuffle softmax
+        const float4 bx = dfl_box<PRECISE>(lv, pix, x, y, lane);
         if (lane == 0) {
-            const T ax = (T)x + (T)0.5, ay = (T)y + (T)0.5, s = (T)lv.stride;
-            const T x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + dbm;
-            stage[0 * 33 + la] = (float)((x1 + x2) * (T)0.5 * s);
-            stage[1 * 33 + la] = (float)((y1 + y2) * (T)0.5 * s);
-            stage[2 * 33 + la] = (float)((x2 - x1) * s);
-            stage[3 * 33 + la] = (float)((y2 - y1) * s);
+            stage[0 * 33 + la] = bx.x; stage[1 * 33 + la] = bx.y; stage[2 * 33 + la] = bx.z; stage[3 * 33 + la] = bx.w;
         }
         // ---- classes: sigmoid, transposed through smem
         const float* cp = lv.cls + pix * lv.cls_pitch;
         for (int c = lane; c < nc; c += 32) {
             const float z = __ldg(cp + c);
-            stage[(4 + c) * 33 + la] = PRECISE ? (float)(1.0 / (1.0 + exp(-(double)z))) : 1.0f / (1.0f + expf(-z));
+            stage[(4 + c) * 33 + la] = cls_score<PRECISE>(z);
         }
     }
     __syncthreads();
@@ -135,6 +148,49 @@ filter_kernel(const float* __restrict__ raw, int nc, int A, const FrameDesc* __r
         const uint32_t slot = base + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
         keys[(size_t)f * key_pitch + slot] = make_key(max_id, max_conf, a);
         box_by_anchor[(size_t)f * A + a] = make_float4(__fdiv_rn(cx, fw), __fdiv_rn(cy, fh), __fdiv_rn(w, fw), __fdiv_rn(h, fh));
+    }
+}
+
+// D1 + F1 fused (engine hot path): the raw head tensor [n,4+nc,A] is never materialised.  One warp per anchor:
+// lanes score the classes (same sigmoid as dfl_decode_kernel), a shuffle reduction finds (max score, lowest class
+// index) == the reference's strict-'>' scan (onnx_engine.cpp:787-796), and ONLY anchors that pass the threshold
+// (:799) pay for the DFL box decode.  Emits the same keys / boxes as filter_kernel, bit for bit.
+template <bool PRECISE>
+__global__ void __launch_bounds__(256)
+decode_filter_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, int nc, int A, const FrameDesc* __restrict__ descs,
+                     float conf_thr, const float* __restrict__ class_weights, uint64_t* __restrict__ keys, int key_pitch,
+                     float4* __restrict__ box_by_anchor, uint32_t* __restrict__ cand_count)
+{
+    const int f = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_begin = (blockIdx.x * 8 + warp) * 8;                 // 8 warps x 8 anchors per CTA
+    for (int a = a_begin; a < min(a_begin + 8, A); ++a) {
+        const HeadLevel& lv = (a >= l2.a0) ? l2 : (a >= l1.a0 ? l1 : l0);
+        const int idx = a - lv.a0;
+        const int y = idx / lv.w, x = idx - y * lv.w;
+        const size_t pix = (size_t)(f * lv.h + y) * lv.w + x;
+        const float* cp = lv.cls + pix * lv.cls_pitch;
+        float best = 0.0f;
+        int best_id = -1;
+        for (int c = lane; c < nc; c += 32) {                        // ascending classes per lane: strict '>' keeps the first
+            float s = cls_score<PRECISE>(__ldg(cp + c));
+            if (class_weights) s = __fmul_rn(s, __ldg(class_weights + c));
+            if (s > best) { best = s; best_id = c; }
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
+            if (oi >= 0 && (ob > best || (ob == best && (best_id < 0 || oi < best_id)))) { best = ob; best_id = oi; }
+        }
+        if (!(best >= conf_thr && best_id >= 0)) continue;           // warp-uniform
+        const float4 bx = dfl_box<PRECISE>(lv, pix, x, y, lane);
+        if (lane == 0) {
+            const float fw = (float)descs[f].w, fh = (float)descs[f].h;
+            const uint32_t slot = atomicAdd(cand_count + f, 1u);
+            keys[(size_t)f * key_pitch + slot] = make_key(best_id, best, a);
+            box_by_anchor[(size_t)f * A + a] = make_float4(__fdiv_rn(bx.x, fw), __fdiv_rn(bx.y, fh), __fdiv_rn(bx.z, fw), __fdiv_rn(bx.w, fh));
+        }
     }
 }
 
@@ -399,6 +455,17 @@ int32_t launch_filter(cudaStream_t st, const float* raw, int32_t n, int32_t nc, 
     if (A > kMaxAnchors || nc > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "filter: A or nc beyond key range");
     dim3 grid(ceil_div(A, 256), n);
     filter_kernel<<<grid, 256, 0, st>>>(raw, nc, A, descs, img_wh, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
+int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, const FrameDesc* descs,
+                             float conf_thr, const float* class_weights, const PostBuffers& pb, bool precise)
+{
+    if (A > kMaxAnchors || nc > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "decode_filter: A or nc beyond key range");
+    dim3 grid(ceil_div(A, 64), n);
+    if (precise) decode_filter_kernel<true><<<grid, 256, 0, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    else decode_filter_kernel<false><<<grid, 256, 0, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }
