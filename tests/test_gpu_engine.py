@@ -194,6 +194,32 @@ def test_fused_decode_filter_equals_raw_path(built_lib, model_n80, prec):
     e.close()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_saturated_scores_tie_to_lowest_class(built_lib, model_n4, prec):
+    """Class logits 18 / 25 / 20 / 25 on every anchor: all four sigmoid scores round to exactly 1.0f, and the
+    reference's strict '>' scan (onnx_engine.cpp:787-796) keeps the FIRST maximum -> class 0 everywhere.  Guards the
+    fused kernel's "only score the classes near the largest logit" shortcut against fp32 score collisions."""
+    import zlb200
+    from oracle import zlw
+    tensors, _ = model_n4
+    t2 = {k: v.copy() for k, v in tensors.items()}
+    for l in range(3):
+        t2[f"model.22.cv3.{l}.2.weight"][:] = 0.0
+        t2[f"model.22.cv3.{l}.2.bias"][:] = np.array([18.0, 25.0, 20.0, 25.0], np.float32)
+    frames = [synth.frames_structured(1, 416, 416, seed=5)[0]]
+    e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP32 if prec == "fp32" else zlb200.FP16, max_batch=1)
+    e.load_weights_blob(zlw.dumps(t2, "n", 4))
+    raw = e.forward_raw(frames)
+    assert np.all(raw[0, 4:] == np.float32(1.0))
+    fused = e.infer(frames)[0]
+    two_step = e.decode_nms(raw, 416, 416, 0.5, 0.45)[0]
+    ref, _ = oracle_c.postprocess(raw[0], 416, 416, 0.5, 0.45)
+    assert len(fused) > 0 and np.all(fused["class_id"] == 0)
+    assert np.array_equal(fused.view(np.uint8), two_step.view(np.uint8))
+    assert np.array_equal(fused.view(np.uint8), ref.view(np.uint8))
+    e.close()
+
+
 def test_fused_preprocess_layer0_equals_unfused(built_lib, model_n4):
     """The optional fused P1+layer-0 kernel (ZL_FUSE_PRE=1) must reproduce the two-kernel path bit for bit
     (same sampled bytes, same 16-bit rounding of x/255, same FMA order), including on stretched 800x600 frames."""

@@ -52,7 +52,7 @@ struct HaloParams {
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
-    int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt;
+    int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
 };
@@ -230,7 +230,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int th = row >> 3, tw = row & 7;
         const int nchunk = ntile >> 4;
         const int items = p.sub * nchunk;
-        const uint32_t stage_out = obase + (warp - 2u) * 2048u;     // this warp's two 1 KB staging blocks ([32 px][16 ch], 32-B swizzle)
+        const uint32_t stage_out = obase + (warp - 2u) * 2u * (uint32_t)p.ostage;   // this warp's two staging blocks ([32 px][16 ch]; 1 KB 16-bit / 2 KB fp32)
         uint32_t nstore = 0;
         uint32_t tl = 0;
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
@@ -278,15 +278,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                             for (int i = 0; i < 16 && c0 + i < cout_l; ++i) a[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
                         }
                     }
-                    uint32_t w[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], p.f16);
-                    const uint32_t sbuf = stage_out + (nstore & 1u) * 1024u;
+                    const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
                     if (nstore >= 2u) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
-                    const uint32_t xr = (lane >> 2) & 1u;                                           // 32-B swizzle: chunk ^= address bit 7
-                    const uint32_t rowb = sbuf + lane * 32u;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((1u ^ xr) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                    if (p.y_f32) {
+                        const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
+                        const uint32_t rowb = sbuf + lane * 64u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)i) ^ xr) << 4)), "r"(__float_as_uint(a[4 * i])),
+                                         "r"(__float_as_uint(a[4 * i + 1])), "r"(__float_as_uint(a[4 * i + 2])), "r"(__float_as_uint(a[4 * i + 3])) : "memory");
+                    } else {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], p.f16);
+                        const uint32_t xr = (lane >> 2) & 1u;                                       // 32-B swizzle: chunk ^= address bit 7
+                        const uint32_t rowb = sbuf + lane * 32u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((1u ^ xr) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                    }
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
@@ -393,7 +402,7 @@ int32_t make_tmap_nhwc(CUtensorMap* map, const View& x, int kc, int swz, bool f1
     return ZL_OK;
 }
 
-int32_t make_tmap_out(CUtensorMap* map, const View& y, bool f16)
+int32_t make_tmap_out(CUtensorMap* map, const View& y, bool f16)   // 16-bit (32-B swizzle) or fp32 (64-B swizzle) output tiles
 {
     void* ptr = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -401,11 +410,13 @@ int32_t make_tmap_out(CUtensorMap* map, const View& y, bool f16)
         ZL_FAIL(ZL_SYSTEM_ERROR, "cuTensorMapEncodeTiled entry point not available");
     EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ptr);
     cuuint64_t dims[4] = {(cuuint64_t)y.c, (cuuint64_t)y.w, (cuuint64_t)y.h, (cuuint64_t)y.n};
-    cuuint64_t strides[3] = {(cuuint64_t)y.pitch * 2, (cuuint64_t)y.w * y.pitch * 2, (cuuint64_t)y.h * y.w * y.pitch * 2};
+    const uint64_t es = y.esize();
+    cuuint64_t strides[3] = {(cuuint64_t)y.pitch * es, (cuuint64_t)y.w * y.pitch * es, (cuuint64_t)y.h * y.w * y.pitch * es};
     cuuint32_t box[4] = {16, (cuuint32_t)kTW, 4, 1};       // one epilogue warp: 16 channels x 8 px x 4 rows
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y.ptr, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const bool f32 = y.dtype == DT_F32;
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, y.ptr, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) ZL_FAIL(ZL_SYSTEM_ERROR, "cuTensorMapEncodeTiled(out) failed, CUresult " + std::to_string((int)r));
     int drv = 0;
     cudaDriverGetVersion(&drv);
@@ -475,7 +486,7 @@ static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int
         if (nt > 256 || 2 * pl->sub * nt > 512) continue;                     // UMMA N limit, two accumulators in TMEM
         const uint32_t wtile_bytes = (uint32_t)nt * pl->kc * 2;
         const uint32_t wtile_alloc = (wtile_bytes + 1023u) & ~1023u;
-        const uint32_t fixed = 3072u + (uint32_t)pl->taps * pl->cchunks * wtile_alloc + (uint32_t)kEpiWarps * 2048u;
+        const uint32_t fixed = 3072u + (uint32_t)pl->taps * pl->cchunks * wtile_alloc + (uint32_t)kEpiWarps * (y.dtype == DT_F32 ? 4096u : 2048u);
         if (fixed + (uint32_t)min_stages * pl->patch_alloc > budget) continue;
         // fits.  Small problems: keep splitting (down to N = 64, the width below which an MMA gets no cheaper)
         // until every SM has work.
@@ -532,7 +543,8 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     // weight box = one slice of nt output channels (rows past Cout_pad are zero-filled by TMA)
     ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, o.nt, o.kc * 2, o.f16));
     ZL_TRY(make_tmap_nhwc(&o.tmap_x, pl.xv, o.kc, o.kc * 2, o.f16, pl.pw, kTH * o.sub + pl.prow_extra, w.stride));
-    o.y_tma = (y.is16() && (y.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
+    o.y_tma = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
+    o.ostage = y.dtype == DT_F32 ? 2048 : 1024;
     if (o.y_tma) ZL_TRY(make_tmap_out(&o.tmap_y, pl.yv, o.f16)); else o.tmap_y = o.tmap_x;
     o.flops = 2.0 * (double)y.pixels() * w.cout * w.ktot;
     o.bytes = (double)x.pixels() * w.cin * 2 + (double)y.pixels() * w.cout * (o.y_f32 ? 4 : 2) + (double)w.cout * w.ktot * 2 +
@@ -555,7 +567,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.y = o.y; p.res = o.res; p.bias = o.bias;
     p.N = o.N; p.H = o.H; p.W = o.W; p.Cin = o.Cin; p.Cout = o.Cout; p.ntile = o.ntile;
     p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16; p.act = o.act;
-    p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma; p.nsplit = o.nsplit; p.nt = o.nt;
+    p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma; p.nsplit = o.nsplit; p.nt = o.nt; p.ostage = o.ostage;
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
     p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc;
     p.tmem_cols = o.tmem_cols;

@@ -72,7 +72,7 @@ struct ConvHaloOp {
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
-    int32_t kc, cchunks, stages, sub, y_tma, taps, nsplit, nt, mode;
+    int32_t kc, cchunks, stages, sub, y_tma, taps, nsplit, nt, mode, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
     int32_t smem_bytes;

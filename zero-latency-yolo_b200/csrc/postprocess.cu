@@ -24,38 +24,43 @@ namespace {
 constexpr int kDflAnchors = 32;    // anchors per CTA
 constexpr int kDflThreads = 256;   // 8 warps, 4 anchors each
 
-// Detect tail for ONE anchor, computed by a whole warp: DFL softmax expectation per side (lane owns bin lane&15 of
-// sides lane>>4 and 2+(lane>>4)), dist2bbox, x stride.  Returns (cx, cy, w, h) in model-input pixels on every lane.
+// Detect tail, four lanes per anchor: lane `side` (0..3 = left, top, right, bottom) reads its 16
+// DFL bins with four float4 loads and does the softmax expectation in-thread, in a fixed order shared by the raw-head
+// kernel and the fused hot-path kernel (so both give the same bits); two xor-shuffles gather the four sides.
 template <bool PRECISE>
-__device__ __forceinline__ float4 dfl_box(const HeadLevel& lv, size_t pix, int x, int y, int lane)
+__device__ __forceinline__ float dfl_side(const float* __restrict__ bins)
 {
-    const float* bp = lv.box + pix * 64;
-    const float va = __ldg(bp + lane), vb = __ldg(bp + 32 + lane);
-    float ma = va, mb = vb;
-#pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) {
-        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
-        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
-    }
     using T = typename std::conditional<PRECISE, double, float>::type;
-    T ea, eb;
-    if (PRECISE) { ea = (T)exp((double)va - (double)ma); eb = (T)exp((double)vb - (double)mb); }
-    else { ea = (T)__expf(va - ma); eb = (T)__expf(vb - mb); }
-    const T bin = (T)(lane & 15);
-    T sa = ea, sb = eb, wa = ea * bin, wb = eb * bin;
+    float z[16];
 #pragma unroll
-    for (int o = 8; o >= 1; o >>= 1) {
-        sa += __shfl_xor_sync(0xffffffffu, sa, o);
-        sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        wa += __shfl_xor_sync(0xffffffffu, wa, o);
-        wb += __shfl_xor_sync(0xffffffffu, wb, o);
+    for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(bins) + q);
+        z[4 * q] = v.x; z[4 * q + 1] = v.y; z[4 * q + 2] = v.z; z[4 * q + 3] = v.w;
     }
-    const T da = PRECISE ? wa / sa : (T)__fdividef((float)wa, (float)sa);      // lanes 0-15: left,right ; lanes 16-31: top,bottom
-    const T db = PRECISE ? wb / sb : (T)__fdividef((float)wb, (float)sb);
-    const T dl = __shfl_sync(0xffffffffu, da, 0), dt = __shfl_sync(0xffffffffu, da, 16);
-    const T dr = __shfl_sync(0xffffffffu, db, 0), dbm = __shfl_sync(0xffffffffu, db, 16);
+    float m = z[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, z[i]);
+    T se = (T)0, sw = (T)0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const T e = PRECISE ? (T)exp((double)z[i] - (double)m) : (T)__expf(z[i] - m);
+        se += e;
+        sw += e * (T)i;
+    }
+    return PRECISE ? (float)(sw / se) : __fdividef((float)sw, (float)se);
+}
+
+// All four lanes of the anchor's quad call this with the same (lv, pix, x, y); every lane returns the box.
+template <bool PRECISE>
+__device__ __forceinline__ float4 dfl_box4(const HeadLevel& lv, size_t pix, int x, int y, int side, unsigned quad_mask)
+{
+    using T = typename std::conditional<PRECISE, double, float>::type;
+    const float d = dfl_side<PRECISE>(lv.box + pix * 64 + side * 16);
+    const int lane = threadIdx.x & 31, q0 = lane & ~3;
+    const float dl = __shfl_sync(quad_mask, d, q0 + 0), dt = __shfl_sync(quad_mask, d, q0 + 1);
+    const float dr = __shfl_sync(quad_mask, d, q0 + 2), db = __shfl_sync(quad_mask, d, q0 + 3);
     const T ax = (T)x + (T)0.5, ay = (T)y + (T)0.5, s = (T)lv.stride;
-    const T x1 = ax - dl, y1 = ay - dt, x2 = ax + dr, y2 = ay + dbm;
+    const T x1 = ax - (T)dl, y1 = ay - (T)dt, x2 = ax + (T)dr, y2 = ay + (T)db;
     return make_float4((float)((x1 + x2) * (T)0.5 * s), (float)((y1 + y2) * (T)0.5 * s), (float)((x2 - x1) * s), (float)((y2 - y1) * s));
 }
 
@@ -76,6 +81,23 @@ dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, in
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rows = 4 + nc;
 
+    // boxes: this CTA's 32 anchors = 128 (anchor, side) pairs, one per thread of warps 0..3
+    if (threadIdx.x < 4 * kDflAnchors) {
+        const int la = threadIdx.x >> 2, side = threadIdx.x & 3;
+        const int a = a0 + la;
+        const unsigned quad_mask = 0xfu << (lane & ~3);
+        if (a < A) {                                     // uniform per quad
+            const HeadLevel& lv = (a >= l2.a0) ? l2 : (a >= l1.a0 ? l1 : l0);
+            const int idx = a - lv.a0;
+            const int y = idx / lv.w, x = idx - y * lv.w;
+            const size_t pix = (size_t)(f * lv.h + y) * lv.w + x;
+            const float4 bx = dfl_box4<PRECISE>(lv, pix, x, y, side, quad_mask);
+            if (side == 0) {
+                stage[0 * 33 + la] = bx.x; stage[1 * 33 + la] = bx.y; stage[2 * 33 + la] = bx.z; stage[3 * 33 + la] = bx.w;
+            }
+        }
+    }
+    // classes: sigmoid, transposed through smem (warp w handles anchors 4w..4w+3)
     for (int i = 0; i < kDflAnchors / 8; ++i) {
         const int la = warp * (kDflAnchors / 8) + i;
         const int a = a0 + la;
@@ -84,12 +106,6 @@ dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, in
         const int idx = a - lv.a0;
         const int y = idx / lv.w, x = idx - y * lv.w;
         const size_t pix = (size_t)(f * lv.h + y) * lv.w + x;
-        // ---- box: 4 sides x 16 bins, 16-lane shuffle softmax
-        const float4 bx = dfl_box<PRECISE>(lv, pix, x, y, lane);
-        if (lane == 0) {
-            stage[0 * 33 + la] = bx.x; stage[1 * 33 + la] = bx.y; stage[2 * 33 + la] = bx.z; stage[3 * 33 + la] = bx.w;
-        }
-        // ---- classes: sigmoid, transposed through smem
         const float* cp = lv.cls + pix * lv.cls_pitch;
         for (int c = lane; c < nc; c += 32) {
             const float z = __ldg(cp + c);
@@ -155,42 +171,128 @@ filter_kernel(const float* __restrict__ raw, int nc, int A, const FrameDesc* __r
 // lanes score the classes (same sigmoid as dfl_decode_kernel), a shuffle reduction finds (max score, lowest class
 // index) == the reference's strict-'>' scan (onnx_engine.cpp:787-796), and ONLY anchors that pass the threshold
 // (:799) pay for the DFL box decode.  Emits the same keys / boxes as filter_kernel, bit for bit.
-template <bool PRECISE>
-__global__ void __launch_bounds__(256)
+template <bool PRECISE, bool STAGED>
+__global__ void __launch_bounds__(128)
 decode_filter_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, int nc, int A, const FrameDesc* __restrict__ descs,
                      float conf_thr, const float* __restrict__ class_weights, uint64_t* __restrict__ keys, int key_pitch,
                      float4* __restrict__ box_by_anchor, uint32_t* __restrict__ cand_count)
 {
+    extern __shared__ float df_sm[];                                // STAGED: [4 warps][32 anchors][nc + 1]
     const int f = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_begin = (blockIdx.x * 8 + warp) * 8;                 // 8 warps x 8 anchors per CTA
-    for (int a = a_begin; a < min(a_begin + 8, A); ++a) {
-        const HeadLevel& lv = (a >= l2.a0) ? l2 : (a >= l1.a0 ? l1 : l0);
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;            // one thread scans the classes of one anchor
+    float best = 0.0f;
+    int best_id = -1;
+    int lx = 0, ly = 0, lvl = 0;
+    size_t pix = 0;
+    if (a < A) {
+        lvl = (a >= l2.a0) ? 2 : (a >= l1.a0 ? 1 : 0);
+        const HeadLevel& lv = lvl == 2 ? l2 : (lvl == 1 ? l1 : l0);
         const int idx = a - lv.a0;
-        const int y = idx / lv.w, x = idx - y * lv.w;
-        const size_t pix = (size_t)(f * lv.h + y) * lv.w + x;
-        const float* cp = lv.cls + pix * lv.cls_pitch;
-        float best = 0.0f;
-        int best_id = -1;
-        for (int c = lane; c < nc; c += 32) {                        // ascending classes per lane: strict '>' keeps the first
-            float s = cls_score<PRECISE>(__ldg(cp + c));
-            if (class_weights) s = __fmul_rn(s, __ldg(class_weights + c));
-            if (s > best) { best = s; best_id = c; }
-        }
+        ly = idx / lv.w; lx = idx - ly * lv.w;
+        pix = (size_t)(f * lv.h + ly) * lv.w + lx;
+    }
+    const float* cp = nullptr;
+    if (a < A) {
+        const HeadLevel& lv = lvl == 2 ? l2 : (lvl == 1 ? l1 : l0);
+        cp = lv.cls + pix * lv.cls_pitch;                            // cls_pitch is a multiple of 4 floats: 16-byte aligned rows
+    }
+    if (STAGED) {
+        // the warp copies its 32 anchors' class rows into shared memory (row stride nc+1: conflict-free per-lane scans)
+        // so every logit crosses L1 exactly once with fully coalesced reads
+        float* wsm = df_sm + (size_t)(threadIdx.x >> 5) * 32 * (nc + 1);
+        const int a_last = a - lane + 31;
+        const int lvl_first = __shfl_sync(0xffffffffu, lvl, 0), lvl_last = __shfl_sync(0xffffffffu, lvl, 31);
+        if (a_last < A && lvl_first == lvl_last) {
+            // common case: 32 anchors of one level = one contiguous run of 32 x cls_pitch floats.  Flat float4 copy,
+            // four independent loads in flight per lane before any store
+            const HeadLevel& lv = lvl_first == 2 ? l2 : (lvl_first == 1 ? l1 : l0);
+            const int pitch = lv.cls_pitch;
+            const float4* src = reinterpret_cast<const float4*>(__shfl_sync(0xffffffffu, (unsigned long long)cp, 0));
+            const int n4 = 8 * pitch;                                  // 32 * pitch / 4
+            for (int i0 = lane; i0 < n4; i0 += 128) {
+                float4 v[4];
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
-            if (oi >= 0 && (ob > best || (ob == best && (best_id < 0 || oi < best_id)))) { best = ob; best_id = oi; }
+                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; v[u] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 32 * u;
+                    if (i < n4) {
+                        const int e = 4 * i, j = e / pitch, c = e - j * pitch;
+                        float* d = wsm + j * (nc + 1) + c;
+                        if (c + 0 < nc) d[0] = v[u].x;
+                        if (c + 1 < nc) d[1] = v[u].y;
+                        if (c + 2 < nc) d[2] = v[u].z;
+                        if (c + 3 < nc) d[3] = v[u].w;
+                    }
+                }
+            }
+        } else {
+            for (int j = 0; j < 32; ++j) {                             // level boundary / tail: row by row
+                const float* rp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)cp, j));
+                if (rp != nullptr)
+                    for (int c = lane; c < nc; c += 32) wsm[j * (nc + 1) + c] = __ldg(rp + c);
+            }
         }
-        if (!(best >= conf_thr && best_id >= 0)) continue;           // warp-uniform
-        const float4 bx = dfl_box<PRECISE>(lv, pix, x, y, lane);
-        if (lane == 0) {
-            const float fw = (float)descs[f].w, fh = (float)descs[f].h;
-            const uint32_t slot = atomicAdd(cand_count + f, 1u);
-            keys[(size_t)f * key_pitch + slot] = make_key(best_id, best, a);
-            box_by_anchor[(size_t)f * A + a] = make_float4(__fdiv_rn(bx.x, fw), __fdiv_rn(bx.y, fh), __fdiv_rn(bx.z, fw), __fdiv_rn(bx.w, fh));
+        __syncwarp();
+        cp = wsm + lane * (nc + 1);
+    }
+    if (a < A) {
+        if (class_weights) {
+            for (int c = 0; c < nc; ++c) {
+                const float s = __fmul_rn(cls_score<PRECISE>(cp[c]), __ldg(class_weights + c));
+                if (s > best) { best = s; best_id = c; }             // strict '>': first maximum wins (onnx_engine.cpp:792)
+            }
+        } else {
+            // the sigmoid is monotone, so only classes whose LOGIT is near the largest one can hold the largest score.
+            // "Near" = within 0.05 of min(zmax, 8): below 8 a logit gap of 0.05 moves the score by >= 1.7e-5, far above
+            // the error of the fast exp; above 8 scores start to collide in fp32 (ties go to the lowest class index),
+            // so every saturated class is scored.  Identical to scoring all nc classes, ~1 sigmoid per anchor.
+            float zmax = -FLT_MAX;
+            for (int c = 0; c < nc; ++c) zmax = fmaxf(zmax, cp[c]);
+            const float zcut = fminf(zmax, 8.0f) - 0.05f;
+            for (int c = 0; c < nc; ++c) {
+                const float z = cp[c];
+                if (z >= zcut) {
+                    const float s = cls_score<PRECISE>(z);
+                    if (s > best) { best = s; best_id = c; }
+                }
+            }
         }
+    }
+    const bool keep = (best >= conf_thr) && (best_id >= 0);         // onnx_engine.cpp:799
+    unsigned todo = __ballot_sync(0xffffffffu, keep);
+    if (todo == 0u) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cand_count + f, (uint32_t)__popc(todo));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned all = todo;
+    // the anchors that pass pay for the DFL box decode: eight at a time, four lanes (one per box side) each
+    const int quad = lane >> 2, side = lane & 3;
+    const unsigned quad_mask = 0xfu << (lane & ~3);
+    while (todo != 0u) {
+        // the quad-th set bit of `todo` is this quad's anchor (if any)
+        unsigned t = todo;
+        for (int i = 0; i < quad; ++i) t &= t - 1u;
+        const bool have = t != 0u;
+        const int src = have ? __ffs(t) - 1 : 0;
+        const int k_lvl = __shfl_sync(0xffffffffu, lvl, src);
+        const int kx = __shfl_sync(0xffffffffu, lx, src), ky = __shfl_sync(0xffffffffu, ly, src);
+        const unsigned long long kpix = __shfl_sync(0xffffffffu, (unsigned long long)pix, src);
+        const float kbest = __shfl_sync(0xffffffffu, best, src);
+        const int kid = __shfl_sync(0xffffffffu, best_id, src);
+        if (have) {
+            const HeadLevel& lv = k_lvl == 2 ? l2 : (k_lvl == 1 ? l1 : l0);
+            const float4 bx = dfl_box4<PRECISE>(lv, (size_t)kpix, kx, ky, side, quad_mask);
+            if (side == 0) {
+                const int ka = a - lane + src;
+                const float fw = (float)descs[f].w, fh = (float)descs[f].h;
+                const uint32_t slot = base + (uint32_t)__popc(all & ((1u << src) - 1u));
+                keys[(size_t)f * key_pitch + slot] = make_key(kid, kbest, ka);
+                box_by_anchor[(size_t)f * A + ka] = make_float4(__fdiv_rn(bx.x, fw), __fdiv_rn(bx.y, fh), __fdiv_rn(bx.z, fw), __fdiv_rn(bx.w, fh));
+            }
+        }
+        for (int i = 0; i < 8 && todo != 0u; ++i) todo &= todo - 1u;     // eight anchors done
     }
 }
 
@@ -463,9 +565,16 @@ int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, 
                              float conf_thr, const float* class_weights, const PostBuffers& pb, bool precise)
 {
     if (A > kMaxAnchors || nc > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "decode_filter: A or nc beyond key range");
-    dim3 grid(ceil_div(A, 64), n);
-    if (precise) decode_filter_kernel<true><<<grid, 256, 0, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
-    else decode_filter_kernel<false><<<grid, 256, 0, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    dim3 grid(ceil_div(A, 128), n);
+    const size_t smem = (size_t)4 * 32 * (nc + 1) * sizeof(float);
+    if (smem <= 48 * 1024) {
+        if (precise) decode_filter_kernel<true, true><<<grid, 128, smem, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+        else decode_filter_kernel<false, true><<<grid, 128, smem, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    } else if (precise) {
+        decode_filter_kernel<true, false><<<grid, 128, 0, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    } else {
+        decode_filter_kernel<false, false><<<grid, 128, 0, st>>>(lv[0], lv[1], lv[2], nc, A, descs, conf_thr, class_weights, pb.keys, pb.key_pitch, pb.box_by_anchor, pb.cand_count);
+    }
     ZL_CUDA(cudaGetLastError());
     return ZL_OK;
 }
