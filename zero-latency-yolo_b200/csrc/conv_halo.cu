@@ -21,6 +21,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "half16.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
@@ -145,6 +147,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // Programmatic dependent launch: let the next kernel's CTAs take this SM as soon as this CTA exits and run their
+    // own prologue (barrier init, TMEM alloc, weight TMA) under this kernel's tail ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
@@ -156,6 +161,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 const int tap = (int)t / p.cchunks, cc = (int)t - tap * p.cchunks;
                 tma_load_2d(&tmap_w, bar_wfull, wbase + t * p.wtile_alloc, tap * p.Cin + cc * p.kc, n_off);
             }
+            // ... but nothing produced by the previous kernel is read (and nothing it may still read is overwritten)
+            // before it has completed: weights and bias above are constants, activations start here
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             uint32_t s = 0, ph = 0;
             for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 const int n = tile / tiles_per_img;
@@ -552,6 +560,8 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     return ZL_OK;
 }
 
+static const bool g_use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
+
 int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
 {
     static thread_local int last_dev = -1;
@@ -573,10 +583,15 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.tmem_cols = o.tmem_cols;
     int grid = o.num_tiles * o.nsplit;
     if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
-    if (o.mode == 9) conv_halo_kernel<9><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
-    else if (o.mode == 2) conv_halo_kernel<2><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
-    else conv_halo_kernel<1><<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_x, o.tmap_y, p);
-    ZL_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)o.smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    if (o.mode == 9) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<9>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    else if (o.mode == 2) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<2>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    else ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<1>, o.tmap_w, o.tmap_x, o.tmap_y, p));
     return ZL_OK;
 }
 
