@@ -152,10 +152,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int tiles_per_img = p.tiles_x * p.tiles_y;
+    bool store_leader = false;                               // set on the one lane per epilogue warp that issues TMA stores
 
     if (warp == 0) {
         // ===== TMA producer: weights once, then one patch per (tile, channel chunk) =====
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(bar_wfull, nwt * p.wtile_bytes);
             for (uint32_t t = 0; t < nwt; ++t) {
                 const int tap = (int)t / p.cchunks, cc = (int)t - tap * p.cchunks;
@@ -207,7 +208,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             for (int cc = 0; cc < p.cchunks; ++cc) {
                 mbar_wait(bar_pfull + 8u * s, ph, 4);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint64_t ad = adesc_base + (uint64_t)(s * patch16);
                     const uint64_t bd = bdesc_base + (uint64_t)((uint32_t)cc * wtile16);
                     const uint32_t nt = (uint32_t)p.nt;                 // accumulator column stride between sub-tiles
@@ -238,6 +239,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int th = row >> 3, tw = row & 7;
         const int nchunk = ntile >> 4;
         const int items = p.sub * nchunk;
+        const bool leader = elect_one();                    // the one lane that owns this warp's TMA-store bulk groups
+        store_leader = leader;
         const uint32_t stage_out = obase + (warp - 2u) * 2u * (uint32_t)p.ostage;   // this warp's two staging blocks ([32 px][16 ch]; 1 KB 16-bit / 2 KB fp32)
         uint32_t nstore = 0;
         uint32_t tl = 0;
@@ -287,7 +290,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                         }
                     }
                     const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
-                    if (nstore >= 2u) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
+                    if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
                     if (p.y_f32) {
                         const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
                         const uint32_t rowb = sbuf + lane * 64u;
@@ -306,7 +309,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (leader) {
                         tma_store_4d(&tmap_y, sbuf, n_off + c0, tx * kTW, (ty * p.sub + j) * kTH + (int)q * 4, n);
                         tma_store_commit();
                     }
@@ -371,11 +374,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             // this warp is done reading the accumulator: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+            if (leader) mbar_arrive(bar_tempty + 8u * acc);
         }
     }
 
-    if (warp >= 2 && lane == 0 && p.y_tma) tma_store_wait_all();     // smem must outlive the bulk stores that read it
+    if (store_leader && p.y_tma) tma_store_wait_all();               // smem must outlive the bulk stores that read it
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);

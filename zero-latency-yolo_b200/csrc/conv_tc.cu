@@ -95,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         // ===== TMA producer =====
         // K-blocks run channel-chunk-major, tap-minor — the same accumulation order as the persistent kernel
         // (conv_halo.cu), so a layer gives bit-identical results whichever kernel the batch size selects.
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t tx = p.b_bytes + (p.a_tma ? p.a_bytes : 0u);
             const int taps = p.k * p.k;
             uint32_t s = 0, ph = 0;
@@ -125,7 +125,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         for (int kb = 0; kb < p.nkb; ++kb) {
             mbar_wait(bar_full + 8u * s, ph);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint64_t adesc = adesc0 + (uint64_t)(s * stage16);
                 const uint64_t bdesc = bdesc0 + (uint64_t)(s * stage16);
                 // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-B units
