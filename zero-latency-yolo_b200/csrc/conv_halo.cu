@@ -504,7 +504,6 @@ static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int
         if (pl->tiles * nsplit < num_sms && nt > 64) continue;
         int stages = (int)((budget - fixed) / pl->patch_alloc);
         if (stages > kMaxPatchStages) stages = kMaxPatchStages;
-        if (stages > 3 * pl->cchunks) stages = 3 * pl->cchunks;
         if (stages < 2) stages = 2;
         pl->nsplit = nsplit; pl->nt = nt; pl->stages = stages;
         pl->wtile_bytes = wtile_bytes; pl->wtile_alloc = wtile_alloc;
