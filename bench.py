@@ -207,6 +207,7 @@ def run_ours(args, rank, local_rank, world):
     import zlb200
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -280,7 +281,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- per-kernel roofline (rank 0): same pass, un-captured, one CUDA-event pair per kernel
     prof = eng.profile(0, 3)
-    tc = [p for p in prof if p["kind"] == 1]
+    tc = [p for p in prof if p["kind"] in (1, 9)]       # tcgen05 conv kernels: persistent (9) and fallback (1)
     tc_ms = sum(p["ms"] for p in tc)
     tc_flops = sum(p["flops"] for p in tc)
     tc_bytes = sum(p["bytes"] for p in tc)
@@ -291,7 +292,7 @@ def run_ours(args, rank, local_rank, world):
     ai = tc_flops / tc_bytes if tc_bytes else 0.0
     hbm_bound = ai < ridge
     roofline = {
-        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % len(tc),
+        "kernel": "conv_halo_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convs, %d launches/step)" % len(tc),
         "bound": "hbm" if hbm_bound else "tensor",
         "achieved": gbs if hbm_bound else tflops,
         "peak": peaks["hbm"] if hbm_bound else peaks["tf_sust"],

@@ -340,7 +340,7 @@ def test_resident_bench_entry_points(built_lib, model_n4):
     assert ms > 0 and launches > 4 * 60 and dets == sum(len(d) for d in e.infer(frames))
     prof = e.profile(0, 2)
     assert len(prof) > 60 and all(p["ms"] >= 0 for p in prof)
-    assert any(p["kind"] == 1 for p in prof), "tcgen05 conv kernels must be on the bf16 path"
+    assert any(p["kind"] in (1, 9) for p in prof), "tcgen05 conv kernels must be on the 16-bit path"
     pms, pbytes = e.bench_preprocess(640, 640, 8, 5)
     assert pms > 0 and pbytes > 0
     e.close()
