@@ -230,16 +230,42 @@ def test_fused_preprocess_layer0_equals_unfused(built_lib, model_n4):
     outs = []
     for flag in ("0", "1"):
         os.environ["ZL_FUSE_PRE"] = flag
+        os.environ["ZL_DISABLE_STEM"] = "1"          # compare the two CUDA-core variants of layer 0
         try:
             e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP16, max_batch=4, max_frame=(800, 600))
         finally:
             os.environ.pop("ZL_FUSE_PRE", None)
+            os.environ.pop("ZL_DISABLE_STEM", None)
         e.load_weights_blob(blob)
         outs.append((e.forward_raw(frames), e.infer(frames)))
         e.close()
     assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
     for a, b in zip(outs[0][1], outs[1][1]):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_tensor_core_stem_matches_cuda_core_layer0(built_lib, model_n4):
+    """Default 16-bit path: preprocessing + layer 0 run as one tcgen05 kernel (16-bit weights).  It must agree with the
+    CUDA-core layer 0 (fp32 weights) to 16-bit accuracy on identity-size and stretched frames, for every tile shape."""
+    import os
+    import zlb200
+    tensors, blob = model_n4
+    frames = list(synth.frames_structured(3, 416, 416, seed=41)) + [synth.frames_noise(1, 600, 800, seed=42)[0]]
+    raws = []
+    for flag in ("0", "1"):
+        os.environ["ZL_DISABLE_STEM"] = flag
+        try:
+            e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP16, max_batch=4, max_frame=(800, 600))
+        finally:
+            os.environ.pop("ZL_DISABLE_STEM", None)
+        e.load_weights_blob(blob)
+        raws.append(e.forward_raw(frames))
+        one = e.forward_raw(frames[:1])          # batch of one: same bits as inside the batch of four
+        assert np.array_equal(one[0].view(np.uint32), raws[-1][0].view(np.uint32))
+        e.close()
+    d = np.abs(raws[0] - raws[1])
+    assert d[:, 4:].max() < 0.05 and np.median(d[:, 4:]) < 1e-4, (d[:, 4:].max(), np.median(d[:, 4:]))
+    assert np.median(d[:, :4]) < 0.05, np.median(d[:, :4])
 
 
 def test_bf16_graph_equals_direct_launch(built_lib, model_n4):

@@ -164,3 +164,15 @@ def test_postprocess_matches_pure_python():
                 removed.add(j)
     assert list(anchors) == out
     assert np.array_equal(kept["class_id"], cls[out])
+
+
+def test_reciprocal_normalisation_equals_division_after_16bit_rounding():
+    """The tensor-core stem evaluates x/255 as x*(1/255).  In fp32 the two differ for 126 byte values, but after rounding
+    to fp16 or bf16 (what the 16-bit modes store) they agree for all 256, so the stem feeds layer 0 exactly the
+    reference's preprocessed values rounded once."""
+    import torch
+    u = np.arange(256, dtype=np.float32)
+    a, b = u / np.float32(255.0), u * np.float32(1.0 / 255.0)
+    assert not np.array_equal(a, b)
+    assert np.array_equal(a.astype(np.float16), b.astype(np.float16))
+    assert bool((torch.tensor(a).to(torch.bfloat16) == torch.tensor(b).to(torch.bfloat16)).all())

@@ -87,6 +87,7 @@ int32_t Engine::init()
     num_sms = prop.multiProcessorCount;
     if (const char* ev = getenv("ZL_DISABLE_HALO")) use_halo = !(ev[0] == '1');
     if (const char* ev = getenv("ZL_FUSE_PRE")) fuse_pre = (ev[0] == '1');
+    if (const char* ev = getenv("ZL_DISABLE_STEM")) use_stem = !(ev[0] == '1');
     ZL_TRY(build_model_def());
     num_anchors = 0;
     for (int s : {8, 16, 32}) num_anchors += (cfg.model_h / s) * (cfg.model_w / s);
@@ -213,6 +214,19 @@ int32_t Engine::load_weights(const void* blob, size_t len)
                             ws[((size_t)(r * s.k + q) * s.cin + ci) * cw->cout_pad + o] = W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q];
             ZL_CUDA(cudaMalloc(&cw->w_simt, ws.size() * 4));
             ZL_CUDA(cudaMemcpy(cw->w_simt, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
+        }
+        if (bf16 && s.cin == 3) {
+            // stem: K = 27 padded to 32, k = (r*3 + s)*3 + channel, for the tensor-core first layer
+            std::vector<uint16_t> wt((size_t)cw->cout_pad * 32, 0);
+            for (int o = 0; o < s.cout; ++o)
+                for (int ci = 0; ci < 3; ++ci)
+                    for (int r = 0; r < 3; ++r)
+                        for (int q = 0; q < 3; ++q) {
+                            const float v = W.data[(((size_t)o * 3 + ci) * 3 + r) * 3 + q];
+                            wt[(size_t)o * 32 + (r * 3 + q) * 3 + ci] = f16 ? f2h(v) : f2bf(v);
+                        }
+            ZL_CUDA(cudaMalloc(&cw->w_tc, wt.size() * 2));
+            ZL_CUDA(cudaMemcpy(cw->w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         }
         if (bf16 && s.cin != 3) {
             std::vector<uint16_t> wt((size_t)cw->cout_pad * cw->ktot, 0);
@@ -402,7 +416,13 @@ int32_t Engine::build_ops(Lane& L, int B)
     };
     const int* c = md.c;
 
-    if (bf16 && fuse_pre) {
+    if (bf16 && use_halo && use_stem && conv_by_name.count("model.0.conv") && conv_by_name["model.0.conv"]->cout_pad <= 64) {
+        // 16-bit modes: preprocessing + layer 0 in ONE tensor-core kernel (the preprocessed image is never written)
+        Op op; op.kind = Op::CONV_HALO; op.name = "preprocess+model.0.conv"; op.w = conv_by_name["model.0.conv"]; op.y = buf("A0");
+        ZL_TRY(conv_stem_prepare(*op.w, L.staging, L.d_descs, cfg.model_w, cfg.model_h, op.y, num_sms, &op.halo));
+        op.flops = op.halo.flops; op.bytes = op.halo.bytes;
+        ops.push_back(op);
+    } else if (bf16 && fuse_pre) {
         // 16-bit modes: preprocessing is fused into layer 0 (the preprocessed image is never written)
         auto it0 = conv_by_name.find("model.0.conv");
         if (it0 == conv_by_name.end()) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "no weights for model.0.conv");
@@ -777,8 +797,9 @@ int32_t Engine::upload_resident(int set, const uint8_t* const* frames, const int
         cudaFree(L.staging);
         L.staging = ns;
         L.staging_slots = (size_t)cfg.max_batch * 5;
-        for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);   // graphs captured the old staging pointer
+        for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);   // graphs and op lists captured the old staging pointer
         L.graphs.clear();
+        L.ops.clear();
     }
     FrameDesc* hd = L.h_descs + (size_t)cfg.max_batch * (1 + set);
     for (int i = 0; i < n; ++i) {

@@ -76,8 +76,14 @@ struct ConvHaloOp {
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
     int32_t smem_bytes;
+    const uint8_t* staging;        // stem (mode 0): u8 frames + descriptors + model input size
+    const FrameDesc* descs;
+    int32_t mw, mh;
     double flops, bytes;
 };
+// P1 + layer 0 fused on the tensor cores (conv_halo.cu, MODE 0).
+int32_t conv_stem_prepare(const ConvWeights& w, const uint8_t* staging, const FrameDesc* descs, int32_t mw, int32_t mh,
+                          const View& y, int num_sms, ConvHaloOp* op);
 bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int num_sms, int* work_units);
 int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, int num_sms, ConvHaloOp* op);
 int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms);
