@@ -118,7 +118,8 @@ GATES = {
 def _check_16bit(e, tensors, scale, nc, frames, mw, mh, mode):
     g = dict(GATES[mode])
     if scale == "m":
-        g["frac99"] = min(g["frac99"], 0.90)      # 83 convs deep: measured 94.7 % on B200 (fp16)
+        g["frac99"] = min(g["frac99"], 0.90)      # 83 convs deep, ~70 % of anchors are candidates: measured 94.7 % / 95.3 % on B200 (fp16)
+        g["frac90"] = min(g["frac90"], 0.93)
     raw_ref, det_ref = oracle_pipeline(tensors, scale, nc, frames, mw, mh)
     dets = e.infer(frames)
     raw = e.forward_raw(frames)
@@ -270,8 +271,9 @@ def test_fused_preprocess_layer0_equals_unfused(built_lib, model_n4):
 
 
 def test_tensor_core_stem_matches_cuda_core_layer0(built_lib, model_n4):
-    """Default 16-bit path: preprocessing + layer 0 run as one tcgen05 kernel (16-bit weights).  It must agree with the
-    CUDA-core layer 0 (fp32 weights) to 16-bit accuracy on identity-size and stretched frames, for every tile shape."""
+    """Default 16-bit path: the preprocess kernel writes a space-to-depth image and layer 0 runs on it as a 2x2 tcgen05 conv
+    (16-bit weights).  It must agree with the CUDA-core layer 0 (fp32 weights) to 16-bit accuracy on identity-size and
+    stretched frames."""
     import os
     import zlb200
     tensors, blob = model_n4

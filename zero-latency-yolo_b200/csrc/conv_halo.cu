@@ -38,13 +38,13 @@ constexpr int kTW = 8, kTH = 16;            // one MMA sub-tile: 8 (w) x 16 (h) 
 // MODE == 2: 3x3 stride-2 conv.  The input region of a tile is fetched as FOUR parity sub-patches (even/odd rows x
 //            even/odd columns) by TMA loads with element stride 2; tap (r,s) then reads sub-patch
 //            (r != 1, s != 1) shifted by (r >= 1, s >= 1) — the same shifted-view trick, patch width 9.
-// MODE == 0: the stem — preprocessing (P1) + layer 0 (3->c 3x3 s2) fused.  Four extra producer warps sample the u8 BGR
-//            frame with the reference's nearest-stretch rule, round x/255 to the 16-bit format and write the im2col
-//            row of each output pixel (27 values, zero-padded to K = 32) straight into the swizzled A tile.
+// MODE == 4: layer 0 (3->c 3x3 s2) as a 2x2 stride-1 conv over the SPACE-TO-DEPTH image the preprocess kernel writes
+//            ([B, H/2, W/2, 16] = the 2x2 pixel block's 12 values + 4 zeros): taps at offsets {-1, 0}^2, patch = tile
+//            + one halo row/column on the top/left, so the first layer runs on TMA + tcgen05 like every other conv.
 template <int MODE> struct Geo {
-    static constexpr int TAPS = (MODE == 1 || MODE == 0) ? 1 : 9;
-    static constexpr int PW = MODE == 9 ? kTW + 2 : (MODE == 2 ? kTW + 1 : kTW);
-    static constexpr int HALO = MODE == 9 ? 1 : 0;
+    static constexpr int TAPS = MODE == 1 ? 1 : (MODE == 4 ? 4 : 9);
+    static constexpr int PW = MODE == 9 ? kTW + 2 : ((MODE == 2 || MODE == 4) ? kTW + 1 : kTW);
+    static constexpr int HALO = (MODE == 9 || MODE == 4) ? 1 : 0;
     static constexpr int NPATCH = MODE == 2 ? 4 : 1;
 };
 constexpr int kEpiWarps = 16;                // 4 per TMEM lane quarter, each owning a share of the accumulator columns
@@ -60,10 +60,6 @@ struct HaloParams {
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
-    // stem (MODE 0) only
-    const uint8_t* staging;
-    const FrameDesc* descs;
-    int32_t mw, mh;
 };
 
 // Issue all MMAs of one (tile, channel chunk): 9 taps x SUB sub-tiles x KSTEPS k-steps, fully unrolled.
@@ -81,6 +77,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
         const int r = tap / 3, sf = tap % 3;
         uint32_t aoff = 0u;
         if (MODE == 9) aoff = (uint32_t)(r * kPW + sf) * swz16;
+        if (MODE == 4) aoff = (uint32_t)((tap >> 1) * kPW + (tap & 1)) * swz16;
         if (MODE == 2) aoff = (uint32_t)((r != 1 ? 2 : 0) + (sf != 1 ? 1 : 0)) * subpatch16 + (uint32_t)((r >= 1 ? kPW : 0) + (sf >= 1 ? 1 : 0)) * swz16;
         const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)tap * btap_stride16);
 #pragma unroll
@@ -92,64 +89,6 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
             }
         }
     }
-}
-
-// Stem (MODE 0): build ONE im2col row of layer 0 — preProcess (onnx_engine.cpp:649-700: nearest stretch, BGR->RGB,
-// /255) rounded to the 16-bit format, 27 values zero-padded to K = 32 — and store it into the 64-byte-swizzled A tile.
-// x/255 is evaluated as x * (1/255): after rounding to fp16 or bf16 the two agree for all 256 byte values (checked
-// exhaustively, tests/test_oracle_kat.py), so the tile holds exactly the reference's preprocessed values.
-// `row` = A row inside the stage buffer, (oy, ox) = its output pixel.
-struct StemRow { uint32_t b[27]; uint32_t okmask; };      // 27 sampled bytes (R,G,B per tap) + validity bit per tap
-
-__device__ __forceinline__ void stem_load_row(const HaloParams& p, const FrameDesc& d, int oy, int ox, StemRow& sr)
-{
-    sr.okmask = 0u;
-    if (!(oy < p.H && ox < p.W && d.w > 0 && d.h > 0)) return;
-    const uint8_t* __restrict__ img = p.staging + d.offset;
-    const float scale_w = __fdiv_rn((float)d.w, (float)p.mw);
-    const float scale_h = __fdiv_rn((float)d.h, (float)p.mh);
-    int so[3];                                            // source byte offset of the three columns, -1 = padding
-    const uint8_t* rp[3];                                 // the three source rows, nullptr = padding
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const int mx = 2 * ox - 1 + q, my = 2 * oy - 1 + q;
-        so[q] = (mx >= 0 && mx < p.mw) ? min(__float2int_rz(__fmul_rn((float)mx, scale_w)), d.w - 1) * 3 : -1;
-        rp[q] = (my >= 0 && my < p.mh) ? img + (size_t)min(__float2int_rz(__fmul_rn((float)my, scale_h)), d.h - 1) * d.w * 3 : nullptr;
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const bool ok = rp[r] != nullptr && so[q] >= 0;
-            const uint8_t* px = ok ? rp[r] + so[q] : img;
-            sr.b[(r * 3 + q) * 3 + 0] = __ldg(px + 2);        // R = byte 2 (the reference reads 2-c)
-            sr.b[(r * 3 + q) * 3 + 1] = __ldg(px + 1);
-            sr.b[(r * 3 + q) * 3 + 2] = __ldg(px);
-            if (ok) sr.okmask |= 1u << (r * 3 + q);
-        }
-    }
-}
-
-__device__ __forceinline__ void stem_store_row(const HaloParams& p, const StemRow& sr, uint32_t stage_base, uint32_t row)
-{
-    float v[28];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const bool ok = (sr.okmask >> t) & 1u;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[t * 3 + c] = ok ? (float)sr.b[t * 3 + c] * (1.0f / 255.0f) : 0.0f;
-    }
-    v[27] = 0.0f;
-    uint32_t kv[16];                                          // 32 halves: k = (r*3+s)*3 + ch, ch = R,G,B; 27..31 = 0
-#pragma unroll
-    for (int i = 0; i < 14; ++i) kv[i] = pack2_16(v[2 * i], v[2 * i + 1], p.f16);
-    kv[14] = 0u; kv[15] = 0u;
-    const uint32_t rowb = stage_base + row * 64u;
-    const uint32_t xr = (row >> 1) & 3u;                       // 64-B swizzle: chunk ^= address bits 7..8
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)c4) ^ xr) << 4)), "r"(kv[4 * c4]), "r"(kv[4 * c4 + 1]),
-                     "r"(kv[4 * c4 + 2]), "r"(kv[4 * c4 + 3]) : "memory");
 }
 
 template <int MODE>
@@ -189,7 +128,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(bar_pfull + 8u * s, MODE == 0 ? (uint32_t)(128 * p.sub) : 1u);   // stem: one arrival per A row
+            mbar_init(bar_pfull + 8u * s, 1u);
             mbar_init(bar_pempty + 8u * s, 1u);
         }
         mbar_init(bar_wfull, 1u);
@@ -199,7 +138,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_w);
-        if (MODE != 0) tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_x);
         if (p.y_tma) tma_prefetch_desc(&tmap_y);
     }
     if (warp == 1) {
@@ -231,7 +170,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             // before it has completed: weights and bias above are constants, activations start here
             asm volatile("griddepcontrol.wait;" ::: "memory");
             uint32_t s = 0, ph = 0;
-            for (int tile = tile0; MODE != 0 && tile < p.num_tiles; tile += tile_step) {
+            for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 const int n = tile / tiles_per_img;
                 const int rem = tile - n * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -309,49 +248,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const uint32_t stage_out = obase + (warp - 2u) * 2u * (uint32_t)p.ostage;   // this warp's two staging blocks ([32 px][16 ch]; 1 KB 16-bit / 2 KB fp32)
         uint32_t nstore = 0;
         uint32_t tl = 0;
-        // stem: these 16 warps also PRODUCE the A tiles (one im2col row per thread), two tiles ahead of the epilogue
-        const int e_row = (int)threadIdx.x - 64;                        // 0..511: A row this thread builds
-        const bool e_prod = MODE == 0 && e_row < 128 * p.sub;
-        uint32_t ps = 0, pph = 0;
-        int ptile = tile0;
-        StemRow sr;
-        bool sr_pending = false;
-        auto produce_load = [&]() {                                     // issue the 27 byte loads of this thread's next row
-            sr_pending = false;
-            if (MODE == 0 && ptile < p.num_tiles) {
-                if (e_prod) {
-                    const int pn = ptile / tiles_per_img;
-                    const int prem = ptile - pn * tiles_per_img;
-                    const int pty = prem / p.tiles_x, ptx = prem - pty * p.tiles_x;
-                    const int j = e_row >> 7, t = e_row & 127;
-                    stem_load_row(p, p.descs[pn], (pty * p.sub + j) * kTH + (t >> 3), ptx * kTW + (t & 7), sr);
-                }
-                sr_pending = true;
-            }
-        };
-        auto produce_store = [&]() {                                    // ... and, later, convert + store + arrive
-            if (MODE == 0 && sr_pending) {
-                if (e_prod) {
-                    mbar_wait(bar_pempty + 8u * ps, pph ^ 1u, 6);
-                    stem_store_row(p, sr, pbase + ps * p.patch_alloc, (uint32_t)e_row);
-                    fence_proxy_async();
-                    mbar_arrive(bar_pfull + 8u * ps);
-                }
-                if (++ps == (uint32_t)stages) { ps = 0; pph ^= 1u; }
-                ptile += tile_step;
-            }
-        };
-        if (MODE == 0) {
-            asm volatile("griddepcontrol.wait;" ::: "memory");          // the frames were copied by the preceding stream work
-            for (int k = 0; k < 3; ++k) { produce_load(); produce_store(); }
-        }
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
             const int n = tile / tiles_per_img;
             const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int ox = tx * kTW + tw;
-            produce_load();                                             // stem: loads of the A row three tiles ahead fly during this epilogue
             mbar_wait(bar_tfull + 8u * acc, aph, 5);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (p.tmem_cols >> 1);
@@ -477,7 +379,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (leader) mbar_arrive(bar_tempty + 8u * acc);
-            produce_store();                                            // stem only
         }
     }
 
@@ -665,43 +566,44 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     return ZL_OK;
 }
 
-int32_t conv_stem_prepare(const ConvWeights& w, const uint8_t* staging, const FrameDesc* descs, int32_t mw, int32_t mh,
-                          const View& y, int num_sms, ConvHaloOp* op)
+// Layer 0 on the space-to-depth image (MODE 4).  x = [B, H/2, W/2, 16] 16-bit written by the preprocess kernel
+// (PRE_S2D16), w.w_tc = [cout_pad][4 taps x 16] (engine.cpp builds it from the 3x3 stride-2 filter).
+int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int num_sms, ConvHaloOp* op)
 {
     (void)num_sms;
-    if (w.cin != 3 || w.k != 3 || w.stride != 2 || !w.w_tc || !y.is16() || (mw & 1) || (mh & 1) || w.cout_pad > 64)
-        ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_stem: expects the 3->c 3x3 s2 first layer, 16-bit output, c <= 64");
-    if (y.h != mh / 2 || y.w != mw / 2 || y.c != w.cout) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_stem: output view mismatch");
+    if (w.cin != 3 || w.k != 3 || w.stride != 2 || !w.w_tc || !x.is16() || y.dtype != x.dtype || x.c != 16 || x.pitch != 16 || w.cout_pad > 128)
+        ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_s2d: expects the 3->c 3x3 s2 first layer on the 16-channel space-to-depth image");
+    if (y.h != x.h || y.w != x.w || y.n != x.n || y.c != w.cout) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_s2d: view mismatch");
     ConvHaloOp& o = *op;
     o = ConvHaloOp{};
-    o.taps = 1; o.mode = 0;
+    o.taps = 4; o.mode = 4;
     o.y = y.ptr; o.res = nullptr; o.bias = w.bias;
-    o.N = y.n; o.H = y.h; o.W = y.w; o.Cin = 32; o.Cout = w.cout; o.ntile = w.cout_pad;
+    o.N = y.n; o.H = y.h; o.W = y.w; o.Cin = 16; o.Cout = w.cout; o.ntile = w.cout_pad;
     o.ypitch = y.pitch; o.rpitch = 0; o.y_f32 = 0; o.f16 = y.dtype == DT_F16 ? 1 : 0; o.act = w.act;
     o.y_vec = 1; o.r_vec = 0;
-    o.kc = 32; o.cchunks = 1; o.nsplit = 1; o.nt = w.cout_pad;
+    o.kc = 16; o.cchunks = 1; o.nsplit = 1; o.nt = w.cout_pad;
     o.sub = halo_sub(w, y.h);
     o.tiles_x = ceil_div(y.w, kTW); o.tiles_y = ceil_div(y.h, kTH * o.sub);
     o.num_tiles = o.tiles_x * o.tiles_y * y.n;
-    o.wtile_bytes = (uint32_t)o.nt * 64u; o.wtile_alloc = (o.wtile_bytes + 1023u) & ~1023u;
-    o.patch_bytes = 128u * o.sub * 64u; o.subpatch_alloc = o.patch_bytes; o.patch_alloc = o.patch_bytes;      // one A tile per stage
-    const uint32_t fixed = 3072u + o.wtile_alloc + (uint32_t)kEpiWarps * 2048u;
+    o.wtile_bytes = (uint32_t)o.nt * 32u; o.wtile_alloc = (o.wtile_bytes + 1023u) & ~1023u;
+    o.patch_bytes = (uint32_t)(kTW + 1) * (kTH * o.sub + 1) * 32u;
+    o.subpatch_alloc = (o.patch_bytes + 1023u) & ~1023u; o.patch_alloc = o.subpatch_alloc;
+    const uint32_t fixed = 3072u + 4u * o.wtile_alloc + (uint32_t)kEpiWarps * 2048u;
     int stages = (int)((227u * 1024u - fixed) / o.patch_alloc);
-    if (stages > 6) stages = 6;
+    if (stages > kMaxPatchStages) stages = kMaxPatchStages;
     o.stages = stages;
     o.smem_bytes = (int)(fixed + (uint32_t)stages * o.patch_alloc);
     o.ostage = 1024;
     int cols = 32;
     while (cols < 2 * o.sub * o.nt) cols <<= 1;
     o.tmem_cols = cols;
-    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, 32, (uint64_t)w.cout_pad, 64, 32, o.nt, 64, o.f16));
-    o.tmap_x = o.tmap_w;
+    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, 64, (uint64_t)w.cout_pad, 128, 16, o.nt, 32, o.f16));
+    ZL_TRY(make_tmap_nhwc(&o.tmap_x, x, 16, 32, o.f16, kTW + 1, kTH * o.sub + 1, 1));
     o.y_tma = ((y.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
-    if (!o.y_tma) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_stem: output must be 16-byte aligned");
+    if (!o.y_tma) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_s2d: output must be 16-byte aligned");
     ZL_TRY(make_tmap_out(&o.tmap_y, y, o.f16));
-    o.staging = staging; o.descs = descs; o.mw = mw; o.mh = mh;
     o.flops = 2.0 * (double)y.pixels() * w.cout * 27;
-    o.bytes = (double)y.n * mw * mh * 3 + (double)y.pixels() * w.cout * 2;
+    o.bytes = (double)x.pixels() * 32 + (double)y.pixels() * w.cout * 2;
     return ZL_OK;
 }
 
@@ -716,7 +618,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
         ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         last_dev = dev;
     }
     HaloParams p;
@@ -727,7 +629,6 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
     p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc;
     p.tmem_cols = o.tmem_cols;
-    p.staging = o.staging; p.descs = o.descs; p.mw = o.mw; p.mh = o.mh;
     int grid = o.num_tiles * o.nsplit;
     if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
     cudaLaunchConfig_t cfg{};
@@ -736,7 +637,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    if (o.mode == 0) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<0>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    if (o.mode == 4) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<4>, o.tmap_w, o.tmap_x, o.tmap_y, p));
     else if (o.mode == 9) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<9>, o.tmap_w, o.tmap_x, o.tmap_y, p));
     else if (o.mode == 2) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<2>, o.tmap_w, o.tmap_x, o.tmap_y, p));
     else ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<1>, o.tmap_w, o.tmap_x, o.tmap_y, p));

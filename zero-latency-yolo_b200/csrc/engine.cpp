@@ -216,14 +216,18 @@ int32_t Engine::load_weights(const void* blob, size_t len)
             ZL_CUDA(cudaMemcpy(cw->w_simt, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
         }
         if (bf16 && s.cin == 3) {
-            // stem: K = 27 padded to 32, k = (r*3 + s)*3 + channel, for the tensor-core first layer
-            std::vector<uint16_t> wt((size_t)cw->cout_pad * 32, 0);
+            // tensor-core first layer on the space-to-depth image: the 3x3 stride-2 filter becomes a 2x2 filter over
+            // 2x2 pixel blocks.  K = 4 taps x 16: k = (ty*2+tx)*16 + (dy*2+dx)*3 + channel, where block tap (ty,tx) sits at
+            // block offset (ty-1, tx-1) and filter row r = 2*ty + dy - 1, column q = 2*tx + dx - 1 (outside 0..2 -> 0).
+            std::vector<uint16_t> wt((size_t)cw->cout_pad * 64, 0);
             for (int o = 0; o < s.cout; ++o)
                 for (int ci = 0; ci < 3; ++ci)
-                    for (int r = 0; r < 3; ++r)
-                        for (int q = 0; q < 3; ++q) {
+                    for (int ty = 0; ty < 2; ++ty) for (int dy = 0; dy < 2; ++dy)
+                        for (int tx = 0; tx < 2; ++tx) for (int dx = 0; dx < 2; ++dx) {
+                            const int r = 2 * ty + dy - 1, q = 2 * tx + dx - 1;
+                            if (r < 0 || q < 0) continue;
                             const float v = W.data[(((size_t)o * 3 + ci) * 3 + r) * 3 + q];
-                            wt[(size_t)o * 32 + (r * 3 + q) * 3 + ci] = f16 ? f2h(v) : f2bf(v);
+                            wt[(size_t)o * 64 + (ty * 2 + tx) * 16 + (dy * 2 + dx) * 3 + ci] = f16 ? f2h(v) : f2bf(v);
                         }
             ZL_CUDA(cudaMalloc(&cw->w_tc, wt.size() * 2));
             ZL_CUDA(cudaMemcpy(cw->w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
@@ -271,6 +275,7 @@ int32_t Engine::alloc_lane(Lane& L)
     auto add = [&](const std::string& n, int h, int w, int c, int dt) { reqs.push_back({n, h, w, c, dt}); };
     const int* c = md.c;
     add("X0", H, W, 4, adt);
+    if (adt != DT_F32) add("X0S", H / 2, W / 2, 16, adt);       // space-to-depth image for the tensor-core first layer
     add("A0", H / 2, W / 2, c[0], adt);
     add("A1", H / 4, W / 4, c[1], adt);
     add("CAT2", H / 4, W / 4, (2 + md.n[0]) * c[1] / 2, adt);  add("T2", H / 4, W / 4, c[1] / 2, adt);  add("A2", H / 4, W / 4, c[1], adt);
@@ -417,9 +422,12 @@ int32_t Engine::build_ops(Lane& L, int B)
     const int* c = md.c;
 
     if (bf16 && use_halo && use_stem && conv_by_name.count("model.0.conv") && conv_by_name["model.0.conv"]->cout_pad <= 64) {
-        // 16-bit modes: preprocessing + layer 0 in ONE tensor-core kernel (the preprocessed image is never written)
-        Op op; op.kind = Op::CONV_HALO; op.name = "preprocess+model.0.conv"; op.w = conv_by_name["model.0.conv"]; op.y = buf("A0");
-        ZL_TRY(conv_stem_prepare(*op.w, L.staging, L.d_descs, cfg.model_w, cfg.model_h, op.y, num_sms, &op.halo));
+        // 16-bit modes: the preprocess kernel writes the space-to-depth image and layer 0 runs as a 2x2 conv on it
+        // through the persistent TMA + tcgen05 kernel, like every other layer
+        { Op op; op.kind = Op::PRE; op.name = "preprocess"; op.y = buf("X0S");
+          op.bytes = (double)B * cfg.model_w * cfg.model_h * (3 + 8); ops.push_back(op); }
+        Op op; op.kind = Op::CONV_HALO; op.name = "model.0.conv"; op.w = conv_by_name["model.0.conv"]; op.x = buf("X0S"); op.y = buf("A0");
+        ZL_TRY(conv_s2d_prepare(*op.w, op.x, op.y, num_sms, &op.halo));
         op.flops = op.halo.flops; op.bytes = op.halo.bytes;
         ops.push_back(op);
     } else if (bf16 && fuse_pre) {
@@ -500,6 +508,7 @@ int32_t Engine::launch_op(Lane& L, int B, const Op& op)
     const bool f16 = cfg.precision == ZL_PRECISION_FP16;
     switch (op.kind) {
         case Op::PRE:
+            if (op.y.c == 16) return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, f16 ? PRE_S2D16_F16 : PRE_S2D16_BF16, op.y.ptr);
             return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr);
         case Op::CONV_TC: return conv_tc_launch(st, op.tc);
         case Op::CONV_HALO: return conv_halo_launch(st, op.halo, num_sms);

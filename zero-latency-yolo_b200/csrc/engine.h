@@ -111,7 +111,7 @@ public:
     int num_anchors = 0;
     int num_sms = 148;
     bool use_halo = true;
-    bool use_stem = true;      // P1 + layer 0 fused on tensor cores
+    bool use_stem = true;      // layer 0 on tensor cores (2x2 conv over the space-to-depth image the preprocess kernel writes)
     bool fuse_pre = false;     // P1 fused into layer 0 (bit-identical, measured slower than the two-kernel path: scattered byte loads)
     bool weights_loaded = false;
 

@@ -24,7 +24,9 @@ enum PreLayout : int32_t {
     PRE_NCHW_F32 = 0,    // [n,3,mh,mw] fp32 planar: the tensor the reference feeds ORT (onnx_engine.cpp:560)
     PRE_NHWC4_F32 = 1,   // [n,mh,mw,4] fp32 (R,G,B,0): input of the fp32 conv path
     PRE_NHWC4_BF16 = 2,  // [n,mh,mw,4] bf16 (R,G,B,0): input of the bf16 conv path
-    PRE_NHWC4_F16 = 3    // same, IEEE half
+    PRE_NHWC4_F16 = 3,   // same, IEEE half
+    PRE_S2D16_BF16 = 4,  // [n,mh/2,mw/2,16] bf16: the 2x2 pixel block (dy,dx) x (R,G,B) = 12 values + 4 zeros (layer 0 on tensor cores)
+    PRE_S2D16_F16 = 5
 };
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
                           int32_t mw, int32_t mh, int32_t layout, void* out);
@@ -76,14 +78,10 @@ struct ConvHaloOp {
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
     int32_t smem_bytes;
-    const uint8_t* staging;        // stem (mode 0): u8 frames + descriptors + model input size
-    const FrameDesc* descs;
-    int32_t mw, mh;
     double flops, bytes;
 };
-// P1 + layer 0 fused on the tensor cores (conv_halo.cu, MODE 0).
-int32_t conv_stem_prepare(const ConvWeights& w, const uint8_t* staging, const FrameDesc* descs, int32_t mw, int32_t mh,
-                          const View& y, int num_sms, ConvHaloOp* op);
+// Layer 0 as a 2x2 conv over the space-to-depth image written by the preprocess kernel (conv_halo.cu, MODE 4).
+int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int num_sms, ConvHaloOp* op);
 bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int num_sms, int* work_units);
 int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, int num_sms, ConvHaloOp* op);
 int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms);

@@ -81,12 +81,58 @@ preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restri
     }
 }
 
+// Space-to-depth variant for the tensor-core first layer: one thread = one 2x2 block of model pixels -> 16 halves
+// (k = (dy*2+dx)*3 + channel, channels R,G,B; 12..15 = 0), one 32-byte store.  Same sampling and rounding as above.
+template <bool F16>
+__global__ void __launch_bounds__(256)
+preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs, int mw, int mh, uint4* __restrict__ out)
+{
+    const int f = blockIdx.y;
+    const int W2 = mw >> 1, H2 = mh >> 1;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= W2 * H2) return;
+    const FrameDesc d = descs[f];
+    if (d.w <= 0 || d.h <= 0) return;
+    const int Y = item / W2, X = item - Y * W2;
+    const uint8_t* __restrict__ img = staging + d.offset;
+    const float scale_w = __fdiv_rn((float)d.w, (float)mw);
+    const float scale_h = __fdiv_rn((float)d.h, (float)mh);
+    float v[12];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int sy = src_index(2 * Y + dy, scale_h, d.h);
+        const uint8_t* __restrict__ row = img + (size_t)sy * d.w * 3;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const uint8_t* px = row + (size_t)src_index(2 * X + dx, scale_w, d.w) * 3;
+            v[(dy * 2 + dx) * 3 + 0] = __fdiv_rn((float)__ldg(px + 2), 255.0f);     // R = byte 2
+            v[(dy * 2 + dx) * 3 + 1] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
+            v[(dy * 2 + dx) * 3 + 2] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
+        }
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w[i] = pack2_16(v[2 * i], v[2 * i + 1], F16);
+    w[6] = 0u; w[7] = 0u;
+    uint4* o = out + ((size_t)f * H2 * W2 + item) * 2;
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 }  // namespace
 
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
                           int32_t mw, int32_t mh, int32_t layout, void* out)
 {
     if (n <= 0) return ZL_OK;
+    if (layout == PRE_S2D16_BF16 || layout == PRE_S2D16_F16) {
+        if ((mw & 1) || (mh & 1)) ZL_FAIL(ZL_INVALID_ARGUMENT, "s2d preprocess needs even model dims");
+        dim3 g(ceil_div((mw / 2) * (mh / 2), 256), n);
+        if (layout == PRE_S2D16_F16) preprocess_s2d_kernel<true><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out);
+        else preprocess_s2d_kernel<false><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out);
+        ZL_CUDA(cudaGetLastError());
+        return ZL_OK;
+    }
     const int threads = 256;
     dim3 grid(ceil_div(ceil_div(mw, 4) * mh, threads), n);
     switch (layout) {
