@@ -224,7 +224,7 @@ def run_ours(args, rank, local_rank, world):
     n_sets = 4
     sets = make_inputs(n_sets, seed0=5678 + 100 * rank)
     prec = zlb200.FP16 if args.dtype == "fp16" else zlb200.BF16
-    E2E_THREADS = 2        # host threads in the end-to-end leg: each owns a lane, so H2D of one batch overlaps compute of the other
+    E2E_THREADS = args.e2e_threads   # host threads in the end-to-end leg: each owns a lane, so H2D of one batch overlaps compute of another
     eng = zlb200.Engine(HW, HW, NC, SCALE, precision=prec, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank, num_lanes=E2E_THREADS)
     eng.load_weights_blob(blob)
     eng.warmup(1)
@@ -377,6 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"], help="16-bit tensor-core format (same speed; fp16 meets the IoU>=0.99 parity gate)")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (= engine lanes) feeding zl_infer_batch in the e2e leg")
     ap.add_argument("--quick", action="store_true", help="skip the latency and CPU-baseline legs (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
