@@ -291,6 +291,12 @@ def run_ours(args, rank, local_rank, world):
     ridge = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)
     ai = tc_flops / tc_bytes if tc_bytes else 0.0
     hbm_bound = ai < ridge
+    traffic = None
+    try:   # ncu --metrics dram__bytes_{read,write}.sum over one pass of the same workload (profiles/README_r01.md)
+        sm = json.load(open(os.path.join(ROOT, "profiles", "step_metrics_summary_r01.json")))
+        traffic = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in sm.items() if k.startswith("conv_halo") or k.startswith("conv_tc"))
+    except Exception:
+        traffic = None
     roofline = {
         "kernel": "conv_halo_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convs, %d launches/step)" % len(tc),
         "bound": "hbm" if hbm_bound else "tensor",
@@ -298,7 +304,10 @@ def run_ours(args, rank, local_rank, world):
         "peak": peaks["hbm"] if hbm_bound else peaks["tf_sust"],
         "unit": "GB/s" if hbm_bound else "TFLOP/s",
         "frac": (gbs / peaks["hbm"]) if hbm_bound else (tflops / peaks["tf_sust"]),
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_note": "DRAM read+write bytes of the conv kernel family per step (ncu, profiles/step_metrics_summary_r01.json); "
+                        "algorithmic bytes per step = %.0f" % tc_bytes,
+        "unit_of_work": "one step = all %d conv launches of a 64-frame batch (the family is one kernel template)" % len(tc),
         "peak_source": peaks["src"] + (", sustained figure: kernel timed inside a long step" if not hbm_bound else ""),
         "tensor_tflops": tflops, "tensor_frac_of_sustained": tflops / peaks["tf_sust"],
         "hbm_gbs_algorithmic": gbs, "hbm_frac": gbs / peaks["hbm"],

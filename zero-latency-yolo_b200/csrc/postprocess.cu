@@ -354,22 +354,51 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     for (int i = tid; i < nwords; i += kNmsThreads) removed[i] = 0u;
     __syncthreads();
 
-    // ---- bitonic sort, ascending
+    // ---- bitonic sort, ascending.  Comparator strides >= 32 go through memory with a block barrier per step; the five
+    // innermost strides (16..1) of every merge stay inside aligned 32-key groups, so a warp runs them in registers with
+    // shuffles (no memory traffic, no barrier): 21 block barriers instead of 66 for 2048 keys.
     if (n > 1) {
+        uint64_t* kk = in_smem ? skeys : gkeys;
         for (int k = 2; k <= P; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
+            int j = k >> 1;
+            for (; j >= 32; j >>= 1) {
                 for (int i = tid; i < P; i += kNmsThreads) {
                     const int ixj = i ^ j;
                     if (ixj > i) {
-                        uint64_t a, b;
-                        uint64_t* kk = in_smem ? skeys : gkeys;
-                        a = kk[i]; b = kk[ixj];
+                        const uint64_t a = kk[i], b = kk[ixj];
                         const bool up = (i & k) == 0;
                         if ((a > b) == up) { kk[i] = b; kk[ixj] = a; }
                     }
                 }
                 __syncthreads();
             }
+            if (P >= 32) {
+                for (int base = warp * 32; base < P; base += kNmsThreads) {      // each warp owns whole 32-key groups
+                    const int i = base + lane;
+                    uint64_t x = kk[i];
+                    const bool up = (i & k) == 0;
+                    for (int jj = j; jj >= 1; jj >>= 1) {
+                        const uint64_t y = __shfl_xor_sync(0xffffffffu, x, jj);
+                        const bool lower = (lane & jj) == 0;                      // this lane keeps the smaller key of the pair when ascending
+                        const bool take_min = lower == up;
+                        x = take_min ? (x < y ? x : y) : (x > y ? x : y);
+                    }
+                    kk[i] = x;
+                }
+            } else {
+                for (; j >= 1; j >>= 1) {                                         // tiny P (< 32): plain steps
+                    for (int i = tid; i < P; i += kNmsThreads) {
+                        const int ixj = i ^ j;
+                        if (ixj > i) {
+                            const uint64_t a = kk[i], b = kk[ixj];
+                            const bool up = (i & k) == 0;
+                            if ((a > b) == up) { kk[i] = b; kk[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            __syncthreads();
         }
     }
     const uint64_t* K = in_smem ? skeys : gkeys;
