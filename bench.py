@@ -362,7 +362,7 @@ def run_ours(args, rank, local_rank, world):
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD.replace("bf16", args.dtype), "inputs": f"{n_sets} rotating resident input sets of {BATCH} frames ({n_sets * BATCH * HW * HW * 3 / 1e6:.0f} MB > 126 MB L2)",
-                   "frames_per_step_per_gpu": BATCH, "parallelism": f"frame-sharded replicas x{world}, no collective"},
+                   "frames_per_step_per_gpu": BATCH, "streams": E2E_THREADS, "parallelism": f"frame-sharded replicas x{world}, no collective"},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * HW * HW * 3, "d2h_bytes_per_step": d2h,
                 "api": f"zl_infer_batch (C-ABI) on pinned host frames from {E2E_THREADS} host threads (one lane each)", "detections_last_step": n_det},
         "gpu_launches": int(launches),

@@ -795,59 +795,70 @@ int32_t Engine::upload_resident(int set, const uint8_t* const* frames, const int
 {
     if (set < 0 || set > 3 || n < 1 || n > cfg.max_batch) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad resident set / count");
     ZL_CUDA(cudaSetDevice(cfg.device));
-    Lane& L = *lanes[0];
-    std::lock_guard<std::mutex> g(L.mu);
     const size_t slot = slot_bytes();
-    if (L.staging_slots < (size_t)cfg.max_batch * 5) {      // grow once: [live | set0 | set1 | set2 | set3]
-        uint8_t* ns = nullptr;
-        ZL_CUDA(cudaMalloc(&ns, (size_t)cfg.max_batch * 5 * slot));
-        ZL_CUDA(cudaMemset(ns, 128, (size_t)cfg.max_batch * 5 * slot));
-        ZL_CUDA(cudaDeviceSynchronize());
-        cudaFree(L.staging);
-        L.staging = ns;
-        L.staging_slots = (size_t)cfg.max_batch * 5;
-        for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);   // graphs and op lists captured the old staging pointer
-        L.graphs.clear();
-        L.ops.clear();
+    for (auto& Lp : lanes) {                                // every lane gets its own copy: resident steps can run on all lanes
+        Lane& L = *Lp;
+        std::lock_guard<std::mutex> g(L.mu);
+        if (L.staging_slots < (size_t)cfg.max_batch * 5) {      // grow once: [live | set0 | set1 | set2 | set3]
+            uint8_t* ns = nullptr;
+            ZL_CUDA(cudaMalloc(&ns, (size_t)cfg.max_batch * 5 * slot));
+            ZL_CUDA(cudaMemset(ns, 128, (size_t)cfg.max_batch * 5 * slot));
+            ZL_CUDA(cudaDeviceSynchronize());
+            cudaFree(L.staging);
+            L.staging = ns;
+            L.staging_slots = (size_t)cfg.max_batch * 5;
+            for (auto& kv : L.graphs) cudaGraphExecDestroy(kv.second);   // graphs and op lists captured the old staging pointer
+            L.graphs.clear();
+            L.ops.clear();
+        }
+        FrameDesc* hd = L.h_descs + (size_t)cfg.max_batch * (1 + set);
+        for (int i = 0; i < n; ++i) {
+            const size_t bytes = (size_t)ws[i] * hs[i] * 3;
+            if (bytes > slot) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame");
+            const size_t off = ((size_t)(1 + set) * cfg.max_batch + i) * slot;
+            ZL_CUDA(cudaMemcpy(L.staging + off, frames[i], bytes, cudaMemcpyHostToDevice));
+            hd[i] = FrameDesc{off, ws[i], hs[i]};
+        }
+        ZL_CUDA(cudaMemcpy(L.d_res_descs + (size_t)set * cfg.max_batch, hd, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice));
+        L.resident_n[set] = n;
     }
-    FrameDesc* hd = L.h_descs + (size_t)cfg.max_batch * (1 + set);
-    for (int i = 0; i < n; ++i) {
-        const size_t bytes = (size_t)ws[i] * hs[i] * 3;
-        if (bytes > slot) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame");
-        const size_t off = ((size_t)(1 + set) * cfg.max_batch + i) * slot;
-        ZL_CUDA(cudaMemcpy(L.staging + off, frames[i], bytes, cudaMemcpyHostToDevice));
-        hd[i] = FrameDesc{off, ws[i], hs[i]};
-    }
-    ZL_CUDA(cudaMemcpy(L.d_res_descs + (size_t)set * cfg.max_batch, hd, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice));
-    L.resident_n[set] = n;
     return ZL_OK;
 }
 
+// `steps` passes over the resident sets, distributed round-robin over all lanes (streams): lane 0's stream forks the
+// others with an event and joins them before the closing event, so the CUDA-event time covers all of them.
 int32_t Engine::run_resident(int n_sets, int steps, float* total_ms, int64_t* launches, int64_t* total_dets)
 {
     if (n_sets < 1 || n_sets > 4 || steps < 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad n_sets / steps");
     ZL_CUDA(cudaSetDevice(cfg.device));
-    Lane& L = *lanes[0];
-    std::lock_guard<std::mutex> g(L.mu);
-    const int n = L.resident_n[0];
-    for (int s = 0; s < n_sets; ++s) if (L.resident_n[s] != n || n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident sets not uploaded / unequal");
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (auto& Lp : lanes) locks.emplace_back(Lp->mu);
+    Lane& L0 = *lanes[0];
+    const int n = L0.resident_n[0];
+    for (int s = 0; s < n_sets; ++s) if (L0.resident_n[s] != n || n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident sets not uploaded / unequal");
     const int B = graph_batch_for(n);
     if (B != n) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident batch must be a power of two or max_batch");
-    if (cfg.use_graph) ZL_TRY(ensure_graph(L, B));
-    int64_t dets = 0;
-    ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
+    const int nl = (int)lanes.size();
+    if (cfg.use_graph) for (auto& Lp : lanes) ZL_TRY(ensure_graph(*Lp, B));
+    ZL_CUDA(cudaDeviceSynchronize());
+    ZL_CUDA(cudaEventRecord(L0.ev0, L0.stream));
+    for (int l = 1; l < nl; ++l) ZL_CUDA(cudaStreamWaitEvent(lanes[l]->stream, L0.ev0, 0));
     for (int s = 0; s < steps; ++s) {
+        Lane& L = *lanes[s % nl];
         ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)(s % n_sets) * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
         ZL_TRY(launch_batch(L, B, false));
     }
-    ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
-    ZL_CUDA(cudaStreamSynchronize(L.stream));
+    for (int l = 1; l < nl; ++l) {
+        ZL_CUDA(cudaEventRecord(lanes[l]->ev1, lanes[l]->stream));
+        ZL_CUDA(cudaStreamWaitEvent(L0.stream, lanes[l]->ev1, 0));
+    }
+    ZL_CUDA(cudaEventRecord(L0.ev1, L0.stream));
+    ZL_CUDA(cudaStreamSynchronize(L0.stream));
     float ms = 0;
-    ZL_CUDA(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
-    dets = ((const uint32_t*)L.h_result)[0];
+    ZL_CUDA(cudaEventElapsedTime(&ms, L0.ev0, L0.ev1));
     if (total_ms) *total_ms = ms;
-    if (launches) *launches = (int64_t)steps * ((int64_t)L.ops[B].size() - 2);     // DECODE + FILTER ops are the raw-mode alternates
-    if (total_dets) *total_dets = dets;
+    if (launches) *launches = (int64_t)steps * ((int64_t)L0.ops[B].size() - 2);     // DECODE + FILTER ops are the raw-mode alternates
+    if (total_dets) *total_dets = ((const uint32_t*)L0.h_result)[0];
     return ZL_OK;
 }
 
