@@ -191,6 +191,8 @@ PERSIST_1X1_CASES = [
     (4, 26, 26, 192, 128, True, False, 7),
     (1, 24, 24, 16, 16, True, False, 0),      # sub = 4 (36 rows of 8)
     (8, 20, 20, 384, 256, True, False, 0),    # weights 196 KB: N-split
+    (1, 13, 13, 256, 128, True, False, 0),    # 169 pixels (not a multiple of 8): native 13x13 view
+    (3, 13, 13, 128, 64, False, True, 0),
     (2, 20, 20, 512, 256, False, False, 0),   # SPPF cv2 shape
 ]
 

@@ -458,7 +458,7 @@ static bool persist_views(const ConvWeights& w, const View& x, const View& y, Vi
     *xv = x; *yv = y;
     if (w.k == 3) return true;
     const size_t m = x.pixels();
-    if (m % 8 != 0) return false;
+    if (m % 8 != 0) return true;          // odd pixel counts (13x13 maps at b=1): keep the native image view, tiles 8 wide x 16 high
     xv->n = 1; xv->w = 8; xv->h = (int32_t)(m / 8);
     yv->n = 1; yv->w = 8; yv->h = (int32_t)(m / 8);
     return true;

@@ -90,6 +90,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // programmatic dependent launch: the next kernel may start its prologue under this one's tail; nothing the previous
+    // kernel produced is touched before griddepcontrol.wait (weights and bias are constants)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -410,9 +414,14 @@ int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& o)
     p.b_bytes = (uint32_t)o.ntile * o.kc * 2;
     p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
     p.tmem_cols = o.tmem_cols;
-    dim3 grid(ceil_div(o.m_total, kTileM), o.ngrid);
-    conv_tc_kernel<<<grid, kThreads, o.smem_bytes, st>>>(o.tmap_w, o.tmap_a, p);
-    ZL_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ceil_div(o.m_total, kTileM), o.ngrid); cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)o.smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, o.tmap_w, o.tmap_a, p));
     return ZL_OK;
 }
 

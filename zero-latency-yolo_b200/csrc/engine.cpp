@@ -88,6 +88,9 @@ int32_t Engine::init()
     if (const char* ev = getenv("ZL_DISABLE_HALO")) use_halo = !(ev[0] == '1');
     if (const char* ev = getenv("ZL_FUSE_PRE")) fuse_pre = (ev[0] == '1');
     if (const char* ev = getenv("ZL_DISABLE_STEM")) use_stem = !(ev[0] == '1');
+    persist_min_units = 0;      // measured: the persistent kernel wins even for b=1 (p50 0.77 -> 0.44 ms), so it always runs when it can
+    if (const char* ev = getenv("ZL_PERSIST_MIN_UNITS")) persist_min_units = atoi(ev);
+    if (const char* ev = getenv("ZL_DEEP_K_PERSIST")) deep_k_persist = (ev[0] == '1');
     ZL_TRY(build_model_def());
     num_anchors = 0;
     for (int s : {8, 16, 32}) num_anchors += (cfg.model_h / s) * (cfg.model_w / s);
@@ -392,7 +395,8 @@ int32_t Engine::build_ops(Lane& L, int B)
                    (double)w.cout * w.ktot * (bf16 ? 2 : 4) + (res ? (double)y.pixels() * w.cout * res->esize() : 0.0);
         if (!bf16) op.kind = Op::CONV_SIMT;
         else if (w.cin == 3) op.kind = Op::CONV0;
-        else if (int units = 0; use_halo && conv_halo_supported(w, x, y, num_sms, &units) && units >= num_sms) {
+        else if (int units = 0; use_halo && conv_halo_supported(w, x, y, num_sms, &units) &&
+                 (units >= persist_min_units || (deep_k_persist && w.k * w.k * (w.cin / 16) >= 72))) {
             // stride-1 layers with at least one work unit per SM: persistent weights-resident kernel
             // (3x3: input read ~1.4x instead of 9x; 1x1: flattened pixel tiles)
             op.kind = Op::CONV_HALO;

@@ -111,6 +111,8 @@ public:
     int num_anchors = 0;
     int num_sms = 148;
     bool use_halo = true;
+    int persist_min_units = 0;     // a layer goes to the persistent kernel when it has at least this many (tile, N-slice) work units ...
+    bool deep_k_persist = false;   // ... or (experiment) when its K loop is deep
     bool use_stem = true;      // layer 0 on tensor cores (2x2 conv over the space-to-depth image the preprocess kernel writes)
     bool fuse_pre = false;     // P1 fused into layer 0 (bit-identical, measured slower than the two-kernel path: scattered byte loads)
     bool weights_loaded = false;
