@@ -49,3 +49,20 @@ def test_adapter_end_to_end_matches_c_abi(host_exe, model_n4, tmp_path):
         assert np.array_equal(recs[:, :24].reshape(-1), ref[i].view(np.uint8).reshape(-1))   # Detection's first 24 bytes == zl_det
         assert np.all(recs[:, 24:28] == 0)                                                   # track_id = 0 (onnx_engine.cpp:812)
     assert sum(len(r) for r in ref) > 5
+
+
+@pytest.mark.gpu
+def test_model_hot_reload(host_exe, tmp_path):
+    """SURVEY.md §8f N4 / onnx_engine.cpp:473-515: the model file is replaced while frames flow; the monitor thread
+    swaps the weights, detections change, a corrupt file leaves the running model in place."""
+    from oracle import synth, yolov8_ref, zlw
+    a = yolov8_ref.synthetic_model("n", 4, seed=0)
+    b = yolov8_ref.synthetic_model("n", 4, seed=7)
+    pa, pb = tmp_path / "a.zlw", tmp_path / "b.zlw"
+    pa.write_bytes(zlw.dumps(a, "n", 4)); pb.write_bytes(zlw.dumps(b, "n", 4))
+    frame = synth.frames_structured(1, 416, 416, seed=5678)[0]
+    fpath = tmp_path / "frame.bin"
+    fpath.write_bytes(frame.tobytes())
+    out = subprocess.run([host_exe, "reload", str(pa), str(pb), "4", str(fpath), "416", "416"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_test reload: ok" in out.stdout

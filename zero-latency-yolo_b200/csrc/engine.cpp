@@ -183,13 +183,9 @@ int32_t Engine::load_weights(const void* blob, size_t len)
         conv(b + ".2", md.cc, md.nc, 1, 1, 0);
     }
 
-    for (auto& w : convs) {
-        if (w->w_simt) cudaFree(w->w_simt);
-        if (w->w_tc) cudaFree(w->w_tc);
-        if (w->bias) cudaFree(w->bias);
-    }
-    convs.clear();
-    conv_by_name.clear();
+    // build the new weight set on the side; it replaces the live one atomically at the end (hot reload while serving)
+    std::vector<std::unique_ptr<ConvWeights>> new_convs;
+    std::map<std::string, ConvWeights*> new_by_name;
     const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
     const bool f16 = cfg.precision == ZL_PRECISION_FP16; (void)f16;
     for (const Spec& s : specs) {
@@ -245,18 +241,29 @@ int32_t Engine::load_weights(const void* blob, size_t len)
             ZL_CUDA(cudaMalloc(&cw->w_tc, wt.size() * 2));
             ZL_CUDA(cudaMemcpy(cw->w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         }
-        conv_by_name[s.name] = cw.get();
-        convs.push_back(std::move(cw));
+        new_by_name[s.name] = cw.get();
+        new_convs.push_back(std::move(cw));
     }
     host_w.clear();
-    // weights changed: every cached op list / graph is stale
-    for (auto& L : lanes) {
-        std::lock_guard<std::mutex> g(L->mu);
-        for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second);
-        L->graphs.clear();
-        L->ops.clear();
+    {
+        // swap under every lane's lock: no batch is in flight, every cached op list / graph is stale
+        std::vector<std::unique_lock<std::mutex>> locks;
+        for (auto& L : lanes) locks.emplace_back(L->mu);
+        ZL_CUDA(cudaDeviceSynchronize());
+        convs.swap(new_convs);
+        conv_by_name.swap(new_by_name);
+        for (auto& L : lanes) {
+            for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second);
+            L->graphs.clear();
+            L->ops.clear();
+        }
+        weights_loaded = true;
     }
-    weights_loaded = true;
+    for (auto& w : new_convs) {                 // the previous set
+        if (w->w_simt) cudaFree(w->w_simt);
+        if (w->w_tc) cudaFree(w->w_tc);
+        if (w->bias) cudaFree(w->bias);
+    }
     return ZL_OK;
 }
 

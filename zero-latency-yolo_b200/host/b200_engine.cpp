@@ -78,6 +78,7 @@ Result<void> B200InferenceEngine::initialize() {
             engines_.push_back(e);
         }
         running_ = true;
+        if (config_.b200.use_model_monitor) monitor_thread_ = std::thread(&B200InferenceEngine::modelMonitorThreadFunc, this);
         return Result<void>::ok();
     } catch (const std::exception& ex) {
         return Result<void>::error(ErrorCode::INFERENCE_ERROR, std::string("Failed to initialize B200 engine: ") + ex.what());
@@ -87,6 +88,9 @@ Result<void> B200InferenceEngine::initialize() {
 Result<void> B200InferenceEngine::shutdown() {
     try {
         if (running_.exchange(false)) {
+            { std::lock_guard<std::mutex> g(monitor_mu_); }
+            monitor_cv_.notify_all();
+            if (monitor_thread_.joinable()) monitor_thread_.join();
             for (zl_engine* e : engines_) { zl_engine_drain(e); zl_engine_destroy(e); }
             engines_.clear();
         }
@@ -103,6 +107,33 @@ Result<void> B200InferenceEngine::submitInference(const InferenceRequest& reques
                                         request.data.data(), request.data.size(), request.is_keyframe ? 1 : 0);
     if (rc != ZL_OK) return Result<void>::error(toErrorCode(rc), lastError());
     return Result<void>::ok();
+}
+
+// Model hot reload (onnx_engine.cpp:473-515): re-hash the model file periodically; on change load the new weights into
+// every device's engine (the swap is atomic under the lanes' locks: frames in flight finish on the old weights) and
+// recapture the CUDA graphs.  A file that fails to load leaves the running model untouched.
+void B200InferenceEngine::modelMonitorThreadFunc() {
+    std::string last_hash = model_hash_;
+    while (running_) {
+        {
+            std::unique_lock<std::mutex> lk(monitor_mu_);
+            monitor_cv_.wait_for(lk, std::chrono::milliseconds(std::max(config_.b200.model_check_interval_ms, 10)), [&] { return !running_.load(); });
+        }
+        if (!running_) break;
+        const std::string h = fileHash(config_.model_path);
+        if (h.empty() || h == last_hash) continue;              // missing file: keep serving (the reference only logs a warning)
+        bool ok = true;
+        for (zl_engine* e : engines_) {
+            if (zl_engine_load_weights(e, config_.model_path.c_str()) != ZL_OK) { ok = false; break; }
+            if (zl_engine_warmup(e, 1) != ZL_OK) { ok = false; break; }
+        }
+        last_hash = h;                                          // do not retry a bad file every interval
+        if (ok) {
+            std::lock_guard<std::mutex> g(monitor_mu_);
+            model_hash_ = h;
+            model_version_++;
+        }
+    }
 }
 
 void B200InferenceEngine::setCallback(InferenceCallback callback) { callback_ = std::move(callback); }
@@ -158,8 +189,8 @@ std::unordered_map<std::string, std::string> B200InferenceEngine::getStatus() co
     s["simulation_mode"] = "false";
     s["running"] = running_ ? "true" : "false";
     s["model_path"] = config_.model_path;
-    s["model_version"] = "1";
-    s["model_hash"] = model_hash_;
+    s["model_version"] = std::to_string(model_version_.load());
+    { std::lock_guard<std::mutex> g(monitor_mu_); s["model_hash"] = model_hash_; }
     s["queue_size"] = std::to_string(acc.queue_size);
     s["queue_high_water_mark"] = std::to_string(acc.queue_high_water_mark);
     s["inference_count"] = std::to_string(acc.inference_count);

@@ -8,7 +8,9 @@
 // non-"onnx" name through InferenceEngineManager.
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 
 #include "../../include/zl_b200.h"
 #include "zl_iface.h"
@@ -32,6 +34,7 @@ private:
     static void onResult(void* user, uint32_t client_id, uint32_t frame_id, uint64_t timestamp, int32_t status,
                          const zl_det* dets, int32_t n);
     static ErrorCode toErrorCode(int32_t rc) { return static_cast<ErrorCode>(rc); }
+    void modelMonitorThreadFunc();                                          // onnx_engine.cpp:473-515
 
     ServerConfig config_;
     std::vector<zl_engine*> engines_;
@@ -39,6 +42,10 @@ private:
     std::atomic<bool> running_{false};
     std::atomic<uint64_t> callback_errors_{0};
     std::string model_hash_;
+    std::atomic<uint32_t> model_version_{1};
+    mutable std::mutex monitor_mu_;
+    std::condition_variable monitor_cv_;
+    std::thread monitor_thread_;
 };
 
 class B200InferenceEngineFactory final : public IInferenceEngineFactory {

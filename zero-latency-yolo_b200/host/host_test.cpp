@@ -150,7 +150,61 @@ static int run_gpu(int argc, char** argv) {
     return 0;
 }
 
+// host_test reload <weightsA> <weightsB> <nc> <frame.bin> <w> <h>: serve with A, overwrite the model file with B, wait for
+// the monitor thread to pick it up, check that detections change and the status map reports the new version/hash.
+static int run_reload(int argc, char** argv) {
+    CHECK(argc >= 8);
+    const std::string live = std::string(argv[2]) + ".live";
+    auto copy = [&](const char* src) { std::ifstream i(src, std::ios::binary); std::ofstream o(live, std::ios::binary | std::ios::trunc); o << i.rdbuf(); };
+    copy(argv[2]);
+    ServerConfig cfg;
+    cfg.inference_engine = "b200"; cfg.model_path = live;
+    cfg.b200.num_classes = std::atoi(argv[4]); cfg.b200.max_batch = 2;
+    cfg.b200.use_model_monitor = true; cfg.b200.model_check_interval_ms = 100;
+    const int w = std::atoi(argv[6]), h = std::atoi(argv[7]);
+    cfg.b200.max_frame_width = w; cfg.b200.max_frame_height = h;
+    std::vector<uint8_t> frame((size_t)w * h * 3);
+    { std::ifstream f(argv[5], std::ios::binary); CHECK(f.read((char*)frame.data(), frame.size())); }
+    auto eng = InferenceEngineManager::getInstance().createEngine("b200", cfg);
+    CHECK(eng->initialize().isOk());
+    std::mutex mu; std::condition_variable cv; std::vector<GameState> got;
+    eng->setCallback([&](uint32_t, const GameState& st) { std::lock_guard<std::mutex> g(mu); got.push_back(st); cv.notify_all(); });
+    auto infer = [&](uint32_t id) -> GameState {
+        InferenceRequest rq; rq.client_id = 1; rq.frame_id = id; rq.width = (uint16_t)w; rq.height = (uint16_t)h; rq.data = frame;
+        while (!eng->submitInference(rq).isOk()) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait_for(lk, std::chrono::seconds(30), [&] { return !got.empty() && got.back().frame_id == id; });
+        return got.back();
+    };
+    const GameState a = infer(1);
+    const std::string hash_a = eng->getStatus()["model_hash"];
+    copy(argv[3]);                                              // the operator drops a new model file in place
+    bool changed = false;
+    for (int i = 0; i < 100 && !changed; ++i) {                 // frames keep flowing while the reload happens
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        (void)infer(100 + i);
+        changed = eng->getStatus()["model_version"] == "2";
+    }
+    CHECK(changed);
+    const GameState b = infer(999);
+    CHECK(eng->getStatus()["model_hash"] != hash_a);
+    bool differ = a.detections.size() != b.detections.size();
+    for (size_t i = 0; !differ && i < a.detections.size(); ++i) differ = std::memcmp(&a.detections[i], &b.detections[i], 24) != 0;
+    CHECK(differ);                                              // different weights -> different detections
+    // a corrupt file must not take the engine down
+    { std::ofstream o(live, std::ios::binary | std::ios::trunc); o << "garbage"; }
+    std::this_thread::sleep_for(std::chrono::milliseconds(400));
+    const GameState c = infer(1000);
+    CHECK(c.detections.size() == b.detections.size());
+    CHECK(eng->getStatus()["model_version"] == "2");
+    CHECK(eng->shutdown().isOk());
+    std::remove(live.c_str());
+    std::printf("host_test reload: ok (%zu -> %zu detections)\n", a.detections.size(), b.detections.size());
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::strcmp(argv[1], "gpu") == 0) return run_gpu(argc, argv);
+    if (argc >= 2 && std::strcmp(argv[1], "reload") == 0) return run_reload(argc, argv);
     return run_cpu();
 }

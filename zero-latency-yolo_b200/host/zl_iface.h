@@ -97,6 +97,8 @@ struct B200Config {
     int num_lanes = 2;
     int batch_window_us = 0;
     bool use_class_weights = false;     // false == the reference's effective behaviour
+    bool use_model_monitor = false;     // hot reload: the reference's optimization.use_model_monitor (onnx_engine.cpp:38,145)
+    int model_check_interval_ms = 10000; // the reference checks every 10 s (onnx_engine.cpp:480)
     std::vector<float> class_weights;
 };
 
