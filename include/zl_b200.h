@@ -131,7 +131,9 @@ typedef void (*zl_result_fn)(void* user, uint32_t client_id, uint32_t frame_id,
 ZL_API void    zl_config_default(zl_config* cfg);
 ZL_API int32_t zl_engine_create(const zl_config* cfg, zl_engine** out);
 ZL_API int32_t zl_engine_destroy(zl_engine* e);
-/* loadModel (onnx_engine.cpp:957-1062): weights container (see DESIGN.md "ZLW1"), BN already folded. */
+/* loadModel (onnx_engine.cpp:957-1062): a ZLW1 weights container or an ultralytics YOLOv8 ONNX export
+ * (the file the reference loads, start.sh:122-125; BN fused, fp32 or fp16 initialisers).  Callable while serving:
+ * the swap is atomic (hot reload, onnx_engine.cpp:473-515). */
 ZL_API int32_t zl_engine_load_weights(zl_engine* e, const char* path);
 ZL_API int32_t zl_engine_load_weights_mem(zl_engine* e, const void* blob, size_t len);
 /* warmupModel (onnx_engine.cpp:919-954): `iters` runs on an all-128 frame of model size; captures graphs. */
@@ -217,6 +219,10 @@ ZL_API int32_t zl_probe_tma(int32_t device, const uint16_t* x, int32_t n, int32_
                             int32_t box_c, int32_t box_w, int32_t box_h, int32_t estride, int32_t swizzle_bytes,
                             int32_t c0, int32_t c1, int32_t c2, int32_t c3, uint32_t expect_bytes,
                             uint8_t* dump, uint32_t dump_bytes, int32_t* completed);
+
+/* Host-only (no CUDA) probe of a model file: which YOLOv8 scale / class count it holds, how many conv tensors, and
+ * an FNV-1a checksum over their names, shapes and values (equal for ZLW1 and ONNX files with the same parameters). */
+ZL_API int32_t zl_model_probe(const void* blob, size_t len, int32_t* scale, int32_t* num_classes, int32_t* n_tensors, uint64_t* checksum);
 
 /* ---- host memory + errors ---- */
 ZL_API void*   zl_host_alloc(size_t bytes);   /* pinned */

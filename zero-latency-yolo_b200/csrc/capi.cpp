@@ -244,6 +244,21 @@ int32_t zl_bench_decode_nms(zl_engine* e, const float* raw, int32_t n, int32_t n
     ZL_GUARD_END
 }
 
+// Host-only model probe (no CUDA): container kind agnostic summary, used by tests and by operators to check a file.
+int32_t zl_model_probe(const void* blob, size_t len, int32_t* scale, int32_t* num_classes, int32_t* n_tensors, uint64_t* checksum)
+{
+    ZL_GUARD_BEGIN
+    zl::ParsedModel pm;
+    int32_t rc = zl::parse_model(blob, len, &pm);
+    if (rc != ZL_OK) return rc;
+    if (scale) *scale = pm.scale;
+    if (num_classes) *num_classes = pm.nc;
+    if (n_tensors) *n_tensors = (int32_t)pm.tensors.size();
+    if (checksum) *checksum = zl::model_checksum(pm);
+    return ZL_OK;
+    ZL_GUARD_END
+}
+
 void* zl_host_alloc(size_t bytes)
 {
     void* p = nullptr;

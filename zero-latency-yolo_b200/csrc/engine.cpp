@@ -1,5 +1,6 @@
 // engine.cpp — model graph, buffers, CUDA graphs, batching queue (see engine.h).
 #include "engine.h"
+#include "weights.h"
 
 #include <algorithm>
 #include <chrono>
@@ -112,31 +113,11 @@ int32_t Engine::init()
 int32_t Engine::load_weights(const void* blob, size_t len)
 {
     ZL_CUDA(cudaSetDevice(cfg.device));
-    const uint8_t* p = (const uint8_t*)blob;
-    if (len < 24 || std::memcmp(p, "ZLW1", 4) != 0) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "not a ZLW1 weights container");
-    uint32_t hdr[5];
-    std::memcpy(hdr, p + 4, 20);
-    if (hdr[0] != 1) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "unsupported ZLW version");
-    if ((int)hdr[1] != cfg.scale || (int)hdr[2] != cfg.num_classes)
-        ZL_FAIL(ZL_MODEL_LOAD_FAILED, "weights are for scale " + std::to_string(hdr[1]) + " nc " + std::to_string(hdr[2]) + ", engine configured otherwise");
-    size_t off = 24;
-    host_w.clear();
-    for (uint32_t i = 0; i < hdr[3]; ++i) {
-        if (off + 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated weights container");
-        uint32_t nl; std::memcpy(&nl, p + off, 4); off += 4;
-        if (off + nl > len || nl > 4096) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated weights container");
-        std::string name((const char*)p + off, nl); off += nl + ((4 - nl % 4) % 4);
-        if (off + 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated weights container");
-        uint32_t nd; std::memcpy(&nd, p + off, 4); off += 4;
-        if (nd > 8 || off + 4ull * nd > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "bad tensor rank");
-        HostTensor t; t.dims.resize(nd);
-        size_t cnt = 1;
-        for (uint32_t d = 0; d < nd; ++d) { std::memcpy(&t.dims[d], p + off, 4); off += 4; cnt *= t.dims[d]; }
-        if (off + cnt * 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated tensor " + name);
-        t.data.resize(cnt);
-        std::memcpy(t.data.data(), p + off, cnt * 4); off += cnt * 4;
-        host_w[name] = std::move(t);
-    }
+    ParsedModel pm;
+    ZL_TRY(parse_model(blob, len, &pm));              // ZLW1 container or an ultralytics ONNX export (BN fused)
+    if (pm.scale != cfg.scale || pm.nc != cfg.num_classes)
+        ZL_FAIL(ZL_MODEL_LOAD_FAILED, "weights are for scale " + std::to_string(pm.scale) + " nc " + std::to_string(pm.nc) + ", engine configured otherwise");
+    host_w.swap(pm.tensors);
 
     // the conv list of YOLOv8, names as ultralytics exports them
     struct Spec { std::string name; int cin, cout, k, s, act; };

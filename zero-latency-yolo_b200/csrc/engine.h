@@ -17,13 +17,9 @@
 #include <vector>
 
 #include "kernels.h"
+#include "weights.h"
 
 namespace zl {
-
-struct HostTensor {
-    std::vector<uint32_t> dims;
-    std::vector<float> data;
-};
 
 struct ModelDef {
     int scale = 0, nc = 0;

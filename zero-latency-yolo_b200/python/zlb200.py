@@ -56,7 +56,7 @@ EXPORTS = [
     "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
     "zl_engine_run_resident", "zl_engine_profile", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
-    "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
+    "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
             "zl_test_conv": (i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
             "zl_probe_umma": (i32, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "zl_probe_tma": (i32, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, u32, vp, u32, C.POINTER(i32)]),
+            "zl_model_probe": (i32, [vp, sz, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(u64)]),
             "zl_host_alloc": (vp, [sz]),
             "zl_host_free": (None, [vp]),
             "zl_last_error": (C.c_char_p, []),
@@ -316,3 +317,11 @@ def probe_tma(x_f16, box, estride, swizzle, coords, expect_bytes, dump_bytes, de
     _check(lib().zl_probe_tma(device, _ptr(x), n, h, w, c, box[0], box[1], box[2], estride, swizzle,
                               coords[0], coords[1], coords[2], coords[3], expect_bytes, _ptr(dump), dump_bytes, C.byref(done)))
     return done.value, dump.view(np.float16)
+
+
+def model_probe(blob: bytes):
+    """Host-only: (scale, nc, n_tensors, checksum) of a ZLW1 or ONNX model file."""
+    buf = np.frombuffer(blob, np.uint8)
+    sc, nc, nt, ck = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+    _check(lib().zl_model_probe(_ptr(buf), buf.size, C.byref(sc), C.byref(nc), C.byref(nt), C.byref(ck)))
+    return sc.value, nc.value, nt.value, ck.value
