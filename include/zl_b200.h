@@ -189,6 +189,13 @@ ZL_API int32_t zl_engine_run_resident(zl_engine* e, int32_t n_sets, int32_t step
 /* Same pass, un-captured, one CUDA-event pair per kernel; fills up to cap records. */
 ZL_API int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters,
                                  zl_op_profile* out, int32_t cap, int32_t* n_out);
+/* Where the persistent conv kernel's cycles go: one un-captured pass with its instrumented instantiation.  out holds
+ * ZL_STALL_SLOTS uint64 per op, in zl_engine_profile's op order (all zero for ops that are not persistent convs):
+ * 0 producer waiting for a free patch stage, 1 MMA warp waiting for a patch, 2 MMA warp waiting for a drained
+ * accumulator, 3 MMA warp issuing, 4 epilogue warp waiting for an accumulator, 5 epilogue warp busy, 6 CTA lifetime
+ * (sum over CTAs), 7 prologue (sum), 8 MMA warp waiting for the weights, 9 slowest CTA, 10 CTAs. */
+#define ZL_STALL_SLOTS 12
+ZL_API int32_t zl_engine_profile_stalls(zl_engine* e, int32_t set, uint64_t* out, int32_t cap_ops, int32_t* n_out);
 /* b=1 latency loop in C (no interpreter in the timed path): `iters` synchronous runInference calls on one
  * HOST frame (pinned or not), each timed with steady_clock from call to detections-on-host; ms_out[iters]. */
 ZL_API int32_t zl_bench_latency(zl_engine* e, const uint8_t* bgr, int32_t width, int32_t height,

@@ -59,3 +59,51 @@ def stress_head_adversarial(n, nc, A, seed=43, img=640, clusters=64):
     score = (rng.integers(1, 9, size=(n, A)) / 8.0).astype(np.float32) * 0.9   # 8 distinct values -> many ties
     np.put_along_axis(raw[:, 4:], cls[:, None, :], score[:, None, :], 1)
     return raw
+
+
+# ---- version-independent generators for the golden fixtures (tests/golden/): pure integer / exact float32 arithmetic,
+# ---- so the same inputs are rebuilt anywhere without depending on a numpy RNG stream
+def _mix64(n, seed):
+    x = (np.arange(n, dtype=np.uint64) + np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)) * np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(0x94D049BB133111EB)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def golden_bytes(shape, seed):
+    """uint8 array of `shape` from a splitmix-style integer hash."""
+    n = int(np.prod(shape))
+    return (_mix64(n, seed) >> np.uint64(24)).astype(np.uint8).reshape(shape)
+
+
+def golden_unit(shape, seed):
+    """float32 in [0, 1) with a 24-bit mantissa (exactly representable)."""
+    n = int(np.prod(shape))
+    return ((_mix64(n, seed) >> np.uint64(40)).astype(np.float32) / np.float32(16777216.0)).reshape(shape)
+
+
+def golden_head(nc, A, seed, img=640, ties=False, clusters=0):
+    """Raw head tensor [4+nc, A] fp32 for the golden post-processing cases.  Scores = u^6 (about 1/3 of the anchors
+    have a class >= 0.01 at nc=80); `clusters` > 0 snaps the boxes onto that many centres with integer jitter (heavy
+    overlap); `ties` quantises the scores to multiples of 1/16 (exact (class, confidence) ties)."""
+    raw = np.empty((4 + nc, A), np.float32)
+    u = golden_unit((4, A), seed)
+    if clusters:
+        c = (golden_unit((2, clusters), seed + 1) * np.float32(img - 80) + np.float32(40)).astype(np.float32)
+        which = (_mix64(A, seed + 2) % np.uint64(clusters)).astype(np.int64)
+        jit = ((_mix64(2 * A, seed + 3) % np.uint64(7)).astype(np.float32) - np.float32(3)).reshape(2, A)
+        raw[0] = c[0][which] + jit[0]
+        raw[1] = c[1][which] + jit[1]
+        raw[2] = np.float32(48) + np.float32(8) * (_mix64(A, seed + 4) % np.uint64(3)).astype(np.float32)
+        raw[3] = np.float32(64) + np.float32(8) * (_mix64(A, seed + 5) % np.uint64(3)).astype(np.float32)
+    else:
+        raw[0:2] = u[0:2] * np.float32(img)
+        raw[2:4] = np.float32(4) + u[2:4] * u[2:4] * np.float32(200)
+    s = golden_unit((nc, A), seed + 7)
+    s2 = s * s
+    s = s2 * s2 * s2
+    if ties:
+        s = np.floor(s * np.float32(16)) / np.float32(16)
+    raw[4:] = s
+    return raw

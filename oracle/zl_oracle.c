@@ -5,12 +5,18 @@
  * host adapter) may link, load or call this file; only tests/, smoke() and
  * bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors
- * for this path and cannot be compiled here (ONNX Runtime
- * and the model are absent; the sources have hard compile errors, SURVEY.md §0
- * fact 5).  This file therefore follows the reference SOURCE TEXT line by
- * line; the known-answer tests in tests/test_oracle_kat.py are derived from
- * that text.  Citations are relative to the reference tree.
+ * PARITY PINNED for P1 / F1 / N1: the reference ships no tests or golden vectors
+ * (SURVEY.md section 4), but preProcess / postProcess / applyNMS / calculateIoU are
+ * self-contained C++, so oracle/ref/ cuts exactly those line ranges out of
+ * /root/reference/src/inference/onnx_engine.cpp (checksummed) and compiles them
+ * UNMODIFIED against a small shim (oracle/_ref/libzl_ref.so).  This file must
+ * equal that library bit for bit (tests/test_oracle_vs_ref.py) and the golden
+ * fixtures minted from it (tests/golden/, tests/test_golden.py).  One behaviour
+ * of the reference is implementation-defined: std::sort's order inside an exact
+ * (class, confidence) tie group; this file completes it with the anchor index.
+ * The conv graph itself (M1 + D1: ONNX Runtime + an exported model, neither in
+ * the tree) stays unpinned: oracle/yolov8_ref.py restates the public YOLOv8
+ * definition.  Citations are relative to the reference tree.
  *
  * Build WITHOUT -ffast-math and with -ffp-contract=off (oracle/Makefile): the
  * reference's Release flags use -ffast-math (CMakeLists.txt:279), which leaves

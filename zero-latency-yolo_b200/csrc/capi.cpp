@@ -218,6 +218,14 @@ int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters, zl_op_profil
     ZL_GUARD_END
 }
 
+int32_t zl_engine_profile_stalls(zl_engine* e, int32_t set, uint64_t* out, int32_t cap_ops, int32_t* n_out)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->profile_stalls(set, out, cap_ops, n_out);
+    ZL_GUARD_END
+}
+
 int32_t zl_bench_latency(zl_engine* e, const uint8_t* bgr, int32_t width, int32_t height, int32_t warmup, int32_t iters, float* ms_out)
 {
     ZL_GUARD_BEGIN

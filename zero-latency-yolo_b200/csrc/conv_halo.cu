@@ -60,6 +60,7 @@ struct HaloParams {
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
     uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
+    unsigned long long* stats;      // STATS instantiation only: kHaloStatSlots cycle counters summed over CTAs (zl_engine_profile_stalls)
 };
 
 // Issue all MMAs of one (tile, channel chunk): 9 taps x SUB sub-tiles x KSTEPS k-steps, fully unrolled.
@@ -91,7 +92,7 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
     }
 }
 
-template <int MODE>
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const __grid_constant__ CUtensorMap tmap_y, const HaloParams p)
@@ -100,6 +101,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     constexpr int kPW = Geo<MODE>::PW, kHalo = Geo<MODE>::HALO, TAPS = Geo<MODE>::TAPS, NPATCH = Geo<MODE>::NPATCH;
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+    // STATS: where each role's cycles go (slot meanings in kernels.h, HaloStat).  Compiled out of the production kernel.
+    long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, t_begin = 0, t_pro = 0;
+    if (STATS) t_begin = clock64();
+#define ZL_ST_BEGIN(t) long long t = 0; if (STATS) t = clock64()
+#define ZL_ST_END(t, acc) if (STATS) acc += clock64() - t
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_pfull = base;                               // kMaxPatchStages x 8
@@ -154,6 +160,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     // Programmatic dependent launch: let the next kernel's CTAs take this SM as soon as this CTA exits and run their
     // own prologue (barrier init, TMEM alloc, weight TMA) under this kernel's tail ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (STATS) t_pro = clock64();
 
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     bool store_leader = false;                               // set on the one lane per epilogue warp that issues TMA stores
@@ -175,7 +182,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 const int rem = tile - n * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 for (int cc = 0; cc < p.cchunks; ++cc) {
+                    ZL_ST_BEGIN(t0);
                     mbar_wait(bar_pempty + 8u * s, ph ^ 1u, 1);
+                    ZL_ST_END(t0, st_a);
                     mbar_arrive_expect_tx(bar_pfull + 8u * s, p.patch_bytes * (uint32_t)NPATCH);
                     if (MODE == 2) {
 #pragma unroll
@@ -188,6 +197,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
                 }
             }
+            if (STATS) atomicAdd(p.stats + 0, (unsigned long long)st_a);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -196,7 +206,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int ksteps = p.kc / 16;
         const uint32_t sbo_a = (uint32_t)kPW * swz;          // one tile row (8 pixels) per 8-row group, groups strided by the patch row
-        mbar_wait(bar_wfull, 0u, 2);
+        {
+            ZL_ST_BEGIN(t0);
+            mbar_wait(bar_wfull, 0u, 2);
+            ZL_ST_END(t0, st_d);
+        }
         tc_fence_after();
         uint32_t s = 0, ph = 0, tl = 0;
         const uint64_t adesc_base = make_smem_desc_sbo(pbase, swz, sbo_a);
@@ -206,12 +220,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int sel = (ksteps == 4 ? 0 : (ksteps == 2 ? 3 : 6)) + (p.sub == 1 ? 0 : (p.sub == 2 ? 1 : 2));
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-            mbar_wait(bar_tempty + 8u * acc, aph ^ 1u, 3);    // epilogue has drained this accumulator
+            {
+                ZL_ST_BEGIN(t0);
+                mbar_wait(bar_tempty + 8u * acc, aph ^ 1u, 3);    // epilogue has drained this accumulator
+                ZL_ST_END(t0, st_b);
+            }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
             for (int cc = 0; cc < p.cchunks; ++cc) {
-                mbar_wait(bar_pfull + 8u * s, ph, 4);
+                {
+                    ZL_ST_BEGIN(t0);
+                    mbar_wait(bar_pfull + 8u * s, ph, 4);
+                    ZL_ST_END(t0, st_a);
+                }
                 tc_fence_after();
+                ZL_ST_BEGIN(t_issue);
                 if (elect_one()) {
                     const uint64_t ad = adesc_base + (uint64_t)(s * patch16);
                     const uint64_t bd = bdesc_base + (uint64_t)((uint32_t)cc * wtile16);
@@ -232,8 +255,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     if (cc == p.cchunks - 1) umma_commit(bar_tfull + 8u * acc);
                 }
                 __syncwarp();
+                ZL_ST_END(t_issue, st_c);
                 if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
             }
+        }
+        if (STATS && lane == 0) {
+            atomicAdd(p.stats + 1, (unsigned long long)st_a);      // MMA warp waiting for patches
+            atomicAdd(p.stats + 2, (unsigned long long)st_b);      // ... for a free accumulator
+            atomicAdd(p.stats + 3, (unsigned long long)st_c);      // ... issuing
+            atomicAdd(p.stats + 8, (unsigned long long)st_d);      // ... for the weights
         }
     } else {
         // ===== epilogue warps: TMEM -> +bias -> SiLU -> +residual -> 16-bit / fp32 NHWC =====
@@ -254,8 +284,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int ox = tx * kTW + tw;
-            mbar_wait(bar_tfull + 8u * acc, aph, 5);
+            {
+                ZL_ST_BEGIN(t0);
+                mbar_wait(bar_tfull + 8u * acc, aph, 5);
+                ZL_ST_END(t0, st_a);
+            }
             tc_fence_after();
+            ZL_ST_BEGIN(t_epi);
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (p.tmem_cols >> 1);
             for (int item = cgp; item < items; item += kEpiWarps / 4) {
                 const int j = item / nchunk, c0 = (item - j * nchunk) << 4;
@@ -379,6 +414,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (leader) mbar_arrive(bar_tempty + 8u * acc);
+            ZL_ST_END(t_epi, st_b);
+        }
+        if (STATS && warp == 2 && lane == 0) {
+            atomicAdd(p.stats + 4, (unsigned long long)st_a);      // epilogue warp 2 waiting for a full accumulator
+            atomicAdd(p.stats + 5, (unsigned long long)st_b);      // ... busy
         }
     }
 
@@ -386,6 +426,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+    if (STATS && threadIdx.x == 0) {
+        const long long t_end = clock64();
+        atomicAdd(p.stats + 6, (unsigned long long)(t_end - t_begin));   // CTA lifetime
+        atomicAdd(p.stats + 7, (unsigned long long)(t_pro - t_begin));   // prologue
+        atomicMax(p.stats + 9, (unsigned long long)(t_end - t_begin));   // slowest CTA
+        atomicAdd(p.stats + 10, 1ull);                                    // CTAs
+        if (blockIdx.x == 0)                                              // the launch plan, packed
+            p.stats[11] = (unsigned long long)p.kc | ((unsigned long long)p.cchunks << 8) | ((unsigned long long)p.sub << 16) |
+                          ((unsigned long long)p.nsplit << 20) | ((unsigned long long)p.stages << 24) | ((unsigned long long)p.nt << 32) |
+                          ((unsigned long long)p.num_tiles << 42);
+    }
+#undef ZL_ST_BEGIN
+#undef ZL_ST_END
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -609,16 +662,20 @@ int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int
 
 static const bool g_use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
 
-int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
+int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsigned long long* stats)
 {
     static thread_local int last_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != last_dev) {
-        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ZL_CUDA(cudaFuncSetAttribute(conv_halo_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         last_dev = dev;
     }
     HaloParams p;
@@ -629,6 +686,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
     p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc;
     p.tmem_cols = o.tmem_cols;
+    p.stats = stats;
     int grid = o.num_tiles * o.nsplit;
     if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
     cudaLaunchConfig_t cfg{};
@@ -637,10 +695,17 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
-    if (o.mode == 4) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<4>, o.tmap_w, o.tmap_x, o.tmap_y, p));
-    else if (o.mode == 9) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<9>, o.tmap_w, o.tmap_x, o.tmap_y, p));
-    else if (o.mode == 2) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<2>, o.tmap_w, o.tmap_x, o.tmap_y, p));
-    else ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<1>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    if (stats) {
+        if (o.mode == 4) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<4, true>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+        else if (o.mode == 9) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<9, true>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+        else if (o.mode == 2) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, true>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+        else ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, true>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+        return ZL_OK;
+    }
+    if (o.mode == 4) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<4, false>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    else if (o.mode == 9) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<9, false>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    else if (o.mode == 2) ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<2, false>, o.tmap_w, o.tmap_x, o.tmap_y, p));
+    else ZL_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<1, false>, o.tmap_w, o.tmap_x, o.tmap_y, p));
     return ZL_OK;
 }
 

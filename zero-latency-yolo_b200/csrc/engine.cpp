@@ -900,6 +900,40 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
     return ZL_OK;
 }
 
+// One un-captured pass with the instrumented persistent conv kernel: kHaloStatSlots cycle counters per op (zero for the
+// ops that are not conv_halo launches), op order == zl_engine_profile's.
+int32_t Engine::profile_stalls(int set, uint64_t* out, int cap_ops, int32_t* n_out)
+{
+    if (set < 0 || set > 3 || !out || !n_out) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    const int n = L.resident_n[set];
+    if (n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident set not uploaded");
+    const int B = graph_batch_for(n);
+    if (!L.ops.count(B)) ZL_TRY(build_ops(L, B));
+    std::vector<Op> ops;
+    for (const Op& op : L.ops[B]) if (op.kind != Op::DECODE && op.kind != Op::FILTER) ops.push_back(op);
+    if ((int)ops.size() > cap_ops) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "stall buffer too small");
+    unsigned long long* d = nullptr;
+    const size_t bytes = ops.size() * kHaloStatSlots * sizeof(unsigned long long);
+    ZL_CUDA(cudaMalloc(&d, bytes));
+    cudaMemsetAsync(d, 0, bytes, L.stream);
+    cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)set * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream);
+    cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, L.stream);
+    cudaMemsetAsync(L.pb.header, 0, 16, L.stream);
+    int32_t rc = ZL_OK;
+    for (size_t i = 0; i < ops.size() && rc == ZL_OK; ++i)
+        rc = ops[i].kind == Op::CONV_HALO ? conv_halo_launch(L.stream, ops[i].halo, num_sms, d + i * kHaloStatSlots) : launch_op(L, B, ops[i]);
+    cudaError_t ce = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, L.stream);
+    cudaError_t cs = cudaStreamSynchronize(L.stream);
+    cudaFree(d);
+    if (rc != ZL_OK) return rc;
+    if (ce != cudaSuccess || cs != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("profile_stalls: ") + cudaGetErrorString(cs != cudaSuccess ? cs : ce));
+    *n_out = (int32_t)ops.size();
+    return ZL_OK;
+}
+
 int32_t Engine::bench_preprocess(int w, int h, int n, int iters, float* ms, double* bytes)
 {
     if (w <= 0 || h <= 0 || n < 1 || iters < 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");

@@ -98,6 +98,7 @@ public:
     int32_t upload_resident(int set, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n);
     int32_t run_resident(int n_sets, int steps, float* total_ms, int64_t* launches, int64_t* total_dets);
     int32_t profile(int set, int iters, zl_op_profile* out, int cap, int32_t* n_out);
+    int32_t profile_stalls(int set, uint64_t* out, int cap_ops, int32_t* n_out);
     int32_t bench_preprocess(int w, int h, int n, int iters, float* ms, double* bytes);
     int32_t bench_latency(const uint8_t* bgr, int w, int h, int warm, int iters, float* ms_out);
 

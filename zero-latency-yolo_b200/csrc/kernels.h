@@ -84,7 +84,12 @@ struct ConvHaloOp {
 int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int num_sms, ConvHaloOp* op);
 bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int num_sms, int* work_units);
 int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, int num_sms, ConvHaloOp* op);
-int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms);
+// stats != nullptr launches the instrumented instantiation: kHaloStatSlots cycle counters summed over CTAs
+//   0 producer waiting for a free patch stage   1 MMA warp waiting for a patch   2 MMA warp waiting for a drained accumulator
+//   3 MMA warp issuing   4 epilogue warp 2 waiting for an accumulator   5 epilogue warp 2 busy   6 CTA lifetime (sum)
+//   7 prologue (sum)   8 MMA warp waiting for the weights   9 slowest CTA   10 CTAs
+constexpr int kHaloStatSlots = 12;
+int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms, unsigned long long* stats = nullptr);
 
 // ---------------------------------------------------------------- pool / upsample
 // SPPF: p1 = max5(a), p2 = max5(p1) = max9(a), p3 = max13(a) in one pass.

@@ -55,7 +55,7 @@ EXPORTS = [
     "zl_engine_load_weights_mem", "zl_engine_warmup", "zl_engine_set_callback", "zl_engine_submit",
     "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
-    "zl_engine_run_resident", "zl_engine_profile", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
+    "zl_engine_run_resident", "zl_engine_profile", "zl_engine_profile_stalls", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
     "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
 
@@ -97,6 +97,7 @@ def lib():
             "zl_engine_upload_resident": (i32, [vp, i32, vp, vp, vp, i32]),
             "zl_engine_run_resident": (i32, [vp, i32, i32, C.POINTER(f32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "zl_engine_profile": (i32, [vp, i32, i32, C.POINTER(OpProfile), i32, C.POINTER(i32)]),
+            "zl_engine_profile_stalls": (i32, [vp, i32, vp, i32, C.POINTER(i32)]),
             "zl_bench_latency": (i32, [vp, vp, i32, i32, i32, i32, vp]),
             "zl_bench_preprocess": (i32, [vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(C.c_double)]),
             "zl_bench_decode_nms": (i32, [vp, vp, i32, i32, i32, f32, f32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int64)]),
@@ -265,6 +266,13 @@ class Engine:
         _check(lib().zl_engine_profile(self.h, set_idx, iters, arr, 256, C.byref(n)))
         return [dict(name=arr[i].name.decode(), kind=arr[i].kind, ms=arr[i].ms, flops=arr[i].flops, bytes=arr[i].bytes)
                 for i in range(n.value)]
+
+    def profile_stalls(self, set_idx=0):
+        """[n_ops, 12] uint64 cycle counters of the instrumented persistent conv kernel (see zl_b200.h)."""
+        out = np.zeros((256, 12), np.uint64)
+        n = C.c_int32()
+        _check(lib().zl_engine_profile_stalls(self.h, set_idx, _ptr(out), 256, C.byref(n)))
+        return out[:n.value]
 
     def bench_latency(self, frame, warmup=50, iters=500):
         f = frame if isinstance(frame, np.ndarray) else np.ascontiguousarray(frame, np.uint8)
