@@ -193,8 +193,9 @@ ZL_API int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters,
  * ZL_STALL_SLOTS uint64 per op, in zl_engine_profile's op order (all zero for ops that are not persistent convs):
  * 0 producer waiting for a free patch stage, 1 MMA warp waiting for a patch, 2 MMA warp waiting for a drained
  * accumulator, 3 MMA warp issuing, 4 epilogue warp waiting for an accumulator, 5 epilogue warp busy, 6 CTA lifetime
- * (sum over CTAs), 7 prologue (sum), 8 MMA warp waiting for the weights, 9 slowest CTA, 10 CTAs. */
-#define ZL_STALL_SLOTS 12
+ * (sum over CTAs), 7 prologue (sum), 8 MMA warp waiting for the weights, 9 slowest CTA, 10 CTAs, 11 launch plan (packed),
+ * 12-15 epilogue warp detail: tcgen05.ld wait, staging-block wait, st.shared + fence + bulk-store issue, accumulator hand-back. */
+#define ZL_STALL_SLOTS 16
 ZL_API int32_t zl_engine_profile_stalls(zl_engine* e, int32_t set, uint64_t* out, int32_t cap_ops, int32_t* n_out);
 /* b=1 latency loop in C (no interpreter in the timed path): `iters` synchronous runInference calls on one
  * HOST frame (pinned or not), each timed with steady_clock from call to detections-on-host; ms_out[iters]. */

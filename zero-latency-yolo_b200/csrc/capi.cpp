@@ -316,7 +316,8 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
     const size_t nx = (size_t)n * h * w * cin, ny = (size_t)n * ho * wo * cout;
     std::vector<void*> frees;
     auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; frees.push_back(p); return p; };
-    auto cleanup = [&] { for (void* p : frees) cudaFree(p); };
+    // cw's buffers are tracked in `frees` like the rest: detach them so ~ConvWeights does not free them again
+    auto cleanup = [&] { for (void* p : frees) cudaFree(p); frees.clear(); cw.bias = nullptr; cw.w_simt = nullptr; cw.w_tc = nullptr; };
     cw.bias = (float*)dalloc(b.size() * 4);
     if (!cw.bias) { cleanup(); set_error("oom"); return ZL_INSUFFICIENT_RESOURCES; }
     cudaMemcpy(cw.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice);

@@ -21,6 +21,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "half16.cuh"
@@ -48,18 +51,25 @@ template <int MODE> struct Geo {
     static constexpr int NPATCH = MODE == 2 ? 4 : 1;
 };
 constexpr int kEpiWarps = 16;                // 4 per TMEM lane quarter, each owning a share of the accumulator columns
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+// Measured on B200 (probes/tma_rate.cu): ONE thread completes a pipeline stage (empty-wait, expect_tx, TMA issue) every
+// ~500 cycles + ~130 per TMA instruction whatever the box size, while issuers in different warps scale linearly (8 warps
+// reach 100 B/clk/SM).  Stages here are 5-25 KB, so a single producer thread caps a CTA at 10-40 B/clk: the stage
+// sequence is dealt round-robin to kProducers warps (warp 0 and the warps after the epilogue warps).
+constexpr int kProducers = 3;
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32 * (kProducers - 1);
 constexpr int kMaxPatchStages = 12;
+constexpr int kMaxAcc = 8;                   // TMEM accumulator ring (512 columns / (sub * nt))
 
 struct HaloParams {
     void* y;
     const __nv_bfloat16* res;
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
-    int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
+    int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act, silu_tanh;
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
-    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
+    int32_t wstream, nacc, nacc_log2, acc_cols;      // weights streamed with the patches (1) or resident (0); accumulator ring
+    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride, tmem_cols;
     unsigned long long* stats;      // STATS instantiation only: kHaloStatSlots cycle counters summed over CTAs (zl_engine_profile_stalls)
 };
 
@@ -102,7 +112,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     // STATS: where each role's cycles go (slot meanings in kernels.h, HaloStat).  Compiled out of the production kernel.
-    long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, t_begin = 0, t_pro = 0;
+    long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, st_e = 0, st_f = 0, t_begin = 0, t_pro = 0;
     if (STATS) t_begin = clock64();
 #define ZL_ST_BEGIN(t) long long t = 0; if (STATS) t = clock64()
 #define ZL_ST_END(t, acc) if (STATS) acc += clock64() - t
@@ -111,14 +121,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const uint32_t bar_pfull = base;                               // kMaxPatchStages x 8
     const uint32_t bar_pempty = base + 8u * kMaxPatchStages;       // kMaxPatchStages x 8
     const uint32_t bar_wfull = base + 16u * kMaxPatchStages;
-    const uint32_t bar_tfull = bar_wfull + 8u;                     // 2 x 8
-    const uint32_t bar_tempty = bar_tfull + 16u;                   // 2 x 8
-    const uint32_t tmem_slot = bar_tempty + 16u;
+    const uint32_t bar_tfull = bar_wfull + 8u;                     // kMaxAcc x 8
+    const uint32_t bar_tempty = bar_tfull + 8u * kMaxAcc;          // kMaxAcc x 8
+    const uint32_t tmem_slot = bar_tempty + 8u * kMaxAcc;
     const uint32_t bias_off = 1024u;                               // fp32 bias[ntile <= 256] in its own 1 KB block
     const uint32_t wbase = base + 2048u;
-    const uint32_t nwt = (uint32_t)TAPS * (uint32_t)p.cchunks;
-    const uint32_t pbase = wbase + nwt * p.wtile_alloc;
-    const uint32_t obase = pbase + (uint32_t)p.stages * p.patch_alloc;    // per-epilogue-warp output staging: 2 x 1 KB each
+    // resident weights: [chunk][tap][nt][kc] in front of the stage ring; streamed weights: the second half of every stage
+    const uint32_t pbase = wbase + (p.wstream ? 0u : (uint32_t)p.cchunks * p.wchunk_alloc);
+    const uint32_t obase = pbase + (uint32_t)p.stages * p.stage_stride;   // per-epilogue-warp output staging: 2 x 1 KB each
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
     const int stages = p.stages;
     // N-split: CTA c owns output-channel slice (c % nsplit) for good, so its weight slice stays resident
@@ -137,8 +147,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             mbar_init(bar_pfull + 8u * s, 1u);
             mbar_init(bar_pempty + 8u * s, 1u);
         }
-        mbar_init(bar_wfull, 1u);
-        for (int a = 0; a < 2; ++a) {
+        mbar_init(bar_wfull, (uint32_t)kProducers);
+        for (int a = 0; a < p.nacc; ++a) {
             mbar_init(bar_tfull + 8u * a, 1u);
             mbar_init(bar_tempty + 8u * a, (uint32_t)kEpiWarps);   // one arrival per epilogue warp
         }
@@ -165,39 +175,52 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     bool store_leader = false;                               // set on the one lane per epilogue warp that issues TMA stores
 
-    if (warp == 0) {
-        // ===== TMA producer: weights once, then one patch per (tile, channel chunk) =====
+    if (warp == 0 || warp >= 2u + kEpiWarps) {
+        // ===== TMA producers: (resident mode) the weights once, then one stage per (tile, channel chunk), dealt round-robin =====
+        const uint32_t pi = warp == 0 ? 0u : warp - (1u + kEpiWarps);            // producer index 0 .. kProducers-1
         if (elect_one()) {
-            mbar_arrive_expect_tx(bar_wfull, nwt * p.wtile_bytes);
-            for (uint32_t t = 0; t < nwt; ++t) {
-                const int tap = (int)t / p.cchunks, cc = (int)t - tap * p.cchunks;
-                tma_load_2d(&tmap_w, bar_wfull, wbase + t * p.wtile_alloc, tap * p.Cin + cc * p.kc, n_off);
+            if (!p.wstream) {
+                // chunk cc of the weight slice = ONE 3-D box [tap][nt][kc] (tensor map dims: channel-in-tap, Cout, tap)
+                uint32_t mine = 0;
+                for (uint32_t cc = pi; cc < (uint32_t)p.cchunks; cc += kProducers) ++mine;
+                mbar_arrive_expect_tx(bar_wfull, mine * p.wchunk_bytes);
+                for (uint32_t cc = pi; cc < (uint32_t)p.cchunks; cc += kProducers)
+                    tma_load_3d(&tmap_w, bar_wfull, wbase + cc * p.wchunk_alloc, (int)cc * p.kc, n_off, 0);
             }
             // ... but nothing produced by the previous kernel is read (and nothing it may still read is overwritten)
             // before it has completed: weights and bias above are constants, activations start here
             asm volatile("griddepcontrol.wait;" ::: "memory");
-            uint32_t s = 0, ph = 0;
+            // Parity waits alias when a producer runs two phases ahead of a stage's barrier.  Producer pi reaches item i only
+            // after item i - np - stages was consumed, so the stage's phase is at most one behind as long as np <= stages.
+            const uint32_t np = (uint32_t)stages < (uint32_t)kProducers ? (uint32_t)stages : (uint32_t)kProducers;
+            uint32_t s = 0, ph = 0, turn = 0;
+            const uint32_t stage_tx = p.patch_bytes * (uint32_t)NPATCH + (p.wstream ? p.wchunk_bytes : 0u);
             for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
                 const int n = tile / tiles_per_img;
                 const int rem = tile - n * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 for (int cc = 0; cc < p.cchunks; ++cc) {
-                    ZL_ST_BEGIN(t0);
-                    mbar_wait(bar_pempty + 8u * s, ph ^ 1u, 1);
-                    ZL_ST_END(t0, st_a);
-                    mbar_arrive_expect_tx(bar_pfull + 8u * s, p.patch_bytes * (uint32_t)NPATCH);
-                    if (MODE == 2) {
+                    if (turn == pi) {
+                        ZL_ST_BEGIN(t0);
+                        mbar_wait(bar_pempty + 8u * s, ph ^ 1u, 1);
+                        ZL_ST_END(t0, st_a);
+                        const uint32_t stage = pbase + s * p.stage_stride;
+                        mbar_arrive_expect_tx(bar_pfull + 8u * s, stage_tx);
+                        if (p.wstream) tma_load_3d(&tmap_w, bar_pfull + 8u * s, stage + p.patch_alloc, cc * p.kc, n_off, 0);
+                        if (MODE == 2) {
 #pragma unroll
-                        for (int pp = 0; pp < 4; ++pp)       // parity sub-patch pp = 2*(row parity) + (column parity)
-                            tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc + (uint32_t)pp * p.subpatch_alloc, cc * p.kc,
-                                        2 * (tx * kTW - 1) + (pp & 1), 2 * (ty * kTH * p.sub - 1) + (pp >> 1), n);
-                    } else {
-                        tma_load_4d(&tmap_x, bar_pfull + 8u * s, pbase + s * p.patch_alloc, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
+                            for (int pp = 0; pp < 4; ++pp)       // parity sub-patch pp = 2*(row parity) + (column parity)
+                                tma_load_4d(&tmap_x, bar_pfull + 8u * s, stage + (uint32_t)pp * p.subpatch_alloc, cc * p.kc,
+                                            2 * (tx * kTW - 1) + (pp & 1), 2 * (ty * kTH * p.sub - 1) + (pp >> 1), n);
+                        } else {
+                            tma_load_4d(&tmap_x, bar_pfull + 8u * s, stage, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
+                        }
                     }
+                    if (++turn == np) turn = 0;
                     if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
                 }
             }
-            if (STATS) atomicAdd(p.stats + 0, (unsigned long long)st_a);
+            if (STATS && pi == 0) atomicAdd(p.stats + 0, (unsigned long long)st_a);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -206,7 +229,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const int ksteps = p.kc / 16;
         const uint32_t sbo_a = (uint32_t)kPW * swz;          // one tile row (8 pixels) per 8-row group, groups strided by the patch row
-        {
+        if (!p.wstream) {
             ZL_ST_BEGIN(t0);
             mbar_wait(bar_wfull, 0u, 2);
             ZL_ST_END(t0, st_d);
@@ -214,19 +237,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         tc_fence_after();
         uint32_t s = 0, ph = 0, tl = 0;
         const uint64_t adesc_base = make_smem_desc_sbo(pbase, swz, sbo_a);
-        const uint64_t bdesc_base = make_smem_desc_sbo(wbase, swz, 8u * swz);
-        const uint32_t patch16 = p.patch_alloc >> 4, wtile16 = p.wtile_alloc >> 4, subpatch16 = p.subpatch_alloc >> 4;
-        const uint32_t btap16 = wtile16 * (uint32_t)p.cchunks;               // weight tiles are laid out [tap][chunk]
+        const uint64_t bdesc_base = make_smem_desc_sbo(p.wstream ? pbase + p.patch_alloc : wbase, swz, 8u * swz);
+        const uint32_t stage16 = p.stage_stride >> 4, wchunk16 = p.wchunk_alloc >> 4, subpatch16 = p.subpatch_alloc >> 4;
+        const uint32_t btap16 = p.wtile_bytes >> 4;                          // a chunk's weight tiles are packed [tap][nt][kc]
         const int sel = (ksteps == 4 ? 0 : (ksteps == 2 ? 3 : 6)) + (p.sub == 1 ? 0 : (p.sub == 2 ? 1 : 2));
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
-            const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+            const uint32_t acc = tl & (uint32_t)(p.nacc - 1), aph = (tl >> p.nacc_log2) & 1u;
             {
                 ZL_ST_BEGIN(t0);
                 mbar_wait(bar_tempty + 8u * acc, aph ^ 1u, 3);    // epilogue has drained this accumulator
                 ZL_ST_END(t0, st_b);
             }
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
+            const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.acc_cols;
             for (int cc = 0; cc < p.cchunks; ++cc) {
                 {
                     ZL_ST_BEGIN(t0);
@@ -236,8 +259,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 tc_fence_after();
                 ZL_ST_BEGIN(t_issue);
                 if (elect_one()) {
-                    const uint64_t ad = adesc_base + (uint64_t)(s * patch16);
-                    const uint64_t bd = bdesc_base + (uint64_t)((uint32_t)cc * wtile16);
+                    const uint64_t ad = adesc_base + (uint64_t)(s * stage16);
+                    const uint64_t bd = bdesc_base + (uint64_t)(p.wstream ? s * stage16 : (uint32_t)cc * wchunk16);
                     const uint32_t nt = (uint32_t)p.nt;                 // accumulator column stride between sub-tiles
                     const bool first = cc == 0;
                     switch (sel) {
@@ -267,6 +290,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
     } else {
         // ===== epilogue warps: TMEM -> +bias -> SiLU -> +residual -> 16-bit / fp32 NHWC =====
+        // Everything below indexes its register arrays with compile-time constants (fully unrolled, predicates instead of
+        // data-dependent trip counts): a[] / v[] must never be demoted to local memory — this loop paces the kernel on the
+        // narrow high-resolution layers (profiles/: epilogue warps busy 60-80 % of the CTA lifetime in round 1).
         const uint32_t q = warp & 3u;                        // TMEM lane quarter this warp may read
         const int cgp = (int)(warp - 2u) >> 2;               // which share of the (sub-tile, 16-column) work items
         const int row = (int)(q * 32u + lane);               // A row == TMEM lane: h = row / 8, w = row % 8
@@ -276,14 +302,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const bool leader = elect_one();                    // the one lane that owns this warp's TMA-store bulk groups
         store_leader = leader;
         const uint32_t stage_out = obase + (warp - 2u) * 2u * (uint32_t)p.ostage;   // this warp's two staging blocks ([32 px][16 ch]; 1 KB 16-bit / 2 KB fp32)
+        const bool f16 = p.f16 != 0;
+        const bool res_fast = res_g != nullptr && p.r_vec;  // residual rows are 16-byte aligned: two 128-bit loads per thread
         uint32_t nstore = 0;
         uint32_t tl = 0;
+        // the residual (and, transitively, everything this kernel overwrites) belongs to earlier kernels of the stream
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
-            const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+            const uint32_t acc = tl & (uint32_t)(p.nacc - 1), aph = (tl >> p.nacc_log2) & 1u;
             const int n = tile / tiles_per_img;
             const int rem = tile - n * tiles_per_img;
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int ox = tx * kTW + tw;
+            // residual of this warp's FIRST item: issued before the accumulator wait, so its latency hides under the MMAs
+            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+            bool r_have = false;
+            if (res_fast && cgp < items) {
+                const int j = cgp / nchunk, c0 = (cgp - j * nchunk) << 4;
+                const int oy = (ty * p.sub + j) * kTH + th;
+                if (oy < p.H && ox < p.W && c0 + 16 <= cout_l) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_g + (((size_t)n * p.H + oy) * p.W + ox) * p.rpitch + c0);
+                    r0 = __ldg(rp);
+                    r1 = __ldg(rp + 1);
+                    r_have = true;
+                }
+            }
             {
                 ZL_ST_BEGIN(t0);
                 mbar_wait(bar_tfull + 8u * acc, aph, 5);
@@ -291,45 +334,69 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             }
             tc_fence_after();
             ZL_ST_BEGIN(t_epi);
-            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (p.tmem_cols >> 1);
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (uint32_t)p.acc_cols;
             for (int item = cgp; item < items; item += kEpiWarps / 4) {
                 const int j = item / nchunk, c0 = (item - j * nchunk) << 4;
                 uint32_t v[16];
                 tmem_ld16(taddr + (uint32_t)(j * p.nt + c0), v);
-                tmem_ld_wait();
                 const int oy = (ty * p.sub + j) * kTH + th;
+                const bool in_img = oy < p.H && ox < p.W && c0 < cout_l;
+                const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
+                if (item != cgp) {                           // later items of the same tile load their residual here
+                    r_have = false;
+                    if (res_fast && in_img && c0 + 16 <= cout_l) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res_g + m * p.rpitch + c0);
+                        r0 = __ldg(rp);
+                        r1 = __ldg(rp + 1);
+                        r_have = true;
+                    }
+                }
+                {
+                    ZL_ST_BEGIN(t0);
+                    tmem_ld_wait();
+                    ZL_ST_END(t0, st_c);
+                }
+                float a[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
+                    a[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+                    a[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+                }
+                if (p.act) {
+                    if (p.silu_tanh) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) a[i] = silu_tanh(a[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) a[i] = silu_exp(a[i]);
+                    }
+                }
+                if (r_have) {
+                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float ra, rb;
+                        unpack2_16(rw[i], f16, ra, rb);
+                        a[2 * i] += ra;
+                        a[2 * i + 1] += rb;
+                    }
+                } else if (res_g != nullptr && in_img) {     // unaligned or ragged residual rows: element by element, statically indexed
+                    const uint16_t* rp = reinterpret_cast<const uint16_t*>(res_g + m * p.rpitch + c0);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < cout_l) a[i] += unpack1_16(rp[i], f16);
+                }
                 if (p.y_tma) {
-                    // ---- fast path: bias + SiLU (+ residual), stage [32 px][16 ch] in smem, one TMA store per warp (clipping by hardware)
-                    float a[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
-                        a[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-                        a[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-                    }
-                    if (p.act) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) a[i] = __fdividef(a[i], 1.0f + __expf(-a[i]));
-                    }
-                    if (res_g != nullptr && oy < p.H && ox < p.W && c0 < cout_l) {
-                        const __nv_bfloat16* rp = res_g + (((size_t)n * p.H + oy) * p.W + ox) * p.rpitch + c0;
-                        if (c0 + 16 <= cout_l && p.r_vec) {
-                            const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-                            const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                float ra, rb;
-                                unpack2_16(rw[i], p.f16, ra, rb);
-                                a[2 * i] += ra;
-                                a[2 * i + 1] += rb;
-                            }
-                        } else {
-                            for (int i = 0; i < 16 && c0 + i < cout_l; ++i) a[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
-                        }
-                    }
+                    // ---- fast path: stage [32 px][16 ch] in smem, one TMA store per warp (image borders and ragged channel
+                    //      counts are clipped by the hardware against the tensor map's extents)
                     const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
-                    if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
+                    {
+                        ZL_ST_BEGIN(t0);
+                        if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
+                        ZL_ST_END(t0, st_d);
+                    }
+                    ZL_ST_BEGIN(t_st);
                     if (p.y_f32) {
                         const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
                         const uint32_t rowb = sbuf + lane * 64u;
@@ -340,7 +407,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     } else {
                         uint32_t w[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], p.f16);
+                        for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
                         const uint32_t xr = (lane >> 2) & 1u;                                       // 32-B swizzle: chunk ^= address bit 7
                         const uint32_t rowb = sbuf + lane * 32u;
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
@@ -352,73 +419,55 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                         tma_store_4d(&tmap_y, sbuf, n_off + c0, tx * kTW, (ty * p.sub + j) * kTH + (int)q * 4, n);
                         tma_store_commit();
                     }
+                    ZL_ST_END(t_st, st_e);
                     ++nstore;
-                    continue;
-                }
-                if (oy >= p.H || ox >= p.W || c0 >= cout_l) continue;
-                const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
-                float f[16];
+                } else if (in_img) {
+                    // ---- outputs whose rows are not 16-byte aligned (e.g. nc = 2 class maps): plain stores, statically indexed
+                    const bool full = (c0 + 16 <= cout_l);
+                    if (p.y_f32) {
+                        float* yp = reinterpret_cast<float*>(y_g) + m * p.ypitch + c0;
+                        if (full && p.y_vec) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
-                    f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-                    f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-                    f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-                    f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-                }
-                if (p.act) {
+                            for (int i = 0; i < 4; ++i)
+                                reinterpret_cast<float4*>(yp)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                        } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __fdividef(f[i], 1.0f + __expf(-f[i]));
-                }
-                const bool full = (c0 + 16 <= cout_l);
-                if (res_g != nullptr) {
-                    const __nv_bfloat16* rp = res_g + m * p.rpitch + c0;
-                    if (full && p.r_vec) {
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float a, b;
-                            unpack2_16(rw[i], p.f16, a, b);
-                            f[2 * i] += a;
-                            f[2 * i + 1] += b;
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < cout_l) yp[i] = a[i];
                         }
                     } else {
-                        for (int i = 0; i < 16 && c0 + i < cout_l; ++i) f[i] += unpack1_16(reinterpret_cast<const uint16_t*>(rp)[i], p.f16);
-                    }
-                }
-                if (p.y_f32) {
-                    float* yp = reinterpret_cast<float*>(y_g) + m * p.ypitch + c0;
-                    if (full && p.y_vec) {
+                        uint16_t* yp = reinterpret_cast<uint16_t*>(y_g) + m * p.ypitch + c0;
+                        if (full && p.y_vec) {
+                            uint32_t w[8];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            reinterpret_cast<float4*>(yp)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    } else {
-                        for (int i = 0; i < 16 && c0 + i < cout_l; ++i) yp[i] = f[i];
-                    }
-                } else {
-                    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y_g) + m * p.ypitch + c0;
-                    if (full && p.y_vec) {
-                        uint32_t w[8];
+                            for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
+                            reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) w[i] = pack2_16(f[2 * i], f[2 * i + 1], p.f16);
-                        reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                        reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-                        for (int i = 0; i < 16 && c0 + i < cout_l; ++i) reinterpret_cast<uint16_t*>(yp)[i] = pack1_16(f[i], p.f16);
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < cout_l) yp[i] = pack1_16(a[i], f16);
+                        }
                     }
                 }
             }
             // this warp is done reading the accumulator: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (leader) mbar_arrive(bar_tempty + 8u * acc);
+            {
+                ZL_ST_BEGIN(t0);
+                tc_fence_before();
+                __syncwarp();
+                if (leader) mbar_arrive(bar_tempty + 8u * acc);
+                ZL_ST_END(t0, st_f);
+            }
             ZL_ST_END(t_epi, st_b);
         }
         if (STATS && warp == 2 && lane == 0) {
             atomicAdd(p.stats + 4, (unsigned long long)st_a);      // epilogue warp 2 waiting for a full accumulator
             atomicAdd(p.stats + 5, (unsigned long long)st_b);      // ... busy
+            atomicAdd(p.stats + 12, (unsigned long long)st_c);     // ...... of which: tcgen05.ld + wait::ld
+            atomicAdd(p.stats + 13, (unsigned long long)st_d);     // ...... waiting for the staging block's previous bulk store to be read
+            atomicAdd(p.stats + 14, (unsigned long long)st_e);     // ...... st.shared + proxy fence + bulk store issue
+            atomicAdd(p.stats + 15, (unsigned long long)st_f);     // ...... handing the accumulator back
         }
     }
 
@@ -435,7 +484,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         if (blockIdx.x == 0)                                              // the launch plan, packed
             p.stats[11] = (unsigned long long)p.kc | ((unsigned long long)p.cchunks << 8) | ((unsigned long long)p.sub << 16) |
                           ((unsigned long long)p.nsplit << 20) | ((unsigned long long)p.stages << 24) | ((unsigned long long)p.nt << 32) |
-                          ((unsigned long long)p.num_tiles << 42);
+                          (((unsigned long long)p.num_tiles & 0x3fffull) << 42) | ((unsigned long long)p.nacc << 56) | ((unsigned long long)p.wstream << 62);
     }
 #undef ZL_ST_BEGIN
 #undef ZL_ST_END
@@ -494,6 +543,31 @@ int32_t make_tmap_out(CUtensorMap* map, const View& y, bool f16)   // 16-bit (32
 
 }  // namespace
 
+// Weight tensor map: w_tc is [cout_pad][ktot] with k = tap * cin + channel.  Seen as a 3-D tensor {channel-in-tap, Cout, tap}
+// (strides ktot*2 and cin*2 bytes: TMA strides need not be monotonic), a box {kc, nt, taps} lands in shared memory as
+// [tap][nt][kc] — every tap's [nt][kc] K-major tile packed behind the previous one — with ONE instruction per channel chunk.
+int32_t make_tmap_w3d(CUtensorMap* map, const void* w, int cin, int cout_pad, int taps, int ktot, int kc, int nt, bool f16)
+{
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        ZL_FAIL(ZL_SYSTEM_ERROR, "cuTensorMapEncodeTiled entry point not available");
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, (cuuint64_t)taps};
+    cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)cin * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)nt, (cuuint32_t)taps};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const int swz = kc * 2;
+    const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) ZL_FAIL(ZL_SYSTEM_ERROR, "cuTensorMapEncodeTiled(weights 3d) failed, CUresult " + std::to_string((int)r));
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (uint64_t)cout_pad * ktot * 2 < 131072ull) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);   // see make_tmap_2d_16
+    return ZL_OK;
+}
+
 // Sub-tiles per tile: narrow layers stack several 8x16 sub-tiles along h so one barrier round trip, one
 // patch and one epilogue pass cover more pixels.  An MMA with N <= 64 costs ~48 tensor-pipe cycles whatever
 // N is (umma_probe), so stacking only pays for per-tile overheads; wide layers keep one sub-tile.
@@ -518,56 +592,90 @@ static bool persist_views(const ConvWeights& w, const View& x, const View& y, Vi
 }
 
 struct PersistPlan {
-    int taps, pw, prow_extra, npatch, kc, cchunks, sub, nsplit, nt, stages, smem, tiles;
-    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc;
+    int taps, pw, prow_extra, npatch, kc, cchunks, sub, nsplit, nt, stages, smem, tiles, wstream, nacc;
+    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride;
     View xv, yv;
+    double cost;
 };
 
-// Geometry + shared-memory plan.  The weight slice a CTA owns must stay resident next to >= 2-3 patch
-// stages; when the whole [taps][Cin][Cout] tensor does not fit, Cout is split over `nsplit` CTAs per tile
-// (each re-reads the patch from L2, each owns nt = Cout/nsplit channels for good).
-static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int num_sms, PersistPlan* pl)
+// Tensor-pipe cycles of one tcgen05.mma (M = 128, K = 16, both operands in shared memory), measured (umma_probe.cu):
+// 46 / 46 / 48 / 64 / 127 for N = 16 / 32 / 64 / 128 / 256 — the operand reads (4 KB of A + 32*N bytes of B at 128 B/clk)
+// below N = 128, the math above.
+static double mma_cycles(int n) { return std::max(46.0, std::max(32.0 + n / 4.0, n / 2.0)); }
+
+// Geometry + shared-memory plan.  Two ways to hold the weights:
+//   resident : the CTA's slice [taps][nt][Cin] stays in shared memory for the whole launch next to >= 2-3 patch stages; if it
+//              does not fit, Cout is split over `nsplit` CTAs per tile (each re-reads the patch from L2);
+//   streamed : (3x3 only) every stage carries the patch chunk AND that chunk's weights [taps][nt][kc], so nt can stay at the
+//              full Cout (<= 256) however large taps*Cin*Cout is — the deep 20x20 / 40x40 layers, where a resident slice
+//              forces nt down to 16-48 and every MMA below N = 64 costs the same 46 cycles.
+// Every candidate (kc, nsplit, mode) that fits is priced with a small cycle model and the cheapest one wins.
+static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int num_sms, PersistPlan* best)
 {
     const bool s2 = w.k == 3 && w.stride == 2;
     if (!(((w.k == 3 || w.k == 1) && w.stride == 1) || s2) || !x.is16() || (w.cin % 16) != 0) return false;
     if (s2 && ((x.h & 1) || (x.w & 1))) return false;
     if ((x.pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(x.ptr) & 15)) return false;
     if (y.is16() && y.dtype != x.dtype) return false;
-    if (!persist_views(w, x, y, &pl->xv, &pl->yv)) return false;
-    pl->taps = w.k * w.k;
-    pl->pw = s2 ? kTW + 1 : (w.k == 3 ? kTW + 2 : kTW);
-    pl->prow_extra = s2 ? 1 : (w.k == 3 ? 2 : 0);
-    pl->npatch = s2 ? 4 : 1;
-    pl->kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
-    if (s2 && pl->kc == 64) pl->kc = 32;                 // four sub-patches per stage: keep a stage under ~40 KB
-    pl->cchunks = w.cin / pl->kc;
-    pl->sub = halo_sub(w, pl->yv.h);
-    pl->tiles = ceil_div(pl->yv.w, kTW) * ceil_div(pl->yv.h, kTH * pl->sub) * pl->yv.n;
-    pl->patch_bytes = (uint32_t)pl->pw * (kTH * pl->sub + pl->prow_extra) * pl->kc * 2;      // one (sub-)patch
-    pl->subpatch_alloc = (pl->patch_bytes + 1023u) & ~1023u;
-    pl->patch_alloc = pl->subpatch_alloc * (uint32_t)pl->npatch;                              // one pipeline stage
+    PersistPlan base{};
+    if (!persist_views(w, x, y, &base.xv, &base.yv)) return false;
+    base.taps = w.k * w.k;
+    base.pw = s2 ? kTW + 1 : (w.k == 3 ? kTW + 2 : kTW);
+    base.prow_extra = s2 ? 1 : (w.k == 3 ? 2 : 0);
+    base.npatch = s2 ? 4 : 1;
+    base.sub = halo_sub(w, base.yv.h);
+    base.tiles = ceil_div(base.yv.w, kTW) * ceil_div(base.yv.h, kTH * base.sub) * base.yv.n;
     const uint32_t budget = 227u * 1024u;
-    const int min_stages = pl->cchunks + 1 < 3 ? pl->cchunks + 1 : 3;
-    for (int nsplit = 1; nsplit <= 16; ++nsplit) {
-        const int nt = round_up(ceil_div(w.cout_pad, nsplit), 16);
-        if (nsplit > 1 && nt * (nsplit - 1) >= w.cout_pad) continue;          // this split count adds nothing
-        if (nt > 256 || 2 * pl->sub * nt > 512) continue;                     // UMMA N limit, two accumulators in TMEM
-        const uint32_t wtile_bytes = (uint32_t)nt * pl->kc * 2;
-        const uint32_t wtile_alloc = (wtile_bytes + 1023u) & ~1023u;
-        const uint32_t fixed = 3072u + (uint32_t)pl->taps * pl->cchunks * wtile_alloc + (uint32_t)kEpiWarps * (y.dtype == DT_F32 ? 4096u : 2048u);
-        if (fixed + (uint32_t)min_stages * pl->patch_alloc > budget) continue;
-        // fits.  Small problems: keep splitting (down to N = 64, the width below which an MMA gets no cheaper)
-        // until every SM has work.
-        if (pl->tiles * nsplit < num_sms && nt > 64) continue;
-        int stages = (int)((budget - fixed) / pl->patch_alloc);
-        if (stages > kMaxPatchStages) stages = kMaxPatchStages;
-        if (stages < 2) stages = 2;
-        pl->nsplit = nsplit; pl->nt = nt; pl->stages = stages;
-        pl->wtile_bytes = wtile_bytes; pl->wtile_alloc = wtile_alloc;
-        pl->smem = (int)(fixed + (uint32_t)stages * pl->patch_alloc);
-        return true;
+    const uint32_t fixed0 = 3072u + (uint32_t)kEpiWarps * (y.dtype == DT_F32 ? 4096u : 2048u);
+    static const int force_stream = [] { const char* e = getenv("ZL_WSTREAM"); return e ? atoi(e) : -1; }();   // A/B: 0 never, 1 whenever possible
+    bool found = false;
+    for (int kc : {64, 32, 16}) {
+        if (w.cin % kc) continue;
+        PersistPlan pl = base;
+        pl.kc = kc;
+        pl.cchunks = w.cin / kc;
+        pl.patch_bytes = (uint32_t)pl.pw * (kTH * pl.sub + pl.prow_extra) * kc * 2;      // one (sub-)patch
+        pl.subpatch_alloc = (pl.patch_bytes + 1023u) & ~1023u;
+        pl.patch_alloc = pl.subpatch_alloc * (uint32_t)pl.npatch;
+        for (int mode = 0; mode < 2; ++mode) {                // 0 resident, 1 streamed
+            if (mode == 1 && (w.k != 3 || force_stream == 0)) continue;
+            if (mode == 0 && force_stream == 1 && w.k == 3) continue;
+            for (int nsplit = 1; nsplit <= 16; ++nsplit) {
+                const int nt = round_up(ceil_div(w.cout_pad, nsplit), 16);
+                if (nsplit > 1 && nt * (nsplit - 1) >= w.cout_pad) continue;          // this split count adds nothing
+                if (nt > 256 || 2 * pl.sub * nt > 512) continue;                      // UMMA N limit, >= two accumulators in TMEM
+                pl.nsplit = nsplit; pl.nt = nt; pl.wstream = mode;
+                pl.wtile_bytes = (uint32_t)nt * kc * 2;
+                pl.wchunk_bytes = (uint32_t)pl.taps * pl.wtile_bytes;
+                pl.wchunk_alloc = (pl.wchunk_bytes + 1023u) & ~1023u;
+                pl.stage_stride = pl.patch_alloc + (mode ? pl.wchunk_alloc : 0u);
+                const uint32_t fixed = fixed0 + (mode ? 0u : (uint32_t)pl.cchunks * pl.wchunk_alloc);
+                const int min_stages = mode ? 2 : (pl.cchunks + 1 < 3 ? pl.cchunks + 1 : 3);
+                if (fixed + (uint32_t)min_stages * pl.stage_stride > budget) continue;
+                int stages = (int)((budget - fixed) / pl.stage_stride);
+                if (stages > kMaxPatchStages) stages = kMaxPatchStages;
+                pl.stages = stages;
+                pl.smem = (int)(fixed + (uint32_t)stages * pl.stage_stride);
+                int nacc = 2;
+                while (nacc * 2 <= kMaxAcc && nacc * 2 * pl.sub * nt <= 512) nacc *= 2;
+                pl.nacc = nacc;
+                // ---- price it (cycles per CTA): waves of (tile, slice) units, each the slower of its MMAs and its stage
+                //      traffic (L2 -> SM at ~48 B/clk sustained, ~210 cycles of issue per stage with kProducers issuers)
+                const double units = (double)pl.tiles * nsplit;
+                const int ctas = units < num_sms ? (int)units : (num_sms / nsplit) * nsplit;
+                const double waves = std::ceil(units / std::max(ctas, 1));
+                const double mma = (double)pl.sub * pl.taps * (w.cin / 16) * mma_cycles(nt);
+                const double stage_cyc = std::max((double)(pl.patch_bytes * pl.npatch + (mode ? pl.wchunk_bytes : 0u)) / 48.0,
+                                                  (500.0 + 130.0 * (pl.npatch + mode)) / kProducers);
+                const double load = pl.cchunks * stage_cyc;
+                const double epi = 350.0 + 90.0 * pl.sub * (nt / 16) / 4.0;             // per-tile epilogue floor of one warp quarter group
+                const double prologue = mode ? 1500.0 : 1500.0 + (double)pl.cchunks * pl.wchunk_bytes / 48.0;
+                pl.cost = prologue + waves * std::max(std::max(mma, load), epi);
+                if (!found || pl.cost < best->cost * 0.97) { *best = pl; found = true; }   // ties: keep the earlier (larger kc, resident, fewer splits)
+            }
+        }
     }
-    return false;
+    return found;
 }
 
 bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int num_sms, int* work_units)
@@ -578,6 +686,17 @@ bool conv_halo_supported(const ConvWeights& w, const View& x, const View& y, int
     return true;
 }
 
+static void fill_ring(ConvHaloOp& o)
+{
+    o.acc_cols = o.sub * o.nt;
+    int nacc = 2;
+    while (nacc * 2 <= kMaxAcc && nacc * 2 * o.acc_cols <= 512) nacc *= 2;
+    o.nacc = nacc;
+    int cols = 32;
+    while (cols < o.nacc * o.acc_cols) cols <<= 1;
+    o.tmem_cols = cols;
+}
+
 int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, const View* res, int num_sms, ConvHaloOp* op)
 {
     PersistPlan pl;
@@ -585,6 +704,7 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     if (y.h != x.h / w.stride || y.w != x.w / w.stride || y.n != x.n || y.c != w.cout || x.c != w.cin) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: view mismatch (" + w.name + ")");
     if (res && (res->dtype != x.dtype || res->c != w.cout)) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_persist: residual view mismatch");
     ConvHaloOp& o = *op;
+    o = ConvHaloOp{};
     o.taps = pl.taps;
     o.mode = (w.k == 1) ? 1 : (w.stride == 2 ? 2 : 9);
     o.y = y.ptr;
@@ -595,20 +715,25 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
     o.f16 = x.dtype == DT_F16 ? 1 : 0;
+    o.silu_tanh = conv_silu_tanh(o.f16 != 0) ? 1 : 0;
     o.act = w.act;
     o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
     o.kc = pl.kc; o.cchunks = pl.cchunks; o.sub = pl.sub; o.nsplit = pl.nsplit; o.nt = pl.nt;
     o.tiles_x = ceil_div(pl.yv.w, kTW); o.tiles_y = ceil_div(pl.yv.h, kTH * o.sub);
     o.num_tiles = pl.tiles;
-    o.wtile_bytes = pl.wtile_bytes; o.wtile_alloc = pl.wtile_alloc;
-    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc; o.subpatch_alloc = pl.subpatch_alloc;
+    o.wstream = pl.wstream;
+    o.wtile_bytes = pl.wtile_bytes; o.wchunk_bytes = pl.wchunk_bytes; o.wchunk_alloc = pl.wchunk_alloc;
+    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc; o.subpatch_alloc = pl.subpatch_alloc; o.stage_stride = pl.stage_stride;
     o.smem_bytes = pl.smem; o.stages = pl.stages;
-    int cols = 32;
-    while (cols < 2 * o.sub * o.nt) cols <<= 1;
-    o.tmem_cols = cols;
-    // weight box = one slice of nt output channels (rows past Cout_pad are zero-filled by TMA)
-    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, (uint64_t)w.ktot, (uint64_t)w.cout_pad, (uint64_t)w.ktot * 2, o.kc, o.nt, o.kc * 2, o.f16));
+    fill_ring(o);
+    static const bool plan_debug = [] { const char* e = getenv("ZL_PLAN_DEBUG"); return e && e[0] == '1'; }();
+    if (plan_debug)
+        fprintf(stderr, "plan %-26s k%d s%d cin %d cout %d | %s kc %d chunks %d sub %d nsplit %d nt %d stages %d nacc %d tiles %d smem %d stage %u wchunk %u cost %.0f\n",
+                w.name.c_str(), w.k, w.stride, w.cin, w.cout, pl.wstream ? "stream" : "resident", pl.kc, pl.cchunks, pl.sub, pl.nsplit, pl.nt, pl.stages, o.nacc,
+                pl.tiles, pl.smem, pl.stage_stride, pl.wchunk_bytes, pl.cost);
+    // weight box = one channel chunk of one slice of nt output channels, all taps (rows past Cout_pad are zero-filled by TMA)
+    ZL_TRY(make_tmap_w3d(&o.tmap_w, w.w_tc, w.cin, w.cout_pad, pl.taps, w.ktot, o.kc, o.nt, o.f16));
     ZL_TRY(make_tmap_nhwc(&o.tmap_x, pl.xv, o.kc, o.kc * 2, o.f16, pl.pw, kTH * o.sub + pl.prow_extra, w.stride));
     o.y_tma = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.ostage = y.dtype == DT_F32 ? 2048 : 1024;
@@ -632,25 +757,24 @@ int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int
     o.taps = 4; o.mode = 4;
     o.y = y.ptr; o.res = nullptr; o.bias = w.bias;
     o.N = y.n; o.H = y.h; o.W = y.w; o.Cin = 16; o.Cout = w.cout; o.ntile = w.cout_pad;
-    o.ypitch = y.pitch; o.rpitch = 0; o.y_f32 = 0; o.f16 = y.dtype == DT_F16 ? 1 : 0; o.act = w.act;
+    o.ypitch = y.pitch; o.rpitch = 0; o.y_f32 = 0; o.f16 = y.dtype == DT_F16 ? 1 : 0; o.act = w.act; o.silu_tanh = conv_silu_tanh(o.f16 != 0) ? 1 : 0;
     o.y_vec = 1; o.r_vec = 0;
     o.kc = 16; o.cchunks = 1; o.nsplit = 1; o.nt = w.cout_pad;
     o.sub = halo_sub(w, y.h);
     o.tiles_x = ceil_div(y.w, kTW); o.tiles_y = ceil_div(y.h, kTH * o.sub);
     o.num_tiles = o.tiles_x * o.tiles_y * y.n;
-    o.wtile_bytes = (uint32_t)o.nt * 32u; o.wtile_alloc = (o.wtile_bytes + 1023u) & ~1023u;
+    o.wstream = 0;
+    o.wtile_bytes = (uint32_t)o.nt * 32u; o.wchunk_bytes = 4u * o.wtile_bytes; o.wchunk_alloc = (o.wchunk_bytes + 1023u) & ~1023u;
     o.patch_bytes = (uint32_t)(kTW + 1) * (kTH * o.sub + 1) * 32u;
-    o.subpatch_alloc = (o.patch_bytes + 1023u) & ~1023u; o.patch_alloc = o.subpatch_alloc;
-    const uint32_t fixed = 3072u + 4u * o.wtile_alloc + (uint32_t)kEpiWarps * 2048u;
-    int stages = (int)((227u * 1024u - fixed) / o.patch_alloc);
+    o.subpatch_alloc = (o.patch_bytes + 1023u) & ~1023u; o.patch_alloc = o.subpatch_alloc; o.stage_stride = o.patch_alloc;
+    const uint32_t fixed = 3072u + o.wchunk_alloc + (uint32_t)kEpiWarps * 2048u;
+    int stages = (int)((227u * 1024u - fixed) / o.stage_stride);
     if (stages > kMaxPatchStages) stages = kMaxPatchStages;
     o.stages = stages;
-    o.smem_bytes = (int)(fixed + (uint32_t)stages * o.patch_alloc);
+    o.smem_bytes = (int)(fixed + (uint32_t)stages * o.stage_stride);
     o.ostage = 1024;
-    int cols = 32;
-    while (cols < 2 * o.sub * o.nt) cols <<= 1;
-    o.tmem_cols = cols;
-    ZL_TRY(make_tmap_2d_16(&o.tmap_w, w.w_tc, 64, (uint64_t)w.cout_pad, 128, 16, o.nt, 32, o.f16));
+    fill_ring(o);
+    ZL_TRY(make_tmap_w3d(&o.tmap_w, w.w_tc, 16, w.cout_pad, 4, 64, 16, o.nt, o.f16));
     ZL_TRY(make_tmap_nhwc(&o.tmap_x, x, 16, 32, o.f16, kTW + 1, kTH * o.sub + 1, 1));
     o.y_tma = ((y.pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     if (!o.y_tma) ZL_FAIL(ZL_INVALID_ARGUMENT, "conv_s2d: output must be 16-byte aligned");
@@ -681,10 +805,13 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     HaloParams p;
     p.y = o.y; p.res = o.res; p.bias = o.bias;
     p.N = o.N; p.H = o.H; p.W = o.W; p.Cin = o.Cin; p.Cout = o.Cout; p.ntile = o.ntile;
-    p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16; p.act = o.act;
+    p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16; p.act = o.act; p.silu_tanh = o.silu_tanh;
     p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma; p.nsplit = o.nsplit; p.nt = o.nt; p.ostage = o.ostage;
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
-    p.wtile_bytes = o.wtile_bytes; p.wtile_alloc = o.wtile_alloc; p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc;
+    p.wtile_bytes = o.wtile_bytes; p.wchunk_bytes = o.wchunk_bytes; p.wchunk_alloc = o.wchunk_alloc;
+    p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc; p.stage_stride = o.stage_stride;
+    p.wstream = o.wstream; p.nacc = o.nacc; p.acc_cols = o.acc_cols;
+    p.nacc_log2 = o.nacc == 8 ? 3 : (o.nacc == 4 ? 2 : (o.nacc == 2 ? 1 : 0));
     p.tmem_cols = o.tmem_cols;
     p.stats = stats;
     int grid = o.num_tiles * o.nsplit;

@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "half16.cuh"
@@ -44,7 +45,7 @@ struct Params {
     int32_t Ho, Wo, Cout, ypitch, rpitch, y_f32;
     int32_t k, stride, pad, act;
     int32_t kc, nkb, cchunks;
-    int32_t ntile, m_total, a_tma, stages, y_vec, r_vec, f16;
+    int32_t ntile, m_total, a_tma, stages, y_vec, r_vec, f16, silu_tanh;
     uint32_t a_bytes, b_bytes, stage_bytes, tmem_cols;
 };
 
@@ -219,7 +220,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 float a = __uint_as_float(v[i]) + __ldg(p.bias + cg + i);
-                f[i] = p.act ? __fdividef(a, 1.0f + __expf(-a)) : a;      // same formula as conv_halo.cu: results do not depend on the kernel chosen
+                f[i] = p.act ? (p.silu_tanh ? silu_tanh(a) : silu_exp(a)) : a;      // same formula as conv_halo.cu: results do not depend on the kernel chosen
             }
             const bool full = (cg + 16 <= p.Cout);
             if (p.res != nullptr) {
@@ -288,6 +289,18 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+// Which SiLU form the 16-bit conv epilogues use (half16.cuh).  ZL_SILU=exp|tanh overrides; read once per process.
+bool conv_silu_tanh(bool f16)
+{
+    static const int forced = [] {
+        const char* e = getenv("ZL_SILU");
+        if (!e) return -1;
+        return (e[0] == 't' || e[0] == 'T' || e[0] == '1') ? 1 : 0;
+    }();
+    if (forced >= 0) return forced == 1;
+    return !f16 ? kSiluTanhDefaultBf16 : kSiluTanhDefaultF16;
+}
+
 int32_t make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes, bool f16)
 {
@@ -338,6 +351,7 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     o.Ho = Ho; o.Wo = Wo; o.Cout = w.cout; o.ypitch = y.pitch; o.rpitch = res ? res->pitch : 0;
     o.y_f32 = y.dtype == DT_F32;
     o.f16 = x.dtype == DT_F16 ? 1 : 0;
+    o.silu_tanh = conv_silu_tanh(o.f16 != 0) ? 1 : 0;
     // 16-byte vector stores / residual loads need aligned slices; otherwise the epilogue goes scalar
     o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
@@ -409,7 +423,7 @@ int32_t conv_tc_launch(cudaStream_t st, const ConvTcOp& o)
     p.Ho = o.Ho; p.Wo = o.Wo; p.Cout = o.Cout; p.ypitch = o.ypitch; p.rpitch = o.rpitch; p.y_f32 = o.y_f32;
     p.k = o.k; p.stride = o.stride; p.pad = o.pad; p.act = o.act;
     p.kc = o.kc; p.nkb = o.nkb; p.cchunks = o.cchunks;
-    p.ntile = o.ntile; p.m_total = o.m_total; p.a_tma = o.a_tma; p.stages = o.stages; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16;
+    p.ntile = o.ntile; p.m_total = o.m_total; p.a_tma = o.a_tma; p.stages = o.stages; p.y_vec = o.y_vec; p.r_vec = o.r_vec; p.f16 = o.f16; p.silu_tanh = o.silu_tanh;
     p.a_bytes = kTileM * o.kc * 2;
     p.b_bytes = (uint32_t)o.ntile * o.kc * 2;
     p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);

@@ -38,11 +38,7 @@ Engine::~Engine()
     stop_workers();
     cudaSetDevice(cfg.device);
     for (auto& L : lanes) free_lane(*L);
-    for (auto& w : convs) {
-        if (w->w_simt) cudaFree(w->w_simt);
-        if (w->w_tc) cudaFree(w->w_tc);
-        if (w->bias) cudaFree(w->bias);
-    }
+    convs.clear();
     if (d_class_weights) cudaFree(d_class_weights);
     if (h_slots) cudaFreeHost(h_slots);
 }
@@ -117,7 +113,8 @@ int32_t Engine::load_weights(const void* blob, size_t len)
     ZL_TRY(parse_model(blob, len, &pm));              // ZLW1 container or an ultralytics ONNX export (BN fused)
     if (pm.scale != cfg.scale || pm.nc != cfg.num_classes)
         ZL_FAIL(ZL_MODEL_LOAD_FAILED, "weights are for scale " + std::to_string(pm.scale) + " nc " + std::to_string(pm.nc) + ", engine configured otherwise");
-    host_w.swap(pm.tensors);
+    std::lock_guard<std::mutex> load_guard(load_mu);      // concurrent loads (API call vs the adapter's model monitor) are serialised
+    const std::map<std::string, HostTensor>& host_w = pm.tensors;
 
     // the conv list of YOLOv8, names as ultralytics exports them
     struct Spec { std::string name; int cin, cout, k, s, act; };
@@ -164,7 +161,18 @@ int32_t Engine::load_weights(const void* blob, size_t len)
         conv(b + ".2", md.cc, md.nc, 1, 1, 0);
     }
 
-    // build the new weight set on the side; it replaces the live one atomically at the end (hot reload while serving)
+    // validate every tensor BEFORE the first device allocation: a bad or partially written file costs nothing
+    for (const Spec& s : specs) {
+        auto wi = host_w.find(s.name + ".weight"), bi = host_w.find(s.name + ".bias");
+        if (wi == host_w.end() || bi == host_w.end()) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "missing tensor " + s.name);
+        const HostTensor& W = wi->second;
+        if (W.dims.size() != 4 || (int)W.dims[0] != s.cout || (int)W.dims[1] != s.cin || (int)W.dims[2] != s.k || (int)W.dims[3] != s.k ||
+            W.data.size() != (size_t)s.cout * s.cin * s.k * s.k || bi->second.data.size() != (size_t)s.cout)
+            ZL_FAIL(ZL_MODEL_LOAD_FAILED, "shape mismatch for " + s.name);
+    }
+
+    // build the new weight set on the side; it replaces the live one atomically at the end (hot reload while serving).
+    // ConvWeights frees its device buffers in its destructor, so every early return below releases what was uploaded.
     std::vector<std::unique_ptr<ConvWeights>> new_convs;
     std::map<std::string, ConvWeights*> new_by_name;
     const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // "bf16" == any 16-bit tensor-core mode
@@ -225,7 +233,6 @@ int32_t Engine::load_weights(const void* blob, size_t len)
         new_by_name[s.name] = cw.get();
         new_convs.push_back(std::move(cw));
     }
-    host_w.clear();
     {
         // swap under every lane's lock: no batch is in flight, every cached op list / graph is stale
         std::vector<std::unique_lock<std::mutex>> locks;
@@ -240,11 +247,7 @@ int32_t Engine::load_weights(const void* blob, size_t len)
         }
         weights_loaded = true;
     }
-    for (auto& w : new_convs) {                 // the previous set
-        if (w->w_simt) cudaFree(w->w_simt);
-        if (w->w_tc) cudaFree(w->w_tc);
-        if (w->bias) cudaFree(w->bias);
-    }
+    new_convs.clear();                          // the previous set: ~ConvWeights frees its device buffers
     return ZL_OK;
 }
 

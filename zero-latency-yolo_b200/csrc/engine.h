@@ -131,7 +131,7 @@ private:
     int inline_dets(int B) const;
 
     ModelDef md;
-    std::map<std::string, HostTensor> host_w;
+    std::mutex load_mu;                            // one load_weights at a time
     std::vector<std::unique_ptr<ConvWeights>> convs;
     std::map<std::string, ConvWeights*> conv_by_name;
     float* d_class_weights = nullptr;

@@ -29,4 +29,18 @@ __device__ __forceinline__ float unpack1_16(uint16_t v, bool f16) {
     return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&v));
 }
 
+// SiLU in the conv epilogues.  Two forms behind one runtime flag (HaloParams / conv_tc Params `silu_tanh`):
+//   exp : x * rcp(1 + ex2(-x*log2e))                      two MUFU operations per element, ~2^-22 relative error
+//   tanh: h + h*tanh.approx(h), h = x/2                    ONE MUFU operation per element; tanh.approx.f32 has a maximum
+//         relative error of 2^-11, i.e. the result is good to the storage format (fp16: 2^-11, bf16: 2^-8) and no better.
+// The SFU pipe issues 16 lanes per clock per SM: on the narrow high-resolution layers the exp form alone costs as much
+// as the layer's MMAs.
+__device__ __forceinline__ float silu_exp(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_tanh(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 }  // namespace zl

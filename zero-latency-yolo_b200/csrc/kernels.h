@@ -17,6 +17,14 @@ struct ConvWeights {
     float* w_simt = nullptr;       // fp32 [ktot][cout_pad]  (k index = (r*k+s)*cin + c)
     __nv_bfloat16* w_tc = nullptr; // bf16 [cout_pad][ktot]  K-major rows for UMMA B
     float* bias = nullptr;         // fp32 [cout_pad]
+    ConvWeights() = default;
+    ConvWeights(const ConvWeights&) = delete;
+    ConvWeights& operator=(const ConvWeights&) = delete;
+    ~ConvWeights() {               // owns its device buffers (load_weights error paths, hot reload, engine teardown)
+        if (w_simt) cudaFree(w_simt);
+        if (w_tc) cudaFree(w_tc);
+        if (bias) cudaFree(bias);
+    }
 };
 
 // ---------------------------------------------------------------- P1
@@ -40,6 +48,10 @@ int32_t launch_conv0_direct(cudaStream_t st, const ConvWeights& w, const View& x
 int32_t launch_pre_conv0(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n, int32_t mw, int32_t mh,
                          const ConvWeights& w, const View& y);
 
+// SiLU form of the 16-bit conv epilogues (half16.cuh): true = one-MUFU tanh form.  ZL_SILU=exp|tanh overrides the defaults.
+constexpr bool kSiluTanhDefaultBf16 = true, kSiluTanhDefaultF16 = true;
+bool conv_silu_tanh(bool f16);
+
 // tcgen05 implicit GEMM.  A operand staged either by TMA (1x1 convs: plain 2-D
 // tiled map over [pixels][cin]) or by producer warps gathering NHWC rows into
 // the swizzled UMMA layout (3x3, any stride); B (weights) always by TMA.
@@ -55,7 +67,7 @@ struct ConvTcOp {
     int32_t k, stride, pad, act;
     int32_t kc, swz, nkb, cchunks;     // channels per K-block, swizzle bytes, #K-blocks, chunks per tap
     int32_t ntile, ngrid;              // N tile (<=256, multiple of 16) and number of N tiles
-    int32_t m_total, a_tma, y_vec, r_vec, f16;
+    int32_t m_total, a_tma, y_vec, r_vec, f16, silu_tanh;
     int32_t stages, smem_bytes, tmem_cols;
     double flops, bytes;
 };
@@ -73,10 +85,11 @@ struct ConvHaloOp {
     const __nv_bfloat16* res;
     const float* bias;
     int32_t N, H, W, Cin, Cout, ntile;
-    int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act;
+    int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act, silu_tanh;
     int32_t kc, cchunks, stages, sub, y_tma, taps, nsplit, nt, mode, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
-    uint32_t wtile_bytes, wtile_alloc, patch_bytes, patch_alloc, subpatch_alloc, tmem_cols;
+    int32_t wstream, nacc, acc_cols;     // weights streamed with the patches / resident; TMEM accumulator ring
+    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride, tmem_cols;
     int32_t smem_bytes;
     double flops, bytes;
 };
@@ -87,8 +100,9 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
 // stats != nullptr launches the instrumented instantiation: kHaloStatSlots cycle counters summed over CTAs
 //   0 producer waiting for a free patch stage   1 MMA warp waiting for a patch   2 MMA warp waiting for a drained accumulator
 //   3 MMA warp issuing   4 epilogue warp 2 waiting for an accumulator   5 epilogue warp 2 busy   6 CTA lifetime (sum)
-//   7 prologue (sum)   8 MMA warp waiting for the weights   9 slowest CTA   10 CTAs
-constexpr int kHaloStatSlots = 12;
+//   7 prologue (sum)   8 MMA warp waiting for the weights   9 slowest CTA   10 CTAs   11 plan (packed)
+//   12-15 epilogue warp 2: tcgen05.ld wait / waiting for the staging block / st.shared + fence + store issue / accumulator hand-back
+constexpr int kHaloStatSlots = 16;
 int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& op, int num_sms, unsigned long long* stats = nullptr);
 
 // ---------------------------------------------------------------- pool / upsample

@@ -123,6 +123,13 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // smem -> global tensor store (bulk async group); OOB elements of the box are clipped by the hardware.
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
     asm volatile(

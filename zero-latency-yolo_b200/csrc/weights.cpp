@@ -17,6 +17,20 @@
 namespace zl {
 namespace {
 
+// Element count of a tensor whose dims come from the FILE: every dim in 1..2^31, and the running product never beyond
+// `limit` (what the container could possibly hold), so the byte-size comparisons below cannot wrap.
+bool checked_count(const std::vector<uint32_t>& dims, size_t limit, size_t* out)
+{
+    size_t cnt = 1;
+    for (uint32_t d : dims) {
+        if (d == 0 || d > 0x7fffffffu) return false;
+        if (cnt > limit / d) return false;
+        cnt *= d;
+    }
+    *out = cnt;
+    return true;
+}
+
 struct Reader {
     const uint8_t* p; const uint8_t* end; bool ok = true;
     bool more() const { return ok && p < end; }
@@ -56,16 +70,26 @@ bool parse_tensor(const uint8_t* b, const uint8_t* e, std::string* name, HostTen
         const uint32_t f = r.field(&wt, &s, &se, &v);
         if (!r.ok) return false;
         if (f == 1) {
-            if (wt == 0) t->dims.push_back((uint32_t)v);
-            else if (wt == 2) { Reader d{s, se}; while (d.more()) t->dims.push_back((uint32_t)d.varint()); if (!d.ok) return false; }
+            // ONNX dims are int64: anything that does not fit a positive 31-bit value is rejected, never truncated
+            if (wt == 0) { if (v == 0 || v > 0x7fffffffull) return false; t->dims.push_back((uint32_t)v); }
+            else if (wt == 2) {
+                Reader d{s, se};
+                while (d.more()) { const uint64_t dv = d.varint(); if (!d.ok || dv == 0 || dv > 0x7fffffffull) return false; t->dims.push_back((uint32_t)dv); }
+                if (!d.ok) return false;
+            }
+            if (t->dims.size() > 8) return false;
         } else if (f == 2 && wt == 0) data_type = (int)v;
         else if (f == 8 && wt == 2) name->assign((const char*)s, (size_t)(se - s));
         else if (f == 9 && wt == 2) { raw = s; raw_end = se; }
         else if (f == 4 && wt == 2) { fd = s; fd_end = se; }
         else if (f == 4 && wt == 5) { float x; const uint32_t u = (uint32_t)v; std::memcpy(&x, &u, 4); unpacked.push_back(x); }
     }
-    size_t cnt = 1;
-    for (uint32_t d : t->dims) cnt *= d;
+    size_t cnt = 0;
+    if (!checked_count(t->dims, (size_t)(e - b), &cnt)) {     // a tensor cannot have more elements than its message has bytes
+        if (data_type == 1 || data_type == 10) return false;
+        t->data.clear();
+        return true;
+    }
     if (data_type == 1) {
         if (raw && (size_t)(raw_end - raw) == cnt * 4) { t->data.resize(cnt); std::memcpy(t->data.data(), raw, cnt * 4); }
         else if (fd && (size_t)(fd_end - fd) == cnt * 4) { t->data.resize(cnt); std::memcpy(t->data.data(), fd, cnt * 4); }
@@ -130,9 +154,9 @@ int32_t parse_zlw(const uint8_t* p, size_t len, ParsedModel* out)
         uint32_t nd; std::memcpy(&nd, p + off, 4); off += 4;
         if (nd > 8 || off + 4ull * nd > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "bad tensor rank");
         HostTensor t; t.dims.resize(nd);
-        size_t cnt = 1;
-        for (uint32_t d = 0; d < nd; ++d) { std::memcpy(&t.dims[d], p + off, 4); off += 4; cnt *= t.dims[d]; }
-        if (off + cnt * 4 > len) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated tensor " + name);
+        for (uint32_t d = 0; d < nd; ++d) { std::memcpy(&t.dims[d], p + off, 4); off += 4; }
+        size_t cnt = 0;
+        if (!checked_count(t.dims, (len - off) / 4, &cnt)) ZL_FAIL(ZL_MODEL_LOAD_FAILED, "truncated or oversized tensor " + name);
         t.data.resize(cnt);
         std::memcpy(t.data.data(), p + off, cnt * 4); off += cnt * 4;
         out->tensors[name] = std::move(t);

@@ -147,30 +147,36 @@ int main(int argc, char** argv)
         {"ld 128B x10x18 L2-res",   64, 64, 80, 32, 64, 10, 18, 1, 128, 8, 16, 1},
         {"ld 32B x10x66 L2-res",    16, 16, 160, 32, 16, 10, 66, 1, 32, 8, 64, 1},
     };
-    printf("\n%-28s %6s %8s %9s %9s %8s\n", "TMA loads (1 thread/CTA)", "stages", "box B", "us", "GB/s", "B/clk/SM");
+    printf("\n%-28s %5s %6s %8s %9s %9s %8s %9s\n", "TMA loads (1 thread/CTA)", "grid", "stages", "box B", "us", "GB/s", "B/clk/SM", "clk/box");
     for (const LoadCfg& c : lc) {
-        for (int stages : {3, 8}) {
-            CUtensorMap m;
-            make_map(&m, buf, c.N, c.HW, c.HW, c.C, c.pitchC, c.bc, c.bw, c.bh, c.estride, c.swz);
-            const uint32_t box_bytes = (uint32_t)c.bc * 2 * c.bw * c.bh;
-            const uint32_t alloc = (box_bytes + 1023u) & ~1023u;
-            if (1024u + 1024u + (uint32_t)stages * alloc > 227u * 1024u) continue;
-            Geo g{c.HW / c.stepw, c.HW / c.steph, c.N, c.stepw, c.steph};
-            const size_t total_bytes_tensor = (size_t)c.N * c.HW * c.HW * c.pitchC * 2;
-            if (total_bytes_tensor > cap) { printf("%s: tensor too large\n", c.name); continue; }
-            const size_t smem = 2048 + 1024 + (size_t)stages * alloc;
-            int iters = (int)((size_t)3 * 1024 * 1024 * 1024 / ((size_t)sms * box_bytes));
-            if (iters > 20000) iters = 20000;
-            iters = iters / c.nchunk * c.nchunk;
-            load_kernel<<<sms, 128, smem>>>(m, g, stages, box_bytes, alloc, iters / 8 + c.nchunk, c.bc, c.nchunk);
-            CK(cudaDeviceSynchronize());
-            CK(cudaEventRecord(e0));
-            load_kernel<<<sms, 128, smem>>>(m, g, stages, box_bytes, alloc, iters, c.bc, c.nchunk);
-            CK(cudaEventRecord(e1));
-            CK(cudaDeviceSynchronize());
-            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-            const double bytes = (double)sms * iters * box_bytes;
-            printf("%-28s %6d %8u %9.1f %9.1f %8.2f\n", c.name, stages, box_bytes, ms * 1e3, bytes / ms / 1e6, bytes / sms / (ms * 1e-3 * clk * 1e3));
+        for (int grid : {1, sms}) {
+            for (int stages : {1, 2, 4, 8}) {
+                if (grid == sms && (stages == 1 || stages == 2)) continue;
+                CUtensorMap m;
+                make_map(&m, buf, c.N, c.HW, c.HW, c.C, c.pitchC, c.bc, c.bw, c.bh, c.estride, c.swz);
+                const uint32_t box_bytes = (uint32_t)c.bc * 2 * c.bw * c.bh;
+                const uint32_t alloc = (box_bytes + 1023u) & ~1023u;
+                if (1024u + 1024u + (uint32_t)stages * alloc > 227u * 1024u) continue;
+                // grid 1: walk only the first image's tiles (L2-resident after the warm-up pass)
+                Geo g{c.HW / c.stepw, c.HW / c.steph, grid == 1 ? 1 : c.N, c.stepw, c.steph};
+                const size_t total_bytes_tensor = (size_t)c.N * c.HW * c.HW * c.pitchC * 2;
+                if (total_bytes_tensor > cap) { printf("%s: tensor too large\n", c.name); continue; }
+                const size_t smem = 2048 + 1024 + (size_t)stages * alloc;
+                int iters = (int)((size_t)3 * 1024 * 1024 * 1024 / ((size_t)sms * box_bytes));
+                if (iters > 20000) iters = 20000;
+                if (grid == 1) iters = 4000;
+                iters = iters / c.nchunk * c.nchunk;
+                load_kernel<<<grid, 128, smem>>>(m, g, stages, box_bytes, alloc, grid == 1 ? iters : iters / 8 + c.nchunk, c.bc, c.nchunk);
+                CK(cudaDeviceSynchronize());
+                CK(cudaEventRecord(e0));
+                load_kernel<<<grid, 128, smem>>>(m, g, stages, box_bytes, alloc, iters, c.bc, c.nchunk);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+                float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                const double bytes = (double)grid * iters * box_bytes;
+                printf("%-28s %5d %6d %8u %9.1f %9.1f %8.2f %9.0f\n", c.name, grid, stages, box_bytes, ms * 1e3, bytes / ms / 1e6, bytes / grid / (ms * 1e-3 * clk * 1e3),
+                       ms * 1e-3 * clk * 1e3 / iters);
+            }
         }
     }
 

@@ -268,8 +268,8 @@ class Engine:
                 for i in range(n.value)]
 
     def profile_stalls(self, set_idx=0):
-        """[n_ops, 12] uint64 cycle counters of the instrumented persistent conv kernel (see zl_b200.h)."""
-        out = np.zeros((256, 12), np.uint64)
+        """[n_ops, 16] uint64 cycle counters of the instrumented persistent conv kernel (see zl_b200.h)."""
+        out = np.zeros((256, 16), np.uint64)
         n = C.c_int32()
         _check(lib().zl_engine_profile_stalls(self.h, set_idx, _ptr(out), 256, C.byref(n)))
         return out[:n.value]
