@@ -102,6 +102,27 @@ __device__ __forceinline__ void issue_chunk(uint32_t tmem_d, uint32_t ntile, uin
     }
 }
 
+// Division-free walk over a CTA's tiles: tile -> (image n, tile row ty, tile column tx), advanced by a fixed step.
+struct TileWalk { int n, ty, tx, dn, dty, dtx; };
+__device__ __forceinline__ void walk_init(TileWalk& t, int tile, int step, int tiles_x, int tiles_y)
+{
+    const int per_img = tiles_x * tiles_y;
+    t.n = tile / per_img;
+    int rem = tile - t.n * per_img;
+    t.ty = rem / tiles_x; t.tx = rem - t.ty * tiles_x;
+    t.dn = step / per_img;
+    rem = step - t.dn * per_img;
+    t.dty = rem / tiles_x; t.dtx = rem - t.dty * tiles_x;
+}
+__device__ __forceinline__ void walk_next(TileWalk& t, int tiles_x, int tiles_y)
+{
+    t.tx += t.dtx;
+    if (t.tx >= tiles_x) { t.tx -= tiles_x; ++t.ty; }
+    t.ty += t.dty;
+    if (t.ty >= tiles_y) { t.ty -= tiles_y; ++t.n; }
+    t.n += t.dn;
+}
+
 template <int MODE, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -150,7 +171,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         mbar_init(bar_wfull, (uint32_t)kProducers);
         for (int a = 0; a < p.nacc; ++a) {
             mbar_init(bar_tfull + 8u * a, 1u);
-            mbar_init(bar_tempty + 8u * a, (uint32_t)kEpiWarps);   // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8u * a, (uint32_t)kEpiWarps / 2u);   // one arrival per epilogue warp of the set that drains it
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_w);
@@ -195,10 +216,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             const uint32_t np = (uint32_t)stages < (uint32_t)kProducers ? (uint32_t)stages : (uint32_t)kProducers;
             uint32_t s = 0, ph = 0, turn = 0;
             const uint32_t stage_tx = p.patch_bytes * (uint32_t)NPATCH + (p.wstream ? p.wchunk_bytes : 0u);
-            for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-                const int n = tile / tiles_per_img;
-                const int rem = tile - n * tiles_per_img;
-                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            TileWalk tw_;
+            walk_init(tw_, tile0, tile_step, p.tiles_x, p.tiles_y);
+            for (int tile = tile0; tile < p.num_tiles; tile += tile_step, walk_next(tw_, p.tiles_x, p.tiles_y)) {
+                const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     if (turn == pi) {
                         ZL_ST_BEGIN(t0);
@@ -290,11 +311,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
     } else {
         // ===== epilogue warps: TMEM -> +bias -> SiLU -> +residual -> 16-bit / fp32 NHWC =====
-        // Everything below indexes its register arrays with compile-time constants (fully unrolled, predicates instead of
-        // data-dependent trip counts): a[] / v[] must never be demoted to local memory — this loop paces the kernel on the
-        // narrow high-resolution layers (profiles/: epilogue warps busy 60-80 % of the CTA lifetime in round 1).
+        // * Register arrays are indexed with compile-time constants only (fully unrolled, predicates instead of data-dependent
+        //   trip counts): a[] / v[] must never be demoted to local memory.
+        // * One (32 px x 16 ch) item is a chain of latencies (barrier wake-up, tcgen05.ld, SFU, proxy fence, bulk-store issue:
+        //   ~1300 cycles measured) around very little arithmetic, so the 16 warps work as TWO SETS of 8 on alternate tiles:
+        //   two tiles' chains overlap, and a warp's items of one tile are processed in pairs with both tcgen05.ld in flight.
+        // * No integer division in the loop: tile coordinates and (sub-tile, chunk) indices advance incrementally.
         const uint32_t q = warp & 3u;                        // TMEM lane quarter this warp may read
-        const int cgp = (int)(warp - 2u) >> 2;               // which share of the (sub-tile, 16-column) work items
+        const int cgp = (int)(warp - 2u) >> 2;               // 0..3 within the quarter
+        const int set = cgp >> 1, c2 = cgp & 1;              // tile parity this warp serves; which half of the quarter's items
         const int row = (int)(q * 32u + lane);               // A row == TMEM lane: h = row / 8, w = row % 8
         const int th = row >> 3, tw = row & 7;
         const int nchunk = ntile >> 4;
@@ -305,23 +330,25 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const bool f16 = p.f16 != 0;
         const bool res_fast = res_g != nullptr && p.r_vec;  // residual rows are 16-byte aligned: two 128-bit loads per thread
         uint32_t nstore = 0;
-        uint32_t tl = 0;
+        // first item of this warp in every tile: item index c2 -> (sub-tile j0, chunk k0)
+        const int j0 = nchunk == 1 ? c2 : 0, k0 = nchunk == 1 ? 0 : c2;
+        // tile walk: this set takes tiles tile0 + set*step, then every 2*step-th; (n, ty, tx) advance by a fixed decomposition
+        TileWalk tw_;
+        walk_init(tw_, tile0 + set * tile_step, 2 * tile_step, p.tiles_x, p.tiles_y);
         // the residual (and, transitively, everything this kernel overwrites) belongs to earlier kernels of the stream
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
-            const uint32_t acc = tl & (uint32_t)(p.nacc - 1), aph = (tl >> p.nacc_log2) & 1u;
-            const int n = tile / tiles_per_img;
-            const int rem = tile - n * tiles_per_img;
-            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        for (int tile = tile0 + set * tile_step, tl = set; tile < p.num_tiles; tile += 2 * tile_step, tl += 2, walk_next(tw_, p.tiles_x, p.tiles_y)) {
+            const uint32_t acc = (uint32_t)tl & (uint32_t)(p.nacc - 1), aph = ((uint32_t)tl >> p.nacc_log2) & 1u;
+            const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
             const int ox = tx * kTW + tw;
+            const size_t img_row0 = (size_t)n * p.H;
             // residual of this warp's FIRST item: issued before the accumulator wait, so its latency hides under the MMAs
             uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
             bool r_have = false;
-            if (res_fast && cgp < items) {
-                const int j = cgp / nchunk, c0 = (cgp - j * nchunk) << 4;
-                const int oy = (ty * p.sub + j) * kTH + th;
-                if (oy < p.H && ox < p.W && c0 + 16 <= cout_l) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res_g + (((size_t)n * p.H + oy) * p.W + ox) * p.rpitch + c0);
+            if (res_fast && c2 < items) {
+                const int oy = (ty * p.sub + j0) * kTH + th;
+                if (oy < p.H && ox < p.W && (k0 << 4) + 16 <= cout_l) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res_g + ((img_row0 + oy) * p.W + ox) * p.rpitch + (k0 << 4));
                     r0 = __ldg(rp);
                     r1 = __ldg(rp + 1);
                     r_have = true;
@@ -335,121 +362,134 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             tc_fence_after();
             ZL_ST_BEGIN(t_epi);
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (uint32_t)p.acc_cols;
-            for (int item = cgp; item < items; item += kEpiWarps / 4) {
-                const int j = item / nchunk, c0 = (item - j * nchunk) << 4;
-                uint32_t v[16];
-                tmem_ld16(taddr + (uint32_t)(j * p.nt + c0), v);
-                const int oy = (ty * p.sub + j) * kTH + th;
-                const bool in_img = oy < p.H && ox < p.W && c0 < cout_l;
-                const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
-                if (item != cgp) {                           // later items of the same tile load their residual here
-                    r_have = false;
-                    if (res_fast && in_img && c0 + 16 <= cout_l) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res_g + m * p.rpitch + c0);
-                        r0 = __ldg(rp);
-                        r1 = __ldg(rp + 1);
-                        r_have = true;
-                    }
-                }
+            int j = j0, k = k0;                              // (sub-tile, chunk) of the pair's first item
+            for (int item = c2; item < items; item += 4) {
+                // the pair: item and item + 2
+                int jb = j, kb = k + 2;
+                while (kb >= nchunk) { kb -= nchunk; ++jb; }
+                const bool have_b = item + 2 < items;
+                uint32_t v[2][16];
+                tmem_ld16(taddr + (uint32_t)(j * p.nt + (k << 4)), v[0]);
+                if (have_b) tmem_ld16(taddr + (uint32_t)(jb * p.nt + (kb << 4)), v[1]);
                 {
                     ZL_ST_BEGIN(t0);
                     tmem_ld_wait();
                     ZL_ST_END(t0, st_c);
                 }
-                float a[16];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
-                    a[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-                    a[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-                }
-                if (p.act) {
-                    if (p.silu_tanh) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) a[i] = silu_tanh(a[i]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) a[i] = silu_exp(a[i]);
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !have_b) break;
+                    const int jj = h == 0 ? j : jb, c0 = (h == 0 ? k : kb) << 4;
+                    const int oy = (ty * p.sub + jj) * kTH + th;
+                    const bool in_img = oy < p.H && ox < p.W && c0 < cout_l;
+                    const size_t m = (img_row0 + oy) * p.W + ox;
+                    if (h == 1 || item != c2) {               // only the tile's first item was prefetched
+                        r_have = false;
+                        if (res_fast && in_img && c0 + 16 <= cout_l) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(res_g + m * p.rpitch + c0);
+                            r0 = __ldg(rp);
+                            r1 = __ldg(rp + 1);
+                            r_have = true;
+                        }
                     }
-                }
-                if (r_have) {
-                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    float a[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float ra, rb;
-                        unpack2_16(rw[i], f16, ra, rb);
-                        a[2 * i] += ra;
-                        a[2 * i + 1] += rb;
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
+                        a[4 * i + 0] = __uint_as_float(v[h][4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[h][4 * i + 1]) + b4.y;
+                        a[4 * i + 2] = __uint_as_float(v[h][4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[h][4 * i + 3]) + b4.w;
                     }
-                } else if (res_g != nullptr && in_img) {     // unaligned or ragged residual rows: element by element, statically indexed
-                    const uint16_t* rp = reinterpret_cast<const uint16_t*>(res_g + m * p.rpitch + c0);
+                    if (p.act) {
+                        if (p.silu_tanh) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < cout_l) a[i] += unpack1_16(rp[i], f16);
-                }
-                if (p.y_tma) {
-                    // ---- fast path: stage [32 px][16 ch] in smem, one TMA store per warp (image borders and ragged channel
-                    //      counts are clipped by the hardware against the tensor map's extents)
-                    const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
-                    {
-                        ZL_ST_BEGIN(t0);
-                        if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
-                        ZL_ST_END(t0, st_d);
-                    }
-                    ZL_ST_BEGIN(t_st);
-                    if (p.y_f32) {
-                        const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
-                        const uint32_t rowb = sbuf + lane * 64u;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)i) ^ xr) << 4)), "r"(__float_as_uint(a[4 * i])),
-                                         "r"(__float_as_uint(a[4 * i + 1])), "r"(__float_as_uint(a[4 * i + 2])), "r"(__float_as_uint(a[4 * i + 3])) : "memory");
-                    } else {
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
-                        const uint32_t xr = (lane >> 2) & 1u;                                       // 32-B swizzle: chunk ^= address bit 7
-                        const uint32_t rowb = sbuf + lane * 32u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((1u ^ xr) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (leader) {
-                        tma_store_4d(&tmap_y, sbuf, n_off + c0, tx * kTW, (ty * p.sub + j) * kTH + (int)q * 4, n);
-                        tma_store_commit();
-                    }
-                    ZL_ST_END(t_st, st_e);
-                    ++nstore;
-                } else if (in_img) {
-                    // ---- outputs whose rows are not 16-byte aligned (e.g. nc = 2 class maps): plain stores, statically indexed
-                    const bool full = (c0 + 16 <= cout_l);
-                    if (p.y_f32) {
-                        float* yp = reinterpret_cast<float*>(y_g) + m * p.ypitch + c0;
-                        if (full && p.y_vec) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                reinterpret_cast<float4*>(yp)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                            for (int i = 0; i < 16; ++i) a[i] = silu_tanh(a[i]);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c0 + i < cout_l) yp[i] = a[i];
+                            for (int i = 0; i < 16; ++i) a[i] = silu_exp(a[i]);
                         }
-                    } else {
-                        uint16_t* yp = reinterpret_cast<uint16_t*>(y_g) + m * p.ypitch + c0;
-                        if (full && p.y_vec) {
+                    }
+                    if (r_have) {
+                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float ra, rb;
+                            unpack2_16(rw[i], f16, ra, rb);
+                            a[2 * i] += ra;
+                            a[2 * i + 1] += rb;
+                        }
+                    } else if (res_g != nullptr && in_img) {     // unaligned or ragged residual rows: element by element, statically indexed
+                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(res_g + m * p.rpitch + c0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < cout_l) a[i] += unpack1_16(rp[i], f16);
+                    }
+                    if (p.y_tma) {
+                        // ---- fast path: stage [32 px][16 ch] in smem, one TMA store per warp (image borders and ragged channel
+                        //      counts are clipped by the hardware against the tensor map's extents)
+                        const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
+                        {
+                            ZL_ST_BEGIN(t0);
+                            if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
+                            ZL_ST_END(t0, st_d);
+                        }
+                        ZL_ST_BEGIN(t_st);
+                        if (p.y_f32) {
+                            const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
+                            const uint32_t rowb = sbuf + lane * 64u;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)i) ^ xr) << 4)), "r"(__float_as_uint(a[4 * i])),
+                                             "r"(__float_as_uint(a[4 * i + 1])), "r"(__float_as_uint(a[4 * i + 2])), "r"(__float_as_uint(a[4 * i + 3])) : "memory");
+                        } else {
                             uint32_t w[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
-                            reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        } else {
+                            const uint32_t xr = (lane >> 2) & 1u;                                       // 32-B swizzle: chunk ^= address bit 7
+                            const uint32_t rowb = sbuf + lane * 32u;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((1u ^ xr) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (leader) {
+                            tma_store_4d(&tmap_y, sbuf, n_off + c0, tx * kTW, (ty * p.sub + jj) * kTH + (int)q * 4, n);
+                            tma_store_commit();
+                        }
+                        ZL_ST_END(t_st, st_e);
+                        ++nstore;
+                    } else if (in_img) {
+                        // ---- outputs whose rows are not 16-byte aligned (e.g. nc = 2 class maps): plain stores, statically indexed
+                        const bool full = (c0 + 16 <= cout_l);
+                        if (p.y_f32) {
+                            float* yp = reinterpret_cast<float*>(y_g) + m * p.ypitch + c0;
+                            if (full && p.y_vec) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c0 + i < cout_l) yp[i] = pack1_16(a[i], f16);
+                                for (int i = 0; i < 4; ++i)
+                                    reinterpret_cast<float4*>(yp)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < cout_l) yp[i] = a[i];
+                            }
+                        } else {
+                            uint16_t* yp = reinterpret_cast<uint16_t*>(y_g) + m * p.ypitch + c0;
+                            if (full && p.y_vec) {
+                                uint32_t w[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
+                                reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                                reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < cout_l) yp[i] = pack1_16(a[i], f16);
+                            }
                         }
                     }
                 }
+                // next pair: item + 4
+                k += 4;
+                while (k >= nchunk) { k -= nchunk; ++j; }
             }
             // this warp is done reading the accumulator: hand it back to the MMA warp
             {
@@ -609,7 +649,7 @@ static double mma_cycles(int n) { return std::max(46.0, std::max(32.0 + n / 4.0,
 //   streamed : (3x3 only) every stage carries the patch chunk AND that chunk's weights [taps][nt][kc], so nt can stay at the
 //              full Cout (<= 256) however large taps*Cin*Cout is — the deep 20x20 / 40x40 layers, where a resident slice
 //              forces nt down to 16-48 and every MMA below N = 64 costs the same 46 cycles.
-// Every candidate (kc, nsplit, mode) that fits is priced with a small cycle model and the cheapest one wins.
+// kc is fixed per layer (conv_kc).  Every candidate (nsplit, mode) that fits is priced with a small cycle model and the cheapest one wins.
 static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int num_sms, PersistPlan* best)
 {
     const bool s2 = w.k == 3 && w.stride == 2;
@@ -629,8 +669,7 @@ static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int
     const uint32_t fixed0 = 3072u + (uint32_t)kEpiWarps * (y.dtype == DT_F32 ? 4096u : 2048u);
     static const int force_stream = [] { const char* e = getenv("ZL_WSTREAM"); return e ? atoi(e) : -1; }();   // A/B: 0 never, 1 whenever possible
     bool found = false;
-    for (int kc : {64, 32, 16}) {
-        if (w.cin % kc) continue;
+    for (int kc : {conv_kc(w, y.dtype == DT_F32)}) {        // fixed per layer: the accumulation order must not depend on the plan
         PersistPlan pl = base;
         pl.kc = kc;
         pl.cchunks = w.cin / kc;

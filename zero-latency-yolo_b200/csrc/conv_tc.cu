@@ -289,6 +289,32 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+// Channels per K chunk of a 16-bit conv.  A function of the LAYER only (never of the batch or the tile count): both
+// tcgen05 kernels accumulate in (chunk, tap, 16-wide k-step) order, so a frame's result does not depend on how it was
+// batched or on which kernel / launch plan ran (tests: test_16bit_results_do_not_depend_on_batch).
+//   * the widest of 64 / 32 / 16 that divides Cin (128 / 64 / 32-byte swizzle rows);
+//   * 3x3 stride 2: at most 32 (a stage holds four parity sub-patches);
+//   * 3x3: halved until two pipeline stages of the weight-STREAMING plan fit at full output width (conv_halo.cu), so
+//     the deep layers never have to fall back to a narrow N split.
+int32_t conv_kc(const ConvWeights& w, bool y_f32)
+{
+    int kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
+    if (w.k == 3 && w.stride == 2 && kc == 64) kc = 32;
+    if (w.k == 3 && w.cin >= 16 && w.cin % 16 == 0) {
+        const int s2 = w.stride == 2;
+        const uint32_t fixed = 3072u + 16u * (y_f32 ? 4096u : 2048u);
+        const int nt = w.cout_pad < 256 ? w.cout_pad : 256;
+        while (kc > 16) {
+            const uint32_t patch = (((uint32_t)(s2 ? 9 : 10) * (16 + (s2 ? 1 : 2)) * kc * 2 + 1023u) & ~1023u) * (s2 ? 4u : 1u);
+            const uint32_t wchunk = (9u * nt * kc * 2 + 1023u) & ~1023u;
+            const bool resident_fits = fixed + (uint32_t)(w.cin / kc) * wchunk + 3u * patch <= 227u * 1024u;
+            if (resident_fits || fixed + 2u * (patch + wchunk) <= 227u * 1024u) break;
+            kc /= 2;
+        }
+    }
+    return kc;
+}
+
 // Which SiLU form the 16-bit conv epilogues use (half16.cuh).  ZL_SILU=exp|tanh overrides; read once per process.
 bool conv_silu_tanh(bool f16)
 {
@@ -356,8 +382,7 @@ int32_t conv_tc_prepare(const ConvWeights& w, const View& x, const View& y, cons
     o.y_vec = ((y.pitch * y.esize()) % 16 == 0 && (reinterpret_cast<uintptr_t>(y.ptr) & 15) == 0) ? 1 : 0;
     o.r_vec = (res && (res->pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(res->ptr) & 15) == 0) ? 1 : 0;
     o.k = w.k; o.stride = w.stride; o.pad = pad; o.act = w.act;
-    o.kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
-    if (w.k == 3 && w.stride == 2 && o.kc == 64) o.kc = 32;     // same K chunking as the persistent kernel's stride-2 mode: identical accumulation order
+    o.kc = conv_kc(w, y.dtype == DT_F32);                       // same K chunking as the persistent kernel: identical accumulation order
     o.swz = o.kc * 2;
     o.cchunks = w.cin / o.kc;
     o.nkb = w.k * w.k * o.cchunks;

@@ -51,6 +51,8 @@ int32_t launch_pre_conv0(cudaStream_t st, const uint8_t* staging, const FrameDes
 // SiLU form of the 16-bit conv epilogues (half16.cuh): true = one-MUFU tanh form.  ZL_SILU=exp|tanh overrides the defaults.
 constexpr bool kSiluTanhDefaultBf16 = true, kSiluTanhDefaultF16 = true;
 bool conv_silu_tanh(bool f16);
+// Channels per K chunk of a 16-bit conv: a function of the layer only, shared by both tcgen05 kernels (conv_tc.cu).
+int32_t conv_kc(const ConvWeights& w, bool y_f32);
 
 // tcgen05 implicit GEMM.  A operand staged either by TMA (1x1 convs: plain 2-D
 // tiled map over [pixels][cin]) or by producer warps gathering NHWC rows into
