@@ -19,6 +19,7 @@
 // patch (1.4x the tile's input) is read and the output written once.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -68,6 +69,7 @@ struct HaloParams {
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act, silu_tanh;
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
+    int32_t epi_variant;                             // epilogue_role specialisation (0..5 fast, 6 generic)
     int32_t wstream, nacc, nacc_log2, acc_cols;      // weights streamed with the patches (1) or resident (0); accumulator ring
     uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride, tmem_cols;
     unsigned long long* stats;      // STATS instantiation only: kHaloStatSlots cycle counters summed over CTAs (zl_engine_profile_stalls)
@@ -121,6 +123,256 @@ __device__ __forceinline__ void walk_next(TileWalk& t, int tiles_x, int tiles_y)
     t.ty += t.dty;
     if (t.ty >= tiles_y) { t.ty -= tiles_y; ++t.n; }
     t.n += t.dn;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Epilogue role.  VAR 0..5 are the specialised fast variants (format = VAR / 3: 0 bf16, 1 fp16; kind = VAR % 3: 0 SiLU ->
+// 16-bit, 1 SiLU + residual -> 16-bit, 2 no activation -> fp32), chosen on the host when the output goes through bulk
+// tensor stores and every 16-channel chunk is whole; VAR 6 is the generic body with run-time flags (ragged channel
+// counts, unaligned rows, plain stores).  Round-2 ncu: the kernel is ISSUE-bound in these warps (issue slots ~60 % busy,
+// ~350 instructions per 32 px x 16 ch item of which 64 are the arithmetic), so the hot variants carry no run-time format
+// / activation / residual branches, no 64-bit index arithmetic per item, and waiting warps sleep in mbarrier.try_wait.
+// * The 16 warps work as TWO SETS of 8 on alternate tiles; a warp's items of one tile are processed in pairs with both
+//   tcgen05.ld in flight.  No integer division in the loop.
+// * Register arrays are indexed with compile-time constants only: a[] / v[] must never be demoted to local memory.
+struct EpiCtx {
+    const CUtensorMap* tmap_y;
+    const float* bias_s;
+    uint32_t tmem_base, bar_tfull, bar_tempty, obase;
+    int tile0, tile_step, n_off, ntile, cout_l;
+    const __nv_bfloat16* res_g;
+    void* y_g;
+    uint32_t warp, lane;
+};
+
+template <bool STATS, int VAR>
+__device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx& c)
+{
+    constexpr bool FAST = VAR < 6;
+    constexpr bool F16C = (VAR / 3) == 1;                    // compile-time format of the fast variants
+    constexpr int KIND = VAR % 3;
+    long long st_a = 0, st_b = 0, st_c = 0, st_d = 0, st_e = 0, st_f = 0;
+#define ZL_ST_BEGIN(t) long long t = 0; if (STATS) t = clock64()
+#define ZL_ST_END(t, acc) if (STATS) acc += clock64() - t
+    const uint32_t warp = c.warp, lane = c.lane;
+    const uint32_t q = warp & 3u;                            // TMEM lane quarter this warp may read
+    const int cgp = (int)(warp - 2u) >> 2;                   // 0..3 within the quarter
+    const int set = cgp >> 1, c2 = cgp & 1;                  // tile parity this warp serves; which half of the quarter's items
+    const int row = (int)(q * 32u + lane);                   // A row == TMEM lane: h = row / 8, w = row % 8
+    const int th = row >> 3, tw = row & 7;
+    const int nchunk = c.ntile >> 4;
+    const int items = p.sub * nchunk;
+    const bool leader = elect_one();                        // the one lane that owns this warp's TMA-store bulk groups
+    const uint32_t stage_out = c.obase + (warp - 2u) * 2u * (uint32_t)p.ostage;   // this warp's two staging blocks ([32 px][16 ch]; 1 KB 16-bit / 2 KB fp32)
+    const bool f16 = FAST ? F16C : (p.f16 != 0);
+    const bool y_f32 = FAST ? (KIND == 2) : (p.y_f32 != 0);
+    const bool act = FAST ? (KIND != 2) : (p.act != 0);
+    const bool has_res = FAST ? (KIND == 1) : (c.res_g != nullptr);
+    const bool res_fast = has_res && (FAST || p.r_vec);      // residual rows are 16-byte aligned: two 128-bit loads per thread
+    const int cout_l = c.cout_l;
+    const __nv_bfloat16* res_g = c.res_g;
+    const float* bias_s = c.bias_s;
+    uint32_t nstore = 0;
+    // first item of this warp in every tile: item index c2 -> (sub-tile j0, chunk k0)
+    const int j0 = nchunk == 1 ? c2 : 0, k0 = nchunk == 1 ? 0 : c2;
+    const int res_jstride = kTH * p.W * p.rpitch;            // residual elements between sub-tiles (fits 32 bits: one image row block)
+    // tile walk: this set takes tiles tile0 + set*step, then every 2*step-th; (n, ty, tx) advance by a fixed decomposition
+    TileWalk tw_;
+    walk_init(tw_, c.tile0 + set * c.tile_step, 2 * c.tile_step, p.tiles_x, p.tiles_y);
+    // the residual (and, transitively, everything this kernel overwrites) belongs to earlier kernels of the stream
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int tile = c.tile0 + set * c.tile_step, tl = set; tile < p.num_tiles; tile += 2 * c.tile_step, tl += 2, walk_next(tw_, p.tiles_x, p.tiles_y)) {
+        const uint32_t acc = (uint32_t)tl & (uint32_t)(p.nacc - 1), aph = ((uint32_t)tl >> p.nacc_log2) & 1u;
+        const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
+        const int ox = tx * kTW + tw;
+        const int oy_base = ty * p.sub * kTH + th;           // this thread's row in sub-tile 0
+        // residual pixel of sub-tile 0 (64-bit once per tile; per item only 32-bit offsets are added)
+        const __nv_bfloat16* res_px = has_res ? res_g + (((size_t)n * p.H + oy_base) * p.W + ox) * p.rpitch : nullptr;
+        // residual of this warp's FIRST item: issued before the accumulator wait, so its latency hides under the MMAs
+        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
+        bool r_have = false;
+        if (res_fast && c2 < items) {
+            const int oy = oy_base + j0 * kTH;
+            if (oy < p.H && ox < p.W && (FAST || (k0 << 4) + 16 <= cout_l)) {
+                const uint4* rp = reinterpret_cast<const uint4*>(res_px + j0 * res_jstride + (k0 << 4));
+                r0 = __ldg(rp);
+                r1 = __ldg(rp + 1);
+                r_have = true;
+            }
+        }
+        {
+            ZL_ST_BEGIN(t0);
+            mbar_wait(c.bar_tfull + 8u * acc, aph, 5);
+            ZL_ST_END(t0, st_a);
+        }
+        tc_fence_after();
+        ZL_ST_BEGIN(t_epi);
+        const uint32_t taddr = c.tmem_base + ((q * 32u) << 16) + acc * (uint32_t)p.acc_cols;
+        int j = j0, k = k0;                                  // (sub-tile, chunk) of the pair's first item
+        for (int item = c2; item < items; item += 4) {
+            // the pair: item and item + 2
+            int jb = j, kb = k + 2;
+            while (kb >= nchunk) { kb -= nchunk; ++jb; }
+            const bool have_b = item + 2 < items;
+            uint32_t v[2][16];
+            tmem_ld16(taddr + (uint32_t)(j * p.nt + (k << 4)), v[0]);
+            if (have_b) tmem_ld16(taddr + (uint32_t)(jb * p.nt + (kb << 4)), v[1]);
+            {
+                ZL_ST_BEGIN(t0);
+                tmem_ld_wait();
+                ZL_ST_END(t0, st_c);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !have_b) break;
+                const int jj = h == 0 ? j : jb, c0 = (h == 0 ? k : kb) << 4;
+                const int oy = oy_base + jj * kTH;
+                const bool in_px = oy < p.H && ox < p.W;
+                const bool in_img = in_px && c0 < cout_l;
+                if (h == 1 || item != c2) {                   // only the tile's first item was prefetched
+                    r_have = false;
+                    if (res_fast && in_px && (FAST || (in_img && c0 + 16 <= cout_l))) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res_px + jj * res_jstride + c0);
+                        r0 = __ldg(rp);
+                        r1 = __ldg(rp + 1);
+                        r_have = true;
+                    }
+                }
+                float a[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
+                    a[4 * i + 0] = __uint_as_float(v[h][4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[h][4 * i + 1]) + b4.y;
+                    a[4 * i + 2] = __uint_as_float(v[h][4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[h][4 * i + 3]) + b4.w;
+                }
+                if (act) {
+                    if (p.silu_tanh) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) a[i] = silu_tanh(a[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) a[i] = silu_exp(a[i]);
+                    }
+                }
+                if (has_res) {
+                    if (r_have) {
+                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        if (f16) {                               // one format branch per item, not per pair of values
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[i]));
+                                a[2 * i] += f.x; a[2 * i + 1] += f.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                a[2 * i] += __uint_as_float(rw[i] << 16);            // bf16 -> fp32 is a shift
+                                a[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u);
+                            }
+                        }
+                    } else if (!FAST && in_img) {                // unaligned or ragged residual rows: element by element, statically indexed
+                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(res_px + jj * res_jstride + c0);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < cout_l) a[i] += unpack1_16(rp[i], f16);
+                    }
+                }
+                if (FAST || p.y_tma) {
+                    // ---- stage [32 px][16 ch] in smem, one TMA store per warp (image borders and ragged channel counts are
+                    //      clipped by the hardware against the tensor map's extents)
+                    const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
+                    {
+                        ZL_ST_BEGIN(t0);
+                        if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
+                        ZL_ST_END(t0, st_d);
+                    }
+                    ZL_ST_BEGIN(t_st);
+                    if (y_f32) {
+                        const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
+                        const uint32_t rowb = sbuf + lane * 64u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)i) ^ xr) << 4)), "r"(__float_as_uint(a[4 * i])),
+                                         "r"(__float_as_uint(a[4 * i + 1])), "r"(__float_as_uint(a[4 * i + 2])), "r"(__float_as_uint(a[4 * i + 3])) : "memory");
+                    } else {
+                        uint32_t w[8];
+                        if (f16) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { const __half2 hh = __floats2half2_rn(a[2 * i], a[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&hh); }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { const __nv_bfloat162 hh = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&hh); }
+                        }
+                        const uint32_t xr = (lane >> 2) & 1u;                                       // 32-B swizzle: chunk ^= address bit 7
+                        const uint32_t rowb = sbuf + lane * 32u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((1u ^ xr) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (leader) {
+                        tma_store_4d(c.tmap_y, sbuf, c.n_off + c0, tx * kTW, (ty * p.sub + jj) * kTH + (int)q * 4, n);
+                        tma_store_commit();
+                    }
+                    ZL_ST_END(t_st, st_e);
+                    ++nstore;
+                } else if (in_img) {
+                    // ---- outputs whose rows are not 16-byte aligned (e.g. nc = 2 class maps): plain stores, statically indexed
+                    const size_t m = ((size_t)n * p.H + oy) * p.W + ox;
+                    const bool full = (c0 + 16 <= cout_l);
+                    if (y_f32) {
+                        float* yp = reinterpret_cast<float*>(c.y_g) + m * p.ypitch + c0;
+                        if (full && p.y_vec) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                reinterpret_cast<float4*>(yp)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < cout_l) yp[i] = a[i];
+                        }
+                    } else {
+                        uint16_t* yp = reinterpret_cast<uint16_t*>(c.y_g) + m * p.ypitch + c0;
+                        if (full && p.y_vec) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
+                            reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < cout_l) yp[i] = pack1_16(a[i], f16);
+                        }
+                    }
+                }
+            }
+            // next pair: item + 4
+            k += 4;
+            while (k >= nchunk) { k -= nchunk; ++j; }
+        }
+        // this warp is done reading the accumulator: hand it back to the MMA warp
+        {
+            ZL_ST_BEGIN(t0);
+            tc_fence_before();
+            __syncwarp();
+            if (leader) mbar_arrive(c.bar_tempty + 8u * acc);
+            ZL_ST_END(t0, st_f);
+        }
+        ZL_ST_END(t_epi, st_b);
+    }
+    if (STATS && warp == 2 && lane == 0) {
+        atomicAdd(p.stats + 4, (unsigned long long)st_a);      // epilogue warp 2 waiting for a full accumulator
+        atomicAdd(p.stats + 5, (unsigned long long)st_b);      // ... busy
+        atomicAdd(p.stats + 12, (unsigned long long)st_c);     // ...... of which: tcgen05.ld + wait::ld
+        atomicAdd(p.stats + 13, (unsigned long long)st_d);     // ...... waiting for the staging block's previous bulk store to be read
+        atomicAdd(p.stats + 14, (unsigned long long)st_e);     // ...... st.shared + proxy fence + bulk store issue
+        atomicAdd(p.stats + 15, (unsigned long long)st_f);     // ...... handing the accumulator back
+    }
+#undef ZL_ST_BEGIN
+#undef ZL_ST_END
+    return leader;
 }
 
 template <int MODE, bool STATS>
@@ -310,204 +562,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             atomicAdd(p.stats + 8, (unsigned long long)st_d);      // ... for the weights
         }
     } else {
-        // ===== epilogue warps: TMEM -> +bias -> SiLU -> +residual -> 16-bit / fp32 NHWC =====
-        // * Register arrays are indexed with compile-time constants only (fully unrolled, predicates instead of data-dependent
-        //   trip counts): a[] / v[] must never be demoted to local memory.
-        // * One (32 px x 16 ch) item is a chain of latencies (barrier wake-up, tcgen05.ld, SFU, proxy fence, bulk-store issue:
-        //   ~1300 cycles measured) around very little arithmetic, so the 16 warps work as TWO SETS of 8 on alternate tiles:
-        //   two tiles' chains overlap, and a warp's items of one tile are processed in pairs with both tcgen05.ld in flight.
-        // * No integer division in the loop: tile coordinates and (sub-tile, chunk) indices advance incrementally.
-        const uint32_t q = warp & 3u;                        // TMEM lane quarter this warp may read
-        const int cgp = (int)(warp - 2u) >> 2;               // 0..3 within the quarter
-        const int set = cgp >> 1, c2 = cgp & 1;              // tile parity this warp serves; which half of the quarter's items
-        const int row = (int)(q * 32u + lane);               // A row == TMEM lane: h = row / 8, w = row % 8
-        const int th = row >> 3, tw = row & 7;
-        const int nchunk = ntile >> 4;
-        const int items = p.sub * nchunk;
-        const bool leader = elect_one();                    // the one lane that owns this warp's TMA-store bulk groups
-        store_leader = leader;
-        const uint32_t stage_out = obase + (warp - 2u) * 2u * (uint32_t)p.ostage;   // this warp's two staging blocks ([32 px][16 ch]; 1 KB 16-bit / 2 KB fp32)
-        const bool f16 = p.f16 != 0;
-        const bool res_fast = res_g != nullptr && p.r_vec;  // residual rows are 16-byte aligned: two 128-bit loads per thread
-        uint32_t nstore = 0;
-        // first item of this warp in every tile: item index c2 -> (sub-tile j0, chunk k0)
-        const int j0 = nchunk == 1 ? c2 : 0, k0 = nchunk == 1 ? 0 : c2;
-        // tile walk: this set takes tiles tile0 + set*step, then every 2*step-th; (n, ty, tx) advance by a fixed decomposition
-        TileWalk tw_;
-        walk_init(tw_, tile0 + set * tile_step, 2 * tile_step, p.tiles_x, p.tiles_y);
-        // the residual (and, transitively, everything this kernel overwrites) belongs to earlier kernels of the stream
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (int tile = tile0 + set * tile_step, tl = set; tile < p.num_tiles; tile += 2 * tile_step, tl += 2, walk_next(tw_, p.tiles_x, p.tiles_y)) {
-            const uint32_t acc = (uint32_t)tl & (uint32_t)(p.nacc - 1), aph = ((uint32_t)tl >> p.nacc_log2) & 1u;
-            const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
-            const int ox = tx * kTW + tw;
-            const size_t img_row0 = (size_t)n * p.H;
-            // residual of this warp's FIRST item: issued before the accumulator wait, so its latency hides under the MMAs
-            uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-            bool r_have = false;
-            if (res_fast && c2 < items) {
-                const int oy = (ty * p.sub + j0) * kTH + th;
-                if (oy < p.H && ox < p.W && (k0 << 4) + 16 <= cout_l) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res_g + ((img_row0 + oy) * p.W + ox) * p.rpitch + (k0 << 4));
-                    r0 = __ldg(rp);
-                    r1 = __ldg(rp + 1);
-                    r_have = true;
-                }
-            }
-            {
-                ZL_ST_BEGIN(t0);
-                mbar_wait(bar_tfull + 8u * acc, aph, 5);
-                ZL_ST_END(t0, st_a);
-            }
-            tc_fence_after();
-            ZL_ST_BEGIN(t_epi);
-            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * (uint32_t)p.acc_cols;
-            int j = j0, k = k0;                              // (sub-tile, chunk) of the pair's first item
-            for (int item = c2; item < items; item += 4) {
-                // the pair: item and item + 2
-                int jb = j, kb = k + 2;
-                while (kb >= nchunk) { kb -= nchunk; ++jb; }
-                const bool have_b = item + 2 < items;
-                uint32_t v[2][16];
-                tmem_ld16(taddr + (uint32_t)(j * p.nt + (k << 4)), v[0]);
-                if (have_b) tmem_ld16(taddr + (uint32_t)(jb * p.nt + (kb << 4)), v[1]);
-                {
-                    ZL_ST_BEGIN(t0);
-                    tmem_ld_wait();
-                    ZL_ST_END(t0, st_c);
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 1 && !have_b) break;
-                    const int jj = h == 0 ? j : jb, c0 = (h == 0 ? k : kb) << 4;
-                    const int oy = (ty * p.sub + jj) * kTH + th;
-                    const bool in_img = oy < p.H && ox < p.W && c0 < cout_l;
-                    const size_t m = (img_row0 + oy) * p.W + ox;
-                    if (h == 1 || item != c2) {               // only the tile's first item was prefetched
-                        r_have = false;
-                        if (res_fast && in_img && c0 + 16 <= cout_l) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(res_g + m * p.rpitch + c0);
-                            r0 = __ldg(rp);
-                            r1 = __ldg(rp + 1);
-                            r_have = true;
-                        }
-                    }
-                    float a[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
-                        a[4 * i + 0] = __uint_as_float(v[h][4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[h][4 * i + 1]) + b4.y;
-                        a[4 * i + 2] = __uint_as_float(v[h][4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[h][4 * i + 3]) + b4.w;
-                    }
-                    if (p.act) {
-                        if (p.silu_tanh) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) a[i] = silu_tanh(a[i]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) a[i] = silu_exp(a[i]);
-                        }
-                    }
-                    if (r_have) {
-                        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float ra, rb;
-                            unpack2_16(rw[i], f16, ra, rb);
-                            a[2 * i] += ra;
-                            a[2 * i + 1] += rb;
-                        }
-                    } else if (res_g != nullptr && in_img) {     // unaligned or ragged residual rows: element by element, statically indexed
-                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(res_g + m * p.rpitch + c0);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (c0 + i < cout_l) a[i] += unpack1_16(rp[i], f16);
-                    }
-                    if (p.y_tma) {
-                        // ---- fast path: stage [32 px][16 ch] in smem, one TMA store per warp (image borders and ragged channel
-                        //      counts are clipped by the hardware against the tensor map's extents)
-                        const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
-                        {
-                            ZL_ST_BEGIN(t0);
-                            if (nstore >= 2u) { if (leader) tma_store_wait_read<1>(); __syncwarp(); }    // the store that last used this block has read it
-                            ZL_ST_END(t0, st_d);
-                        }
-                        ZL_ST_BEGIN(t_st);
-                        if (p.y_f32) {
-                            const uint32_t xr = (lane >> 1) & 3u;                                       // 64-B swizzle: chunk ^= address bits 7..8
-                            const uint32_t rowb = sbuf + lane * 64u;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((((uint32_t)i) ^ xr) << 4)), "r"(__float_as_uint(a[4 * i])),
-                                             "r"(__float_as_uint(a[4 * i + 1])), "r"(__float_as_uint(a[4 * i + 2])), "r"(__float_as_uint(a[4 * i + 3])) : "memory");
-                        } else {
-                            uint32_t w[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
-                            const uint32_t xr = (lane >> 2) & 1u;                                       // 32-B swizzle: chunk ^= address bit 7
-                            const uint32_t rowb = sbuf + lane * 32u;
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((0u ^ xr) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((1u ^ xr) << 4)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-                        }
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (leader) {
-                            tma_store_4d(&tmap_y, sbuf, n_off + c0, tx * kTW, (ty * p.sub + jj) * kTH + (int)q * 4, n);
-                            tma_store_commit();
-                        }
-                        ZL_ST_END(t_st, st_e);
-                        ++nstore;
-                    } else if (in_img) {
-                        // ---- outputs whose rows are not 16-byte aligned (e.g. nc = 2 class maps): plain stores, statically indexed
-                        const bool full = (c0 + 16 <= cout_l);
-                        if (p.y_f32) {
-                            float* yp = reinterpret_cast<float*>(y_g) + m * p.ypitch + c0;
-                            if (full && p.y_vec) {
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    reinterpret_cast<float4*>(yp)[i] = make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (c0 + i < cout_l) yp[i] = a[i];
-                            }
-                        } else {
-                            uint16_t* yp = reinterpret_cast<uint16_t*>(y_g) + m * p.ypitch + c0;
-                            if (full && p.y_vec) {
-                                uint32_t w[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) w[i] = pack2_16(a[2 * i], a[2 * i + 1], f16);
-                                reinterpret_cast<uint4*>(yp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                                reinterpret_cast<uint4*>(yp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (c0 + i < cout_l) yp[i] = pack1_16(a[i], f16);
-                            }
-                        }
-                    }
-                }
-                // next pair: item + 4
-                k += 4;
-                while (k >= nchunk) { k -= nchunk; ++j; }
-            }
-            // this warp is done reading the accumulator: hand it back to the MMA warp
-            {
-                ZL_ST_BEGIN(t0);
-                tc_fence_before();
-                __syncwarp();
-                if (leader) mbar_arrive(bar_tempty + 8u * acc);
-                ZL_ST_END(t0, st_f);
-            }
-            ZL_ST_END(t_epi, st_b);
-        }
-        if (STATS && warp == 2 && lane == 0) {
-            atomicAdd(p.stats + 4, (unsigned long long)st_a);      // epilogue warp 2 waiting for a full accumulator
-            atomicAdd(p.stats + 5, (unsigned long long)st_b);      // ... busy
-            atomicAdd(p.stats + 12, (unsigned long long)st_c);     // ...... of which: tcgen05.ld + wait::ld
-            atomicAdd(p.stats + 13, (unsigned long long)st_d);     // ...... waiting for the staging block's previous bulk store to be read
-            atomicAdd(p.stats + 14, (unsigned long long)st_e);     // ...... st.shared + proxy fence + bulk store issue
-            atomicAdd(p.stats + 15, (unsigned long long)st_f);     // ...... handing the accumulator back
+        // ===== epilogue warps: TMEM -> +bias -> SiLU -> +residual -> 16-bit / fp32 NHWC (epilogue_role, specialised per variant) =====
+        EpiCtx ec;
+        ec.tmap_y = &tmap_y; ec.bias_s = bias_s; ec.tmem_base = tmem_base; ec.bar_tfull = bar_tfull; ec.bar_tempty = bar_tempty; ec.obase = obase;
+        ec.tile0 = tile0; ec.tile_step = tile_step; ec.n_off = n_off; ec.ntile = ntile; ec.cout_l = cout_l;
+        ec.res_g = res_g; ec.y_g = y_g; ec.warp = warp; ec.lane = lane;
+        switch (p.epi_variant) {
+            case 0: store_leader = epilogue_role<STATS, 0>(p, ec); break;
+            case 1: store_leader = epilogue_role<STATS, 1>(p, ec); break;
+            case 2: store_leader = epilogue_role<STATS, 2>(p, ec); break;
+            case 3: store_leader = epilogue_role<STATS, 3>(p, ec); break;
+            case 4: store_leader = epilogue_role<STATS, 4>(p, ec); break;
+            case 5: store_leader = epilogue_role<STATS, 5>(p, ec); break;
+            default: store_leader = epilogue_role<STATS, 6>(p, ec); break;
         }
     }
 
@@ -850,6 +917,13 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.wtile_bytes = o.wtile_bytes; p.wchunk_bytes = o.wchunk_bytes; p.wchunk_alloc = o.wchunk_alloc;
     p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc; p.stage_stride = o.stage_stride;
     p.wstream = o.wstream; p.nacc = o.nacc; p.acc_cols = o.acc_cols;
+    p.epi_variant = 6;
+    if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC")) {
+        const int fmt = o.f16 ? 3 : 0;
+        if (!o.y_f32 && o.act && !o.res) p.epi_variant = fmt + 0;
+        else if (!o.y_f32 && o.act && o.res && o.r_vec) p.epi_variant = fmt + 1;
+        else if (o.y_f32 && !o.act && !o.res) p.epi_variant = fmt + 2;
+    }
     p.nacc_log2 = o.nacc == 8 ? 3 : (o.nacc == 4 ? 2 : (o.nacc == 2 ? 1 : 0));
     p.tmem_cols = o.tmem_cols;
     p.stats = stats;

@@ -9,7 +9,8 @@
 namespace zl {
 namespace tc {
 
-constexpr uint32_t kSpinLimit = 200u * 1000u * 1000u;   // mbarrier wait bound: trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 1u << 24;     // failed waits before a trap (instead of hanging the GPU): seconds at the least
+constexpr uint32_t kWaitHintNs = 20000u;     // suspend-time hint of one mbarrier.try_wait
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -22,21 +23,25 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out, so a waiting warp
+// polls rarely instead of competing for issue slots with the warps that work (round 1-2 profiles: the spin loops of
+// idle epilogue warps were ~20 % of all executed instructions of the persistent conv kernel).
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kWaitHintNs)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int id = 0) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;            // the common case: already complete
+    uint32_t fails = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) {
+        if (++fails > kSpinLimit) {
             printf("zl_b200: mbarrier wait timed out (site %d, block %d, thread %d, parity %u)\n", id, (int)blockIdx.x, (int)threadIdx.x, parity);
             __trap();
         }
