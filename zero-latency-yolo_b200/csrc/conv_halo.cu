@@ -71,7 +71,8 @@ struct HaloParams {
     int32_t tiles_x, tiles_y, num_tiles;
     int32_t epi_variant;                             // epilogue_role specialisation (0..5 fast, 6 generic)
     int32_t wstream, nacc, nacc_log2, acc_cols;      // weights streamed with the patches (1) or resident (0); accumulator ring
-    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride, tmem_cols;
+    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, chunk_stride, stage_stride, tmem_cols;
+    int32_t cps, nst;                                // channel chunks per pipeline stage; stages per tile (= cchunks / cps)
     unsigned long long* stats;      // STATS instantiation only: kHaloStatSlots cycle counters summed over CTAs (zl_engine_profile_stalls)
 };
 
@@ -467,26 +468,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             // after item i - np - stages was consumed, so the stage's phase is at most one behind as long as np <= stages.
             const uint32_t np = (uint32_t)stages < (uint32_t)kProducers ? (uint32_t)stages : (uint32_t)kProducers;
             uint32_t s = 0, ph = 0, turn = 0;
-            const uint32_t stage_tx = p.patch_bytes * (uint32_t)NPATCH + (p.wstream ? p.wchunk_bytes : 0u);
+            const uint32_t stage_tx = (p.patch_bytes * (uint32_t)NPATCH + (p.wstream ? p.wchunk_bytes : 0u)) * (uint32_t)p.cps;
             TileWalk tw_;
             walk_init(tw_, tile0, tile_step, p.tiles_x, p.tiles_y);
             for (int tile = tile0; tile < p.num_tiles; tile += tile_step, walk_next(tw_, p.tiles_x, p.tiles_y)) {
                 const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
-                for (int cc = 0; cc < p.cchunks; ++cc) {
+                for (int cs = 0; cs < p.nst; ++cs) {        // one pipeline stage = cps consecutive channel chunks under ONE barrier
                     if (turn == pi) {
                         ZL_ST_BEGIN(t0);
                         mbar_wait(bar_pempty + 8u * s, ph ^ 1u, 1);
                         ZL_ST_END(t0, st_a);
-                        const uint32_t stage = pbase + s * p.stage_stride;
                         mbar_arrive_expect_tx(bar_pfull + 8u * s, stage_tx);
-                        if (p.wstream) tma_load_3d(&tmap_w, bar_pfull + 8u * s, stage + p.patch_alloc, cc * p.kc, n_off, 0);
-                        if (MODE == 2) {
+                        for (int g = 0; g < p.cps; ++g) {
+                            const int cc = cs * p.cps + g;
+                            const uint32_t stage = pbase + s * p.stage_stride + (uint32_t)g * p.chunk_stride;
+                            if (p.wstream) tma_load_3d(&tmap_w, bar_pfull + 8u * s, stage + p.patch_alloc, cc * p.kc, n_off, 0);
+                            if (MODE == 2) {
 #pragma unroll
-                            for (int pp = 0; pp < 4; ++pp)       // parity sub-patch pp = 2*(row parity) + (column parity)
-                                tma_load_4d(&tmap_x, bar_pfull + 8u * s, stage + (uint32_t)pp * p.subpatch_alloc, cc * p.kc,
-                                            2 * (tx * kTW - 1) + (pp & 1), 2 * (ty * kTH * p.sub - 1) + (pp >> 1), n);
-                        } else {
-                            tma_load_4d(&tmap_x, bar_pfull + 8u * s, stage, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
+                                for (int pp = 0; pp < 4; ++pp)       // parity sub-patch pp = 2*(row parity) + (column parity)
+                                    tma_load_4d(&tmap_x, bar_pfull + 8u * s, stage + (uint32_t)pp * p.subpatch_alloc, cc * p.kc,
+                                                2 * (tx * kTW - 1) + (pp & 1), 2 * (ty * kTH * p.sub - 1) + (pp >> 1), n);
+                            } else {
+                                tma_load_4d(&tmap_x, bar_pfull + 8u * s, stage, cc * p.kc, tx * kTW - kHalo, ty * kTH * p.sub - kHalo, n);
+                            }
                         }
                     }
                     if (++turn == np) turn = 0;
@@ -511,7 +515,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         uint32_t s = 0, ph = 0, tl = 0;
         const uint64_t adesc_base = make_smem_desc_sbo(pbase, swz, sbo_a);
         const uint64_t bdesc_base = make_smem_desc_sbo(p.wstream ? pbase + p.patch_alloc : wbase, swz, 8u * swz);
-        const uint32_t stage16 = p.stage_stride >> 4, wchunk16 = p.wchunk_alloc >> 4, subpatch16 = p.subpatch_alloc >> 4;
+        const uint32_t stage16 = p.stage_stride >> 4, chunk16 = p.chunk_stride >> 4, wchunk16 = p.wchunk_alloc >> 4, subpatch16 = p.subpatch_alloc >> 4;
         const uint32_t btap16 = p.wtile_bytes >> 4;                          // a chunk's weight tiles are packed [tap][nt][kc]
         const int sel = (ksteps == 4 ? 0 : (ksteps == 2 ? 3 : 6)) + (p.sub == 1 ? 0 : (p.sub == 2 ? 1 : 2));
         for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++tl) {
@@ -523,7 +527,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             }
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.acc_cols;
-            for (int cc = 0; cc < p.cchunks; ++cc) {
+            for (int cs = 0; cs < p.nst; ++cs) {
                 {
                     ZL_ST_BEGIN(t0);
                     mbar_wait(bar_pfull + 8u * s, ph, 4);
@@ -532,23 +536,26 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 tc_fence_after();
                 ZL_ST_BEGIN(t_issue);
                 if (elect_one()) {
-                    const uint64_t ad = adesc_base + (uint64_t)(s * stage16);
-                    const uint64_t bd = bdesc_base + (uint64_t)(p.wstream ? s * stage16 : (uint32_t)cc * wchunk16);
                     const uint32_t nt = (uint32_t)p.nt;                 // accumulator column stride between sub-tiles
-                    const bool first = cc == 0;
-                    switch (sel) {
-                        case 0: issue_chunk<4, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 1: issue_chunk<4, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 2: issue_chunk<4, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 3: issue_chunk<2, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 4: issue_chunk<2, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 5: issue_chunk<2, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 6: issue_chunk<1, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        case 7: issue_chunk<1, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
-                        default: issue_chunk<1, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                    for (int g = 0; g < p.cps; ++g) {
+                        const int cc = cs * p.cps + g;
+                        const uint64_t ad = adesc_base + (uint64_t)(s * stage16 + (uint32_t)g * chunk16);
+                        const uint64_t bd = bdesc_base + (uint64_t)(p.wstream ? s * stage16 + (uint32_t)g * chunk16 : (uint32_t)cc * wchunk16);
+                        const bool first = cc == 0;
+                        switch (sel) {
+                            case 0: issue_chunk<4, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 1: issue_chunk<4, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 2: issue_chunk<4, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 3: issue_chunk<2, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 4: issue_chunk<2, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 5: issue_chunk<2, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 6: issue_chunk<1, 1, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            case 7: issue_chunk<1, 2, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                            default: issue_chunk<1, 4, MODE>(tmem_d, nt, ad, bd, subpatch16, btap16, idesc, first); break;
+                        }
                     }
                     umma_commit(bar_pempty + 8u * s);
-                    if (cc == p.cchunks - 1) umma_commit(bar_tfull + 8u * acc);
+                    if (cs == p.nst - 1) umma_commit(bar_tfull + 8u * acc);
                 }
                 __syncwarp();
                 ZL_ST_END(t_issue, st_c);
@@ -699,8 +706,8 @@ static bool persist_views(const ConvWeights& w, const View& x, const View& y, Vi
 }
 
 struct PersistPlan {
-    int taps, pw, prow_extra, npatch, kc, cchunks, sub, nsplit, nt, stages, smem, tiles, wstream, nacc;
-    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride;
+    int taps, pw, prow_extra, npatch, kc, cchunks, sub, nsplit, nt, stages, smem, tiles, wstream, nacc, cps;
+    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, chunk_stride, stage_stride;
     View xv, yv;
     double cost;
 };
@@ -754,30 +761,39 @@ static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int
                 pl.wtile_bytes = (uint32_t)nt * kc * 2;
                 pl.wchunk_bytes = (uint32_t)pl.taps * pl.wtile_bytes;
                 pl.wchunk_alloc = (pl.wchunk_bytes + 1023u) & ~1023u;
-                pl.stage_stride = pl.patch_alloc + (mode ? pl.wchunk_alloc : 0u);
+                pl.chunk_stride = pl.patch_alloc + (mode ? pl.wchunk_alloc : 0u);
                 const uint32_t fixed = fixed0 + (mode ? 0u : (uint32_t)pl.cchunks * pl.wchunk_alloc);
-                const int min_stages = mode ? 2 : (pl.cchunks + 1 < 3 ? pl.cchunks + 1 : 3);
-                if (fixed + (uint32_t)min_stages * pl.stage_stride > budget) continue;
-                int stages = (int)((budget - fixed) / pl.stage_stride);
-                if (stages > kMaxPatchStages) stages = kMaxPatchStages;
-                pl.stages = stages;
-                pl.smem = (int)(fixed + (uint32_t)stages * pl.stage_stride);
-                int nacc = 2;
-                while (nacc * 2 <= kMaxAcc && nacc * 2 * pl.sub * nt <= 512) nacc *= 2;
-                pl.nacc = nacc;
-                // ---- price it (cycles per CTA): waves of (tile, slice) units, each the slower of its MMAs and its stage
-                //      traffic (L2 -> SM at ~48 B/clk sustained, ~210 cycles of issue per stage with kProducers issuers)
-                const double units = (double)pl.tiles * nsplit;
-                const int ctas = units < num_sms ? (int)units : (num_sms / nsplit) * nsplit;
-                const double waves = std::ceil(units / std::max(ctas, 1));
-                const double mma = (double)pl.sub * pl.taps * (w.cin / 16) * mma_cycles(nt);
-                const double stage_cyc = std::max((double)(pl.patch_bytes * pl.npatch + (mode ? pl.wchunk_bytes : 0u)) / 48.0,
-                                                  (500.0 + 130.0 * (pl.npatch + mode)) / kProducers);
-                const double load = pl.cchunks * stage_cyc;
-                const double epi = 350.0 + 90.0 * pl.sub * (nt / 16) / 4.0;             // per-tile epilogue floor of one warp quarter group
-                const double prologue = mode ? 1500.0 : 1500.0 + (double)pl.cchunks * pl.wchunk_bytes / 48.0;
-                pl.cost = prologue + waves * std::max(std::max(mma, load), epi);
-                if (!found || pl.cost < best->cost * 0.97) { *best = pl; found = true; }   // ties: keep the earlier (larger kc, resident, fewer splits)
+                // chunks per stage: one barrier round trip (producer ~500 cycles, MMA warp ~250) then covers cps chunks
+                for (int cps = 1; cps <= pl.cchunks; ++cps) {
+                    if (pl.cchunks % cps) continue;
+                    pl.cps = cps;
+                    pl.stage_stride = pl.chunk_stride * (uint32_t)cps;
+                    const int nst = pl.cchunks / cps;
+                    const int min_stages = mode ? 2 : (nst + 1 < 3 ? nst + 1 : 3);
+                    if (fixed + (uint32_t)min_stages * pl.stage_stride > budget) continue;
+                    int stages = (int)((budget - fixed) / pl.stage_stride);
+                    if (stages > kMaxPatchStages) stages = kMaxPatchStages;
+                    pl.stages = stages;
+                    pl.smem = (int)(fixed + (uint32_t)stages * pl.stage_stride);
+                    int nacc = 2;
+                    while (nacc * 2 <= kMaxAcc && nacc * 2 * pl.sub * nt <= 512) nacc *= 2;
+                    pl.nacc = nacc;
+                    // ---- price it (cycles per CTA): waves of (tile, slice) units, each the slower of its MMAs, its stage
+                    //      traffic (L2 -> SM at ~48 B/clk sustained) and its barrier round trips
+                    const double units = (double)pl.tiles * nsplit;
+                    const int ctas = units < num_sms ? (int)units : (num_sms / nsplit) * nsplit;
+                    const double waves = std::ceil(units / std::max(ctas, 1));
+                    const double mma = (double)pl.sub * pl.taps * (w.cin / 16) * mma_cycles(nt) + 250.0 * nst;
+                    const double stage_bytes = (double)(pl.patch_bytes * pl.npatch + (mode ? pl.wchunk_bytes : 0u)) * cps;
+                    const int np = std::min(kProducers, stages);
+                    const double stage_cyc = std::max(stage_bytes / 48.0, (500.0 + 130.0 * cps * (pl.npatch + mode)) / np);
+                    const double load = nst * stage_cyc;
+                    const double epi = 350.0 + 90.0 * pl.sub * (nt / 16) / 4.0;             // per-tile epilogue floor of one warp quarter group
+                    const double fill = stage_cyc * 0.5;                                      // the first stage of a CTA is exposed
+                    const double prologue = mode ? 1500.0 : 1500.0 + (double)pl.cchunks * pl.wchunk_bytes / 48.0;
+                    pl.cost = prologue + fill + waves * std::max(std::max(mma, load), epi);
+                    if (!found || pl.cost < best->cost * 0.97) { *best = pl; found = true; }   // ties: keep the earlier (resident, fewer splits, fewer chunks per stage)
+                }
             }
         }
     }
@@ -830,13 +846,14 @@ int32_t conv_halo_prepare(const ConvWeights& w, const View& x, const View& y, co
     o.num_tiles = pl.tiles;
     o.wstream = pl.wstream;
     o.wtile_bytes = pl.wtile_bytes; o.wchunk_bytes = pl.wchunk_bytes; o.wchunk_alloc = pl.wchunk_alloc;
-    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc; o.subpatch_alloc = pl.subpatch_alloc; o.stage_stride = pl.stage_stride;
+    o.patch_bytes = pl.patch_bytes; o.patch_alloc = pl.patch_alloc; o.subpatch_alloc = pl.subpatch_alloc; o.chunk_stride = pl.chunk_stride; o.stage_stride = pl.stage_stride;
+    o.cps = pl.cps; o.nst = pl.cchunks / pl.cps;
     o.smem_bytes = pl.smem; o.stages = pl.stages;
     fill_ring(o);
     static const bool plan_debug = [] { const char* e = getenv("ZL_PLAN_DEBUG"); return e && e[0] == '1'; }();
     if (plan_debug)
-        fprintf(stderr, "plan %-26s k%d s%d cin %d cout %d | %s kc %d chunks %d sub %d nsplit %d nt %d stages %d nacc %d tiles %d smem %d stage %u wchunk %u cost %.0f\n",
-                w.name.c_str(), w.k, w.stride, w.cin, w.cout, pl.wstream ? "stream" : "resident", pl.kc, pl.cchunks, pl.sub, pl.nsplit, pl.nt, pl.stages, o.nacc,
+        fprintf(stderr, "plan %-26s k%d s%d cin %d cout %d | %s kc %d chunks %d cps %d sub %d nsplit %d nt %d stages %d nacc %d tiles %d smem %d stage %u wchunk %u cost %.0f\n",
+                w.name.c_str(), w.k, w.stride, w.cin, w.cout, pl.wstream ? "stream" : "resident", pl.kc, pl.cchunks, pl.cps, pl.sub, pl.nsplit, pl.nt, pl.stages, o.nacc,
                 pl.tiles, pl.smem, pl.stage_stride, pl.wchunk_bytes, pl.cost);
     // weight box = one channel chunk of one slice of nt output channels, all taps (rows past Cout_pad are zero-filled by TMA)
     ZL_TRY(make_tmap_w3d(&o.tmap_w, w.w_tc, w.cin, w.cout_pad, pl.taps, w.ktot, o.kc, o.nt, o.f16));
@@ -872,7 +889,8 @@ int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int
     o.wstream = 0;
     o.wtile_bytes = (uint32_t)o.nt * 32u; o.wchunk_bytes = 4u * o.wtile_bytes; o.wchunk_alloc = (o.wchunk_bytes + 1023u) & ~1023u;
     o.patch_bytes = (uint32_t)(kTW + 1) * (kTH * o.sub + 1) * 32u;
-    o.subpatch_alloc = (o.patch_bytes + 1023u) & ~1023u; o.patch_alloc = o.subpatch_alloc; o.stage_stride = o.patch_alloc;
+    o.subpatch_alloc = (o.patch_bytes + 1023u) & ~1023u; o.patch_alloc = o.subpatch_alloc; o.chunk_stride = o.patch_alloc; o.stage_stride = o.patch_alloc;
+    o.cps = 1; o.nst = 1;
     const uint32_t fixed = 3072u + o.wchunk_alloc + (uint32_t)kEpiWarps * 2048u;
     int stages = (int)((227u * 1024u - fixed) / o.stage_stride);
     if (stages > kMaxPatchStages) stages = kMaxPatchStages;
@@ -915,7 +933,8 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.kc = o.kc; p.cchunks = o.cchunks; p.stages = o.stages; p.sub = o.sub; p.y_tma = o.y_tma; p.nsplit = o.nsplit; p.nt = o.nt; p.ostage = o.ostage;
     p.tiles_x = o.tiles_x; p.tiles_y = o.tiles_y; p.num_tiles = o.num_tiles;
     p.wtile_bytes = o.wtile_bytes; p.wchunk_bytes = o.wchunk_bytes; p.wchunk_alloc = o.wchunk_alloc;
-    p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc; p.stage_stride = o.stage_stride;
+    p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc; p.chunk_stride = o.chunk_stride; p.stage_stride = o.stage_stride;
+    p.cps = o.cps; p.nst = o.nst;
     p.wstream = o.wstream; p.nacc = o.nacc; p.acc_cols = o.acc_cols;
     p.epi_variant = 6;
     if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC")) {

@@ -91,7 +91,8 @@ struct ConvHaloOp {
     int32_t kc, cchunks, stages, sub, y_tma, taps, nsplit, nt, mode, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
     int32_t wstream, nacc, acc_cols;     // weights streamed with the patches / resident; TMEM accumulator ring
-    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, stage_stride, tmem_cols;
+    uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, chunk_stride, stage_stride, tmem_cols;
+    int32_t cps, nst;                    // channel chunks per pipeline stage, stages per tile
     int32_t smem_bytes;
     double flops, bytes;
 };
