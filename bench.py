@@ -202,6 +202,49 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+# algorithmic work per FRAME at 640x640, nc = 80 (conv FLOPs = 2*MAC; activation bytes = every conv
+# output written once and read once, 16-bit) — the roofline numerators, never the engine's per-layer operand sums.
+ALGO = {"n": dict(flops=8.743e9, act_bytes=60.4e6), "s": dict(flops=28.602e9, act_bytes=109.5e6), "m": dict(flops=78.936e9, act_bytes=193.3e6)}
+# north_star's 16-bit gate, as measured by tests/test_gpu_engine.py::test_16bit_contract_* and scripts/gpu_diag.py on B200
+GATE = {"fp16": "pass (every matched detection IoU >= 0.99; 2-4 % NMS knife-edge flips; profiles/accuracy_r02.md)",
+        "bf16": "fail (19-45 % of the matched detections reach IoU 0.99, all reach 0.9; profiles/accuracy_r02.md)"}
+
+
+def conv_family(prof):
+    tc = [p for p in prof if p["kind"] in (1, 9)]       # tcgen05 conv kernels: persistent (9) and fallback (1)
+    return tc, sum(p["ms"] for p in tc)
+
+
+def measure_resident(eng, n_sets, steps, warmup):
+    eng.run_resident(n_sets, max(warmup, 3))
+    ms, launches, _ = eng.run_resident(n_sets, steps)
+    return ms, launches
+
+
+def side_config(zlb200, scale, batch, prec, device, steps, peaks, dtype):
+    """BASELINE configs[3] models (YOLOv8s / YOLOv8m 640x640, batch 256 sharded over the ranks): frames/s of this rank's
+    shard with the frames resident, plus the tensor-roof fraction (the compute-bound models of the family)."""
+    from oracle import synth, yolov8_ref, zlw
+    t = yolov8_ref.synthetic_model(scale, NC, seed=0)
+    lanes = 2
+    e = zlb200.Engine(HW, HW, NC, scale, precision=prec, conf=CONF, iou=IOU, max_batch=batch, device=device, num_lanes=lanes)
+    e.load_weights_blob(zlw.dumps(t, scale, NC))
+    e.warmup(1)
+    frames = synth.frames_structured(min(batch, 32), HW, HW, seed=900)
+    reps = [frames[i % len(frames)] for i in range(batch)]
+    for sidx in range(2):
+        e.upload_resident(sidx, reps)
+    ms, _ = measure_resident(e, 2, steps, 3)
+    fps = batch * steps / (ms / 1e3)
+    prof = e.profile(0, 1)
+    tc, tc_ms = conv_family(prof)
+    e.close()
+    return {"model": f"yolov8{scale}", "batch_per_gpu": batch, "dtype": dtype, "frames_per_s_this_gpu": fps, "ms_per_step": ms / steps,
+            "tensor_tflops_whole_step": fps * ALGO[scale]["flops"] / 1e12, "tensor_frac_of_sustained": fps * ALGO[scale]["flops"] / (peaks["tf_sust"] * 1e12),
+            "conv_tflops_kernels_only": ALGO[scale]["flops"] * batch / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+            "conv_hbm_gbs_algorithmic": ALGO[scale]["act_bytes"] * batch / (tc_ms * 1e-3) / 1e9 if tc_ms else None, "conv_launches": len(tc)}
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import zlb200
@@ -219,13 +262,31 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    # keep this rank's host threads (and the pinned buffers they first touch) on the cores next to its GPU
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        if cpus and world > 1:
+            share = max(len(cpus) // world, 1)
+            mine = cpus[(local_rank * share) % len(cpus):][:share] or cpus
+            os.sched_setaffinity(0, set(mine))
+    except Exception:
+        pass
+
     peaks = load_peaks()
     tensors, blob = make_model()
     n_sets = 4
     sets = make_inputs(n_sets, seed0=5678 + 100 * rank)
-    prec = zlb200.FP16 if args.dtype == "fp16" else zlb200.BF16
-    E2E_THREADS = args.e2e_threads   # host threads in the end-to-end leg: each owns a lane, so H2D of one batch overlaps compute of another
-    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=prec, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank, num_lanes=E2E_THREADS)
+    PREC = {"fp16": zlb200.FP16, "bf16": zlb200.BF16}
+    prec = PREC[args.dtype]
+    LANES = args.e2e_threads   # host threads in the end-to-end leg: each owns a lane, so H2D of one batch overlaps compute of another
+    eng = zlb200.Engine(HW, HW, NC, SCALE, precision=prec, conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank, num_lanes=LANES)
     eng.load_weights_blob(blob)
     eng.warmup(1)
     for s in range(n_sets):
@@ -245,85 +306,138 @@ def run_ours(args, rank, local_rank, world):
     max_ms = reduce_max(ms, dist, "cuda")
     value = world * BATCH * args.steps / (max_ms / 1e3)
 
-    # ---- end to end through the public C-ABI call with pinned HOST frames: every step copies its 64 frames
-    # host->device and reads the detections back; E2E_THREADS host threads keep one batch each in flight
-    pinned = [zlb200.pinned_array((BATCH, HW, HW, 3)) for _ in range(E2E_THREADS)]
+    # ---- end to end through the public C-ABI call (zl_infer_batch) with pinned HOST frames, looped in C so no interpreter
+    # sits in the timed path: every step copies its 64 frames host->device (one copy: they are contiguous) and reads the
+    # detections back; LANES host threads keep one batch each in flight
+    pinned = [zlb200.pinned_array((BATCH, HW, HW, 3)) for _ in range(LANES)]
     for t, buf in enumerate(pinned):
         buf[:] = sets[t % n_sets]
-    pframes = [[buf[i] for i in range(BATCH)] for buf in pinned]
-    last = [None] * E2E_THREADS
-
-    def e2e_worker(t, nsteps):
-        for _ in range(nsteps):
-            last[t] = eng.infer(pframes[t])
-
-    def run_e2e(total_steps):
-        share = [total_steps // E2E_THREADS + (1 if t < total_steps % E2E_THREADS else 0) for t in range(E2E_THREADS)]
-        th = [threading.Thread(target=e2e_worker, args=(t, share[t])) for t in range(E2E_THREADS)]
-        t0 = time.perf_counter()
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        return time.perf_counter() - t0
-
-    run_e2e(2 * E2E_THREADS)
+    eng.bench_e2e(pinned, 2 * LANES)
     barrier()
-    e2e_s = run_e2e(args.steps)
+    e2e_s, n_det = eng.bench_e2e(pinned, args.steps)
     barrier()
     e2e_fps = world * BATCH * args.steps / reduce_max(e2e_s, dist, "cuda")
-    dets = next(x for x in last if x is not None)
-    n_det = sum(len(d) for d in dets)
     d2h = (4 + 2 * BATCH) * 4 + min(BATCH * 64, BATCH * eng.A) * 24
+    # the e2e leg's ceiling: pinned H2D bandwidth of this rank while every rank measures at the same time
+    barrier()
+    h2d_peak = eng.bench_h2d(256 << 20, 6)
+    h2d_peak_min = -reduce_max(-h2d_peak, dist, "cuda")
+    barrier()
+
+    # ---- config 4 (YOLOv8s / YOLOv8m 640x640, batch 256 sharded over the ranks): every rank runs its shard, rank 0 reports
+    cfg4 = None
+    if not args.quick:
+        cfg4 = []
+        shard = max(256 // world, 1)
+        for sc in ("s", "m"):
+            try:
+                barrier()
+                r = side_config(zlb200, sc, shard, prec, local_rank, 6, peaks, args.dtype)
+                slow = reduce_max(r["ms_per_step"], dist, "cuda")
+                r["frames_per_s_all_gpus"] = 256 / (slow / 1e3) if world * shard == 256 else world * shard / (slow / 1e3)
+                r["global_batch"] = world * shard
+                r["scaling"] = "strong (global batch 256 split over the ranks)"
+                cfg4.append(r)
+            except Exception as ex:
+                cfg4.append({"model": f"yolov8{sc}", "error": str(ex)})
 
     if rank != 0:
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
         return
 
-    # ---- per-kernel roofline (rank 0): same pass, un-captured, one CUDA-event pair per kernel
+    # ---- per-kernel roofline (rank 0): the same pass un-captured on ONE stream, a CUDA-event pair around every kernel
+    # (serial and un-overlapped, so its sum exceeds the timed step, which overlaps LANES streams with graphs + PDL)
     prof = eng.profile(0, 3)
-    tc = [p for p in prof if p["kind"] in (1, 9)]       # tcgen05 conv kernels: persistent (9) and fallback (1)
-    tc_ms = sum(p["ms"] for p in tc)
-    tc_flops = sum(p["flops"] for p in tc)
-    tc_bytes = sum(p["bytes"] for p in tc)
+    tc, tc_ms = conv_family(prof)
     step_ms_prof = sum(p["ms"] for p in prof)
-    tflops = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    gbs = tc_bytes / (tc_ms * 1e-3) / 1e9 if tc_ms > 0 else 0.0
+    algo = ALGO[SCALE]
+    tflops = algo["flops"] * BATCH / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    gbs = algo["act_bytes"] * BATCH / (tc_ms * 1e-3) / 1e9 if tc_ms > 0 else 0.0
     ridge = peaks["tf_sust"] * 1e12 / (peaks["hbm"] * 1e9)
-    ai = tc_flops / tc_bytes if tc_bytes else 0.0
+    ai = algo["flops"] / algo["act_bytes"]
     hbm_bound = ai < ridge
     traffic = None
-    try:   # ncu --metrics dram__bytes_{read,write}.sum over one pass of the same workload (profiles/README_r01.md)
-        sm = json.load(open(os.path.join(ROOT, "profiles", "step_metrics_summary_r01.json")))
-        traffic = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in sm.items() if k.startswith("conv_halo") or k.startswith("conv_tc"))
+    try:   # ncu dram__bytes_{read,write}.sum of the conv family per step (profiles/)
+        for name in ("step_metrics_summary_r02.json", "step_metrics_summary_r01.json"):
+            pth = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(pth):
+                sm = json.load(open(pth))
+                traffic = sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in sm.items() if k.startswith("conv_halo") or k.startswith("conv_tc"))
+                break
     except Exception:
         traffic = None
     roofline = {
-        "kernel": "conv_halo_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convs, %d launches/step)" % len(tc),
+        "kernel": "conv_halo_kernel (persistent tcgen05 implicit-GEMM conv, %d launches/step)" % len(tc),
         "bound": "hbm" if hbm_bound else "tensor",
         "achieved": gbs if hbm_bound else tflops,
         "peak": peaks["hbm"] if hbm_bound else peaks["tf_sust"],
         "unit": "GB/s" if hbm_bound else "TFLOP/s",
         "frac": (gbs / peaks["hbm"]) if hbm_bound else (tflops / peaks["tf_sust"]),
         "traffic": traffic,
-        "traffic_note": "DRAM read+write bytes of the conv kernel family per step (ncu, profiles/step_metrics_summary_r01.json); "
-                        "algorithmic bytes per step = %.0f" % tc_bytes,
+        "algorithmic_bytes_per_step": algo["act_bytes"] * BATCH,
+        "algorithmic_note": "SURVEY.md 8(d): 60.4 MB of 16-bit activations per frame (every conv output written once and read once) x 64 frames; "
+                            "8.743 GFLOP per frame",
         "unit_of_work": "one step = all %d conv launches of a 64-frame batch (the family is one kernel template)" % len(tc),
         "peak_source": peaks["src"] + (", sustained figure: kernel timed inside a long step" if not hbm_bound else ""),
         "tensor_tflops": tflops, "tensor_frac_of_sustained": tflops / peaks["tf_sust"],
         "hbm_gbs_algorithmic": gbs, "hbm_frac": gbs / peaks["hbm"],
         "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": ridge,
+        "conv_ms_per_step_serial": tc_ms, "all_kernels_ms_per_step_serial": step_ms_prof,
         "share_of_step": tc_ms / step_ms_prof if step_ms_prof else None,
-        "how": "zl_engine_profile: CUDA-event pair around every kernel on the engine stream, 3 passes after the timed region",
+        "how": "zl_engine_profile: CUDA-event pair around every kernel on ONE un-captured stream, 3 passes after the timed region; serial, "
+               "so the sum exceeds ms_per_step (timed region = %d streams overlapping, CUDA graphs + programmatic dependent launch)" % LANES,
+        "whole_step_hbm_frac": value / world * algo["act_bytes"] / 1e9 / peaks["hbm"],
+        "whole_step_tensor_frac_of_sustained": value / world * algo["flops"] / (peaks["tf_sust"] * 1e12),
     }
     top = sorted(prof, key=lambda p: -p["ms"])[:8]
-    roofline["top_kernels_ms"] = [{"name": p["name"], "ms": round(p["ms"], 4),
-                                   "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["ms"] > 0 and p["flops"] else None,
-                                   "gbs": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1) if p["ms"] > 0 and p["bytes"] else None} for p in top]
-    # P1 stand-alone (in the 16-bit pipeline it is fused into layer 0): achieved GB/s against the HBM peak
+    roofline["top_kernels_ms"] = [{"name": p["name"], "ms": round(p["ms"], 4)} for p in top]
+    # P1 stand-alone: achieved GB/s against the HBM peak
     pre_ms, pre_bytes = eng.bench_preprocess(HW, HW, BATCH, 20)
     roofline["preprocess"] = {"kernel": "preprocess_kernel stand-alone, 64 frames 640x640 -> NHWC4 16-bit", "ms": pre_ms,
                               "gbs": pre_bytes / (pre_ms * 1e-3) / 1e9, "hbm_frac": pre_bytes / (pre_ms * 1e-3) / 1e9 / peaks["hbm"],
                               "bytes_per_launch": pre_bytes}
+
+    # ---- steady state: >= 5 s of back-to-back steps, clocks and power sampled over the whole window
+    steady = None
+    if not args.quick:
+        n_long = int(max(5.5e3 / (max_ms / args.steps), 200))
+        smp = ClockSampler(local_rank)
+        smp.start()
+        ms_long, _, _ = eng.run_resident(n_sets, n_long)
+        ck = smp.stop()
+        steady = {"seconds": ms_long / 1e3, "steps": n_long, "frames_per_s": BATCH * n_long / (ms_long / 1e3), "clocks": ck}
+
+    # ---- the other 16-bit format (same kernels, the UMMA instruction descriptor differs): BASELINE configs[2] says bf16
+    other = None
+    if not args.quick:
+        od = "bf16" if args.dtype == "fp16" else "fp16"
+        try:
+            eng.close()
+            eng = zlb200.Engine(HW, HW, NC, SCALE, precision=PREC[od], conf=CONF, iou=IOU, max_batch=BATCH, device=local_rank, num_lanes=LANES)
+            eng.load_weights_blob(blob)
+            eng.warmup(1)
+            for s in range(n_sets):
+                eng.upload_resident(s, list(sets[s]))
+            oms, _ = measure_resident(eng, n_sets, args.steps, args.warmup)
+            other = {"dtype": od, "value": BATCH * args.steps / (oms / 1e3), "unit": UNIT, "ms_per_step": oms / args.steps, "n_gpus": 1, "gate": GATE[od]}
+        except Exception as ex:
+            other = {"dtype": od, "error": str(ex)}
+
+    # ---- cfg5 (BASELINE configs[4]): decode/NMS stress, 8400 anchors x 80 classes x batch 128, conf 0.01
+    cfg5 = None
+    if not args.quick:
+        try:
+            from oracle import synth
+            raw = synth.stress_head(128, 80, 8400)
+            mf, mn, kept = eng.bench_decode_nms(raw, 0.01, 0.45, iters=5)
+            b = 128 * 2.822e6
+            cfg5 = {"workload": "head tensor [128, 84, 8400] fp32, conf 0.01, iou 0.45 (SURVEY 8d stress set)", "filter_ms": mf, "nms_ms": mn, "kept": kept,
+                    "filter_gbs_vs_2.822MB_per_frame": b / (mf * 1e-3) / 1e9, "filter_hbm_frac": b / (mf * 1e-3) / 1e9 / peaks["hbm"],
+                    "decode_plus_nms_frames_per_s": 128 / ((mf + mn) * 1e-3)}
+        except Exception as ex:
+            cfg5 = {"error": str(ex)}
 
     # ---- b=1 416x416 latency (BASELINE configs[1]), CUDA graph, frame in pinned host memory
     latency = None
@@ -355,21 +469,27 @@ def run_ours(args, rank, local_rank, world):
         fps8, dt8, _ = cpu_pipeline_fps(tensors, sample, cores, 8)
         cpu_baseline = {"value": fps1, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"16 frames b=1 sequential ({dt1:.1f}s), as the reference runs; batched b=8: {fps8:.1f} frames/s ({dt8:.1f}s)",
-                        "note": "torch-CPU fp32 stand-in for the ORT-CPU session + C pre/post (reference not compilable here)"}
+                        "note": "torch-CPU fp32 stand-in for the ORT-CPU session + the oracle's C pre/post (pinned to the reference's own compiled text, oracle/_ref)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD.replace("bf16", args.dtype), "inputs": f"{n_sets} rotating resident input sets of {BATCH} frames ({n_sets * BATCH * HW * HW * 3 / 1e6:.0f} MB > 126 MB L2)",
-                   "frames_per_step_per_gpu": BATCH, "streams": E2E_THREADS, "parallelism": f"frame-sharded replicas x{world}, no collective"},
+                   "frames_per_step_per_gpu": BATCH, "streams": LANES, "parallelism": f"frame-sharded replicas x{world}, no collective"},
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": BATCH * HW * HW * 3, "d2h_bytes_per_step": d2h,
-                "api": f"zl_infer_batch (C-ABI) on pinned host frames from {E2E_THREADS} host threads (one lane each)", "detections_last_step": n_det},
+                "api": f"zl_infer_batch (C-ABI) on pinned host frames, looped in C (zl_bench_e2e) from {LANES} host threads (one lane each)", "detections_last_step": int(n_det),
+                "h2d_gbs_achieved_per_gpu": e2e_fps / world * HW * HW * 3 / 1e9, "h2d_gbs_pinned_peak_per_gpu_all_ranks_busy": h2d_peak_min},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "latency_b1_416": latency,
+        "gate_16bit": {"fp16": GATE["fp16"], "bf16": GATE["bf16"], "bf16_gate": "fail", "fp16_gate": "pass"},
+        "other_dtype": other,
+        "steady_state": steady,
+        "cfg4_yolov8s_m_b256": cfg4,
+        "cfg5_decode_nms": cfg5,
         "tensor_roof_frac_whole_step": value * FLOPS_PER_FRAME / (world * peaks["tf_sust"] * 1e12),
         "wall_ms_per_step_rank0": wall_ms / args.steps,
     }

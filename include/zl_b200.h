@@ -201,6 +201,14 @@ ZL_API int32_t zl_engine_profile_stalls(zl_engine* e, int32_t set, uint64_t* out
  * HOST frame (pinned or not), each timed with steady_clock from call to detections-on-host; ms_out[iters]. */
 ZL_API int32_t zl_bench_latency(zl_engine* e, const uint8_t* bgr, int32_t width, int32_t height,
                                 int32_t warmup, int32_t iters, float* ms_out);
+/* End-to-end throughput loop in C: `threads` host threads (one engine lane each), thread t owning the batch of n
+ * equal-size frames stored back to back at batches[t] (pinned host memory), call zl_infer_batch steps_total times in
+ * all: every step copies its frames host->device, runs the whole path and reads the detections back.  seconds = wall
+ * time until the slowest thread is done. */
+ZL_API int32_t zl_bench_e2e(zl_engine* e, const uint8_t* const* batches, int32_t threads, int32_t n, int32_t width, int32_t height,
+                            int32_t steps_total, double* seconds, int64_t* dets_last_step);
+/* Pinned host -> device copy bandwidth on the engine's device (GB/s): the ceiling of the end-to-end leg. */
+ZL_API int32_t zl_bench_h2d(zl_engine* e, size_t bytes, int32_t iters, double* gbs);
 /* Stand-alone kernels with device-resident synthetic data, for roofline lines. */
 ZL_API int32_t zl_bench_preprocess(zl_engine* e, int32_t width, int32_t height, int32_t n,
                                    int32_t iters, float* ms_per_launch, double* bytes_per_launch);

@@ -182,14 +182,23 @@ def _round_sig(v, sig=3):
 
 
 @torch.inference_mode()
-def calibrate(tensors, scale, nc, size=256, target_frac=0.02, cls_std=1.5):
+def calibrate(tensors, scale, nc, size=256, target_frac=0.02, cls_std=1.5, dfl_beta=0.5, dfl_mu0=4.0, dfl_mu_std=0.35):
     """Data-dependent rescale of random-init weights (LSUV style) so the synthetic
     model carries a real signal to the head instead of exploding / vanishing:
     every conv's (w, b) is multiplied by 1/std(pre-activation) measured on one
     fixed structured frame, the class head gets std `cls_std`, and each level's
     class bias is set so ~target_frac of its anchors score >= 0.5 (SURVEY.md §7
-    "random-init weights give degenerate scores").  Scale factors are rounded to
-    3 significant digits so the result is bit-stable across CPUs.
+    "random-init weights give degenerate scores").  The DFL box head (cv2.*.2) is
+    given the STRUCTURE a trained head has instead of 64 independent random rows:
+    for every side s the 16 bin logits are  logit_k = alpha_s(x) * k - dfl_beta * k^2
+    (+ a constant slope), alpha_s a linear function of the features (the seeded
+    random row s*16 of the conv, rescaled), i.e. a discretised Gaussian over the bins
+    with variance 1 / (2 dfl_beta) whose mean dfl_mu0 + alpha_s / (2 dfl_beta) moves
+    with the input (std dfl_mu_std bins on the calibration frame).  Independent
+    unit-variance logits give near-flat or multi-modal distributions: expectations of
+    ~7.5 bins on every side (900-px boxes on a 416-px image) that are twenty times
+    more sensitive to rounding than any trained detector's.  Scale factors are
+    rounded to 3 significant digits so the result is bit-stable across CPUs.
     Returns a new tensor dict (numpy fp32).
     """
     from oracle import synth
@@ -204,10 +213,19 @@ def calibrate(tensors, scale, nc, size=256, target_frac=0.02, cls_std=1.5):
         sp = net.specs[name]
         w, b = net.t[name + ".weight"], net.t[name + ".bias"]
         y = F.conv2d(xin, w, b, stride=sp["s"], padding=sp["k"] // 2)
-        if sp["act"] or ".cv2." in name:
+        if sp["act"]:
             s = _round_sig(1.0 / max(float(y.std()), 1e-12))
             w.mul_(s)
             b.mul_(s)
+        elif ".cv2." in name:                   # DFL box head: unimodal bin distributions with a data-dependent mean
+            w0 = w.clone()
+            for side in range(4):
+                row = w0[side * 16].clone()                                        # the side's seeded random direction
+                alpha = F.conv2d(xin, row.view(1, -1, 1, 1), None)
+                sc = _round_sig(dfl_mu_std * 2.0 * dfl_beta / max(float(alpha.std()), 1e-12))
+                for kbin in range(16):
+                    w[side * 16 + kbin] = row * (sc * kbin)
+                    b[side * 16 + kbin] = -dfl_beta * kbin * kbin + 2.0 * dfl_beta * dfl_mu0 * kbin
         else:                                   # class logits: scale, then bias by quantile
             s = _round_sig(cls_std / max(float((y - b.view(1, -1, 1, 1)).std()), 1e-12))
             w.mul_(s)

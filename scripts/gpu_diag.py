@@ -31,9 +31,12 @@ def bf16_stats(scale, nc, hw, nframes, precision=None):
     for d, r in zip(dets, det_ref):
         for i in range(len(r)):
             same = d[d["class_id"] == r["class_id"][i]]
-            if len(same):
-                ious.append(float(box_iou(same, r[i]).max()))
+            ious.append(float(box_iou(same, r[i]).max()) if len(same) else 0.0)
     ious = np.array(ious)
+    out["n_oracle_dets"] = int(sum(len(r) for r in det_ref))
+    out["n_below_0.99"] = int(out["n_oracle_dets"] - (ious >= 0.99).sum())      # north_star: every matched detection IoU >= 0.99
+    out["kept_equal"] = bool(all(len(d) == len(r) for d, r in zip(dets, det_ref)))
+    out["iou_hist_lt0.9_0.9to0.99_ge0.99"] = [int((ious < 0.9).sum()), int(((ious >= 0.9) & (ious < 0.99)).sum()), int((ious >= 0.99).sum())]
     out["matched_ge_0.5"] = int((ious >= 0.5).sum())
     m = ious[ious >= 0.5]
     out["iou_min"] = float(m.min()); out["iou_p01"] = float(np.quantile(m, 0.01)); out["iou_med"] = float(np.median(m))

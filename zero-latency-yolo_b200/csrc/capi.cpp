@@ -218,6 +218,23 @@ int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters, zl_op_profil
     ZL_GUARD_END
 }
 
+int32_t zl_bench_e2e(zl_engine* e, const uint8_t* const* batches, int32_t threads, int32_t n, int32_t width, int32_t height,
+                     int32_t steps_total, double* seconds, int64_t* dets_last_step)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->bench_e2e(batches, threads, n, width, height, steps_total, seconds, dets_last_step);
+    ZL_GUARD_END
+}
+
+int32_t zl_bench_h2d(zl_engine* e, size_t bytes, int32_t iters, double* gbs)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->bench_h2d(bytes, iters, gbs);
+    ZL_GUARD_END
+}
+
 int32_t zl_engine_profile_stalls(zl_engine* e, int32_t set, uint64_t* out, int32_t cap_ops, int32_t* n_out)
 {
     ZL_GUARD_BEGIN
@@ -271,9 +288,10 @@ void* zl_host_alloc(size_t bytes)
 {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); zl::set_error("cudaHostAlloc failed"); return nullptr; }
+    zl::register_pinned_range(p, bytes);
     return p;
 }
-void zl_host_free(void* p) { if (p) cudaFreeHost(p); }
+void zl_host_free(void* p) { if (p) { zl::unregister_pinned_range(p); cudaFreeHost(p); } }
 const char* zl_last_error(void) { return zl::get_error(); }
 const char* zl_version(void) { return "zl_b200 0.1 (sm_100a)"; }
 int32_t zl_device_count(void)

@@ -294,8 +294,8 @@ EncodeTiledFn get_encode_fn() {
 // batched or on which kernel / launch plan ran (tests: test_16bit_results_do_not_depend_on_batch).
 //   * the widest of 64 / 32 / 16 that divides Cin (128 / 64 / 32-byte swizzle rows);
 //   * 3x3 stride 2: at most 32 (a stage holds four parity sub-patches);
-//   * 3x3: halved until two pipeline stages of the weight-STREAMING plan fit at full output width (conv_halo.cu), so
-//     the deep layers never have to fall back to a narrow N split.
+//   * 3x3: halved until two pipeline stages of the weight-STREAMING plan fit at an output width of min(Cout, 128)
+//     (conv_halo.cu; an MMA gets no cheaper per column beyond N = 128), so the deep layers never fall back to a narrow N split.
 int32_t conv_kc(const ConvWeights& w, bool y_f32)
 {
     int kc = (w.cin % 64 == 0) ? 64 : (w.cin % 32 == 0 ? 32 : 16);
@@ -303,7 +303,7 @@ int32_t conv_kc(const ConvWeights& w, bool y_f32)
     if (w.k == 3 && w.cin >= 16 && w.cin % 16 == 0) {
         const int s2 = w.stride == 2;
         const uint32_t fixed = 3072u + 16u * (y_f32 ? 4096u : 2048u);
-        const int nt = w.cout_pad < 256 ? w.cout_pad : 256;
+        const int nt = w.cout_pad < 128 ? w.cout_pad : 128;     // an MMA gets no cheaper per column beyond N = 128 (umma_probe)
         while (kc > 16) {
             const uint32_t patch = (((uint32_t)(s2 ? 9 : 10) * (16 + (s2 ? 1 : 2)) * kc * 2 + 1023u) & ~1023u) * (s2 ? 4u : 1u);
             const uint32_t wchunk = (9u * nt * kc * 2 + 1023u) & ~1023u;

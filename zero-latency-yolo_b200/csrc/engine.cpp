@@ -589,15 +589,25 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
     ZL_CUDA(cudaSetDevice(cfg.device));
     const int B = graph_batch_for(n);
     const size_t slot = slot_bytes();
+    // Frames that sit back to back in pinned host memory and fill their slots exactly (the bench's batches, the async
+    // path's slot ring when consecutive) go up in ONE copy; anything else is one copy per frame.
+    bool one_copy = frames_pinned && n > 1;
     for (int i = 0; i < n; ++i) {
         const size_t bytes = (size_t)ws[i] * hs[i] * 3;
         if (ws[i] <= 0 || hs[i] <= 0 || bytes > slot) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame_w x max_frame_h");
-        const uint8_t* src = frames[i];
-        if (!frames_pinned) {
-            std::memcpy(L.h_frames + (size_t)i * slot, frames[i], bytes);
-            src = L.h_frames + (size_t)i * slot;
+        if (bytes != slot || (i > 0 && frames[i] != frames[i - 1] + slot)) one_copy = false;
+    }
+    if (one_copy) ZL_CUDA(cudaMemcpyAsync(L.staging, frames[0], (size_t)n * slot, cudaMemcpyHostToDevice, L.stream));
+    for (int i = 0; i < n; ++i) {
+        const size_t bytes = (size_t)ws[i] * hs[i] * 3;
+        if (!one_copy) {
+            const uint8_t* src = frames[i];
+            if (!frames_pinned) {
+                std::memcpy(L.h_frames + (size_t)i * slot, frames[i], bytes);
+                src = L.h_frames + (size_t)i * slot;
+            }
+            ZL_CUDA(cudaMemcpyAsync(L.staging + (size_t)i * slot, src, bytes, cudaMemcpyHostToDevice, L.stream));
         }
-        ZL_CUDA(cudaMemcpyAsync(L.staging + (size_t)i * slot, src, bytes, cudaMemcpyHostToDevice, L.stream));
         L.h_descs[i] = FrameDesc{(uint64_t)i * slot, ws[i], hs[i]};
     }
     for (int i = n; i < B; ++i) L.h_descs[i] = L.h_descs[0];     // padding frames repeat frame 0; their results are ignored
@@ -630,11 +640,44 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
     return ZL_OK;
 }
 
-static bool is_pinned(const void* p)
+static bool is_pinned_query(const void* p)
 {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
+}
+
+// Pinned-ness of a caller's frame buffers, remembered per thread: a serving loop hands the same few buffers in again and
+// again, and cudaPointerGetAttributes costs microseconds per frame (64 of them per batch in round 1).  A batch whose first
+// and last frame lie inside one remembered pinned range is pinned; ranges come from zl_host_alloc (registered exactly)
+// or are learnt one frame at a time.
+namespace {
+struct PinRange { const uint8_t* lo; const uint8_t* hi; };
+std::mutex g_pin_mu;
+std::vector<PinRange> g_pin_ranges;
+}
+void register_pinned_range(const void* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    g_pin_ranges.push_back(PinRange{(const uint8_t*)p, (const uint8_t*)p + bytes});
+}
+void unregister_pinned_range(const void* p)
+{
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (size_t i = 0; i < g_pin_ranges.size(); ++i)
+        if (g_pin_ranges[i].lo == (const uint8_t*)p) { g_pin_ranges.erase(g_pin_ranges.begin() + i); return; }
+}
+static bool in_registered_range(const uint8_t* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (const PinRange& r : g_pin_ranges)
+        if (p >= r.lo && p + bytes <= r.hi) return true;
+    return false;
+}
+static bool is_pinned(const void* p, size_t bytes)
+{
+    if (in_registered_range((const uint8_t*)p, bytes)) return true;
+    return is_pinned_query(p);
 }
 
 int32_t Engine::infer_batch(const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
@@ -660,7 +703,7 @@ int32_t Engine::infer_batch(const uint8_t* const* frames, const int32_t* ws, con
     for (int i0 = 0; i0 < n; i0 += cfg.max_batch) {
         const int nb = std::min(cfg.max_batch, n - i0);
         bool pinned = true;
-        for (int i = 0; i < nb; ++i) pinned = pinned && is_pinned(frames[i0 + i]);
+        for (int i = 0; i < nb && pinned; ++i) pinned = is_pinned(frames[i0 + i], (size_t)ws[i0 + i] * hs[i0 + i] * 3);
         std::vector<int32_t> cnt(nb);
         ZL_TRY(run_lane_batch(L, frames + i0, ws + i0, hs + i0, nb, pinned, &dets, cnt.data(), raw_out != nullptr));
         if (raw_out) {
@@ -978,7 +1021,7 @@ int32_t Engine::bench_latency(const uint8_t* bgr, int w, int h, int warm, int it
     if (!bgr || !ms_out || iters < 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
     Lane& L = *lanes[0];
     std::lock_guard<std::mutex> g(L.mu);
-    const bool pinned = is_pinned(bgr);
+    const bool pinned = is_pinned(bgr, (size_t)w * h * 3);
     std::vector<zl_det> dets;
     int32_t cnt = 0;
     const uint8_t* fr[1] = {bgr};
@@ -988,6 +1031,69 @@ int32_t Engine::bench_latency(const uint8_t* bgr, int w, int h, int warm, int it
         const auto t1 = std::chrono::steady_clock::now();
         if (i >= warm) ms_out[i - warm] = std::chrono::duration<float, std::milli>(t1 - t0).count();
     }
+    return ZL_OK;
+}
+
+// End-to-end throughput loop in C (no interpreter in the timed path): `threads` host threads, each owning one batch of
+// `n` equal-size frames that sit back to back in (pinned) host memory at batches[t], call infer_batch `steps_per_thread`
+// times: H2D of the frames, the whole device path, D2H of the detections, every step.  Returns the wall time of the
+// slowest thread and the detections of the last step.
+int32_t Engine::bench_e2e(const uint8_t* const* batches, int threads, int n, int w, int h, int steps_total, double* seconds, int64_t* dets_last)
+{
+    if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
+    if (!batches || threads < 1 || threads > 16 || n < 1 || steps_total < 1 || !seconds) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    const size_t fb = (size_t)w * h * 3;
+    std::vector<int32_t> rcs(threads, ZL_OK);
+    std::vector<std::string> errs(threads);
+    std::vector<int64_t> nd(threads, 0);
+    std::vector<std::thread> th;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < threads; ++t) {
+        const int my_steps = steps_total / threads + (t < steps_total % threads ? 1 : 0);
+        th.emplace_back([&, t, my_steps] {
+            cudaSetDevice(cfg.device);
+            std::vector<const uint8_t*> fr(n);
+            std::vector<int32_t> ws(n, w), hs(n, h), cnt(n), off(n);
+            for (int i = 0; i < n; ++i) fr[i] = batches[t] + (size_t)i * fb;
+            std::vector<zl_det> out((size_t)n * 512);
+            for (int s = 0; s < my_steps; ++s) {
+                int32_t rc = infer_batch(fr.data(), ws.data(), hs.data(), n, out.data(), (int)out.size(), cnt.data(), off.data(), nullptr);
+                if (rc == ZL_INSUFFICIENT_RESOURCES) rc = ZL_OK;          // more detections than the scratch holds: counts are still valid
+                if (rc != ZL_OK) { rcs[t] = rc; errs[t] = get_error(); return; }
+                int64_t k = 0;
+                for (int i = 0; i < n; ++i) k += cnt[i];
+                nd[t] = k;
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int t = 0; t < threads; ++t) if (rcs[t] != ZL_OK) { set_error(errs[t]); return rcs[t]; }
+    if (dets_last) *dets_last = nd[0];
+    return ZL_OK;
+}
+
+// Pinned host -> device copy bandwidth on this engine's device (the e2e leg's ceiling): `iters` copies of `bytes`.
+int32_t Engine::bench_h2d(size_t bytes, int iters, double* gbs)
+{
+    if (bytes == 0 || iters < 1 || !gbs) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    void* h = nullptr; void* d = nullptr;
+    ZL_CUDA(cudaHostAlloc(&h, bytes, cudaHostAllocDefault));
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaFreeHost(h); ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "bench_h2d: out of device memory"); }
+    std::memset(h, 1, bytes);
+    Lane& L = *lanes[0];
+    std::lock_guard<std::mutex> g(L.mu);
+    cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, L.stream);
+    cudaEventRecord(L.ev0, L.stream);
+    for (int i = 0; i < iters; ++i) cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, L.stream);
+    cudaEventRecord(L.ev1, L.stream);
+    const cudaError_t cs = cudaStreamSynchronize(L.stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, L.ev0, L.ev1);
+    cudaFree(d); cudaFreeHost(h);
+    if (cs != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("bench_h2d: ") + cudaGetErrorString(cs));
+    *gbs = (double)bytes * iters / (ms * 1e-3) / 1e9;
     return ZL_OK;
 }
 

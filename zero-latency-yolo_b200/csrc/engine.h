@@ -101,6 +101,8 @@ public:
     int32_t profile_stalls(int set, uint64_t* out, int cap_ops, int32_t* n_out);
     int32_t bench_preprocess(int w, int h, int n, int iters, float* ms, double* bytes);
     int32_t bench_latency(const uint8_t* bgr, int w, int h, int warm, int iters, float* ms_out);
+    int32_t bench_e2e(const uint8_t* const* batches, int threads, int n, int w, int h, int steps_total, double* seconds, int64_t* dets_last);
+    int32_t bench_h2d(size_t bytes, int iters, double* gbs);
 
     zl_config cfg;
     zl_result_fn cb = nullptr;
@@ -157,5 +159,8 @@ private:
     int graph_captured = 0;
     std::atomic<uint32_t> sync_rr{0};
 };
+
+void register_pinned_range(const void* p, size_t bytes);     // zl_host_alloc / zl_host_free keep the pinned-range table exact
+void unregister_pinned_range(const void* p);
 
 }  // namespace zl

@@ -55,7 +55,7 @@ EXPORTS = [
     "zl_engine_load_weights_mem", "zl_engine_warmup", "zl_engine_set_callback", "zl_engine_submit",
     "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
-    "zl_engine_run_resident", "zl_engine_profile", "zl_engine_profile_stalls", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
+    "zl_engine_run_resident", "zl_engine_profile", "zl_engine_profile_stalls", "zl_bench_e2e", "zl_bench_h2d", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
     "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
 
@@ -98,6 +98,8 @@ def lib():
             "zl_engine_run_resident": (i32, [vp, i32, i32, C.POINTER(f32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
             "zl_engine_profile": (i32, [vp, i32, i32, C.POINTER(OpProfile), i32, C.POINTER(i32)]),
             "zl_engine_profile_stalls": (i32, [vp, i32, vp, i32, C.POINTER(i32)]),
+            "zl_bench_e2e": (i32, [vp, vp, i32, i32, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+            "zl_bench_h2d": (i32, [vp, sz, i32, C.POINTER(C.c_double)]),
             "zl_bench_latency": (i32, [vp, vp, i32, i32, i32, i32, vp]),
             "zl_bench_preprocess": (i32, [vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(C.c_double)]),
             "zl_bench_decode_nms": (i32, [vp, vp, i32, i32, i32, f32, f32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int64)]),
@@ -193,7 +195,7 @@ class Engine:
         """frames: list of [h,w,3] uint8 BGR.  Returns list of structured det arrays (one per frame)."""
         frames, ptrs, ws, hs, n = self._frame_args(frames)
         cap = capacity if capacity is not None else n * self.A
-        dets = np.zeros(max(cap, 1), DET_DTYPE)
+        dets = np.empty(max(cap, 1), DET_DTYPE)          # the library fills [0, sum(counts)); nothing else is read
         counts = np.zeros(n, np.int32)
         offs = np.zeros(n, np.int32)
         _check(lib().zl_infer_batch(self.h, ptrs, _ptr(ws), _ptr(hs), n, _ptr(dets), cap, _ptr(counts), _ptr(offs)))
@@ -273,6 +275,19 @@ class Engine:
         n = C.c_int32()
         _check(lib().zl_engine_profile_stalls(self.h, set_idx, _ptr(out), 256, C.byref(n)))
         return out[:n.value]
+
+    def bench_e2e(self, batches, steps_total):
+        """batches: list (one per host thread / lane) of pinned uint8 arrays [n,h,w,3].  Returns (seconds, dets of the last step)."""
+        n, h, w = batches[0].shape[:3]
+        ptrs = (C.c_void_p * len(batches))(*[b.ctypes.data for b in batches])
+        sec, nd = C.c_double(), C.c_int64()
+        _check(lib().zl_bench_e2e(self.h, ptrs, len(batches), n, w, h, steps_total, C.byref(sec), C.byref(nd)))
+        return sec.value, nd.value
+
+    def bench_h2d(self, nbytes=256 << 20, iters=8):
+        g = C.c_double()
+        _check(lib().zl_bench_h2d(self.h, nbytes, iters, C.byref(g)))
+        return g.value
 
     def bench_latency(self, frame, warmup=50, iters=500):
         f = frame if isinstance(frame, np.ndarray) else np.ascontiguousarray(frame, np.uint8)
