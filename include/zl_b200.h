@@ -86,7 +86,10 @@ typedef struct zl_config {
     int32_t num_lanes;          /* concurrent pipelines (streams + buffers) for the async path, 1..4 */
     int32_t use_graph;          /* 1 = capture each batch size in a CUDA graph */
     int32_t batch_window_us;    /* async path: wait this long to coalesce a batch (0 = take what is queued) */
-    int32_t reserved[8];
+    int32_t emit_wire;          /* 1 = also emit every frame's result in the reference's wire layout on the device (zl_*_wire entry points) */
+    int32_t cpu_core_id;        /* ServerConfig::use_cpu_affinity / cpu_core_id: worker i is pinned to core cpu_core_id + i; -1 = not pinned */
+    int32_t high_priority;      /* ServerConfig::use_high_priority: raise the workers' scheduling priority (best effort) */
+    int32_t reserved[5];
 } zl_config;
 
 typedef struct zl_stats {
@@ -127,6 +130,18 @@ typedef void (*zl_result_fn)(void* user, uint32_t client_id, uint32_t frame_id,
                              uint64_t timestamp, int32_t status,
                              const zl_det* dets, int32_t n);
 
+/* Result wire layout.  The body of the reference's DetectionResultPacket
+ * (src/common/protocol.h:541-567) for one frame, byte for byte:
+ *     uint32 frame_id | uint64 timestamp | uint16 count | count x Detection
+ * with Detection the 40-byte record of src/common/types.h:20-26 ({x,y,w,h,confidence f32; class_id i32; track_id u32 = 0;
+ * 4 padding bytes = 0; timestamp u64 = the batch's wall-clock ms, onnx_engine.cpp:812-815).  Packed, unaligned (14-byte
+ * header).  The device writes these blocks itself, frame after frame in batch order, and they come back in ONE copy:
+ * the adapter hands the bytes through (or memcpy's the records into GameState::detections) without touching a detection. */
+#define ZL_WIRE_HEADER_BYTES 14
+#define ZL_WIRE_DET_BYTES 40
+typedef void (*zl_wire_fn)(void* user, uint32_t client_id, uint32_t frame_id, uint64_t timestamp, int32_t status,
+                           const uint8_t* packet_body, size_t body_bytes);
+
 /* ---- lifecycle (IInferenceEngine::initialize / shutdown, onnx_engine.cpp:67-221) ---- */
 ZL_API void    zl_config_default(zl_config* cfg);
 ZL_API int32_t zl_engine_create(const zl_config* cfg, zl_engine** out);
@@ -136,6 +151,12 @@ ZL_API int32_t zl_engine_destroy(zl_engine* e);
  * the swap is atomic (hot reload, onnx_engine.cpp:473-515). */
 ZL_API int32_t zl_engine_load_weights(zl_engine* e, const char* path);
 ZL_API int32_t zl_engine_load_weights_mem(zl_engine* e, const void* blob, size_t len);
+/* The two halves of a load, for hosts that serve several devices: prepare builds the new weight set on the device next
+ * to the live one (serving continues), commit swaps atomically, discard drops a prepared set.  Reload that is atomic
+ * ACROSS devices = prepare on every engine, then commit on all of them or discard on all of them. */
+ZL_API int32_t zl_engine_prepare_weights(zl_engine* e, const char* path);
+ZL_API int32_t zl_engine_commit_weights(zl_engine* e);
+ZL_API int32_t zl_engine_discard_weights(zl_engine* e);
 /* warmupModel (onnx_engine.cpp:919-954): `iters` runs on an all-128 frame of model size; captures graphs. */
 ZL_API int32_t zl_engine_warmup(zl_engine* e, int32_t iters);
 
@@ -145,6 +166,8 @@ ZL_API int32_t zl_engine_set_callback(zl_engine* e, zl_result_fn fn, void* user)
 ZL_API int32_t zl_engine_submit(zl_engine* e, uint32_t client_id, uint32_t frame_id,
                                 uint64_t timestamp, int32_t width, int32_t height,
                                 const uint8_t* bgr, size_t len, int32_t is_keyframe);
+/* Async results as wire blocks (needs cfg.emit_wire = 1); replaces the zl_result_fn callback when set. */
+ZL_API int32_t zl_engine_set_wire_callback(zl_engine* e, zl_wire_fn fn, void* user);
 ZL_API size_t  zl_engine_queue_size(const zl_engine* e);
 /* Blocks until every accepted frame has had its callback. */
 ZL_API int32_t zl_engine_drain(zl_engine* e);
@@ -161,6 +184,12 @@ ZL_API int32_t zl_infer_batch(zl_engine* e, const uint8_t* const* frames,
                               const int32_t* widths, const int32_t* heights, int32_t n,
                               zl_det* dets_out, int32_t det_capacity,
                               int32_t* counts, int32_t* offsets);
+/* runInference over n frames with the results in the wire layout (needs cfg.emit_wire = 1): frame i's packet body is
+ * out[offsets[i] .. offsets[i+1]); offsets has n+1 entries.  det_timestamp_ms is the value every Detection::timestamp
+ * of the batch carries (the reference stamps wall-clock ms at post-processing time). */
+ZL_API int32_t zl_infer_batch_wire(zl_engine* e, const uint8_t* const* frames, const int32_t* widths, const int32_t* heights, int32_t n,
+                                   const uint32_t* frame_ids, const uint64_t* timestamps, uint64_t det_timestamp_ms,
+                                   uint8_t* out, size_t out_capacity, uint32_t* offsets);
 /* preProcess alone: out = [3, model_h, model_w] fp32 NCHW, exactly the tensor
  * the reference hands to ORT (onnx_engine.cpp:560-569). */
 ZL_API int32_t zl_preprocess(zl_engine* e, const uint8_t* bgr, int32_t width, int32_t height,

@@ -23,7 +23,8 @@ def test_registry_errors_and_no_fallback(host_exe):
 
 
 @pytest.mark.gpu
-def test_adapter_end_to_end_matches_c_abi(host_exe, model_n4, tmp_path):
+@pytest.mark.parametrize("results", ["device", "host"])
+def test_adapter_end_to_end_matches_c_abi(host_exe, model_n4, tmp_path, results):
     import zlb200
     from oracle import synth
     tensors, blob = model_n4
@@ -33,7 +34,9 @@ def test_adapter_end_to_end_matches_c_abi(host_exe, model_n4, tmp_path):
     fpath = tmp_path / "frames.bin"
     fpath.write_bytes(frames.tobytes())
     opath = tmp_path / "dets.bin"
-    out = subprocess.run([host_exe, "gpu", str(wpath), "4", "fp16", str(opath), str(fpath), "6", "800", "600"],
+    # results = "device": Detection records written by the GPU in the wire layout; "host": 24-byte records
+    # widened by the adapter.  Both must give the same 40-byte Detections; the run also checks the four EventBus events.
+    out = subprocess.run([host_exe, "gpu", str(wpath), "4", "fp16", str(opath), str(fpath), "6", "800", "600", results],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP16, max_batch=4, max_frame=(800, 600))
@@ -48,6 +51,9 @@ def test_adapter_end_to_end_matches_c_abi(host_exe, model_n4, tmp_path):
         assert c == len(ref[i])
         assert np.array_equal(recs[:, :24].reshape(-1), ref[i].view(np.uint8).reshape(-1))   # Detection's first 24 bytes == zl_det
         assert np.all(recs[:, 24:28] == 0)                                                   # track_id = 0 (onnx_engine.cpp:812)
+        if c:
+            ts = np.frombuffer(recs[:, 32:40].tobytes(), "<u8")
+            assert ts.min() > 1_600_000_000_000 and len(np.unique(ts)) == 1                  # one wall-clock ms stamp per batch
     assert sum(len(r) for r in ref) > 5
 
 

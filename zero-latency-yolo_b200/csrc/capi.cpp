@@ -56,6 +56,9 @@ void zl_config_default(zl_config* c)
     c->num_lanes = 1;
     c->use_graph = 1;
     c->batch_window_us = 0;
+    c->emit_wire = 0;
+    c->cpu_core_id = -1;
+    c->high_priority = 0;
 }
 
 int32_t zl_engine_create(const zl_config* cfg, zl_engine** out)
@@ -103,6 +106,37 @@ int32_t zl_engine_load_weights(zl_engine* e, const char* path)
     std::vector<char> buf((size_t)n);
     if (!f.read(buf.data(), n)) { zl::set_error(std::string("cannot read ") + path); return ZL_MODEL_LOAD_FAILED; }
     return e->impl->load_weights(buf.data(), buf.size());
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_prepare_weights(zl_engine* e, const char* path)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (!path) { zl::set_error("null path"); return ZL_INVALID_ARGUMENT; }
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) { zl::set_error(std::string("Model file not found: ") + path); return ZL_MODEL_NOT_FOUND; }
+    const std::streamsize n = f.tellg();
+    f.seekg(0);
+    std::vector<char> buf((size_t)n);
+    if (!f.read(buf.data(), n)) { zl::set_error(std::string("cannot read ") + path); return ZL_MODEL_LOAD_FAILED; }
+    return e->impl->prepare_weights(buf.data(), buf.size());
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_commit_weights(zl_engine* e)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->commit_weights();
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_discard_weights(zl_engine* e)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->discard_weights();
     ZL_GUARD_END
 }
 
@@ -215,6 +249,26 @@ int32_t zl_engine_profile(zl_engine* e, int32_t set, int32_t iters, zl_op_profil
     ZL_GUARD_BEGIN
     ZL_CHECK_ENGINE(e)
     return e->impl->profile(set, iters, out, cap, n_out);
+    ZL_GUARD_END
+}
+
+int32_t zl_engine_set_wire_callback(zl_engine* e, zl_wire_fn fn, void* user)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    if (fn && !e->impl->cfg.emit_wire) { zl::set_error("engine was created without emit_wire"); return ZL_INVALID_ARGUMENT; }
+    e->impl->wire_cb = fn; e->impl->wire_user = user;
+    return ZL_OK;
+    ZL_GUARD_END
+}
+
+int32_t zl_infer_batch_wire(zl_engine* e, const uint8_t* const* frames, const int32_t* widths, const int32_t* heights, int32_t n,
+                            const uint32_t* frame_ids, const uint64_t* timestamps, uint64_t det_timestamp_ms,
+                            uint8_t* out, size_t out_capacity, uint32_t* offsets)
+{
+    ZL_GUARD_BEGIN
+    ZL_CHECK_ENGINE(e)
+    return e->impl->infer_batch_wire(frames, widths, heights, n, frame_ids, timestamps, det_timestamp_ms, out, out_capacity, offsets);
     ZL_GUARD_END
 }
 

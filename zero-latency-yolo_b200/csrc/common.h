@@ -74,6 +74,29 @@ struct FrameDesc {
     int32_t w, h;
 };
 
+// Letterbox preprocessing (ZL_PRE_LETTERBOX; north_star (1) — NOT a parity mode: the reference stretches,
+// onnx_engine.cpp:673-693).  The frame is resized with ONE gain (aspect preserved, nearest sampling like the parity mode),
+// centred, and the border is filled with 114/255 (the ultralytics convention).  The same mapping, inverted, takes the
+// kept boxes back to the request frame.
+struct LetterboxMap {
+    float gain, inv_gain;
+    int32_t nw, nh, pad_x, pad_y;
+};
+__host__ __device__ inline LetterboxMap letterbox_map(int w, int h, int mw, int mh)
+{
+    LetterboxMap m;
+    const float gw = (float)mw / (float)w, gh = (float)mh / (float)h;
+    m.gain = gw < gh ? gw : gh;
+    m.nw = (int)((float)w * m.gain + 0.5f); m.nh = (int)((float)h * m.gain + 0.5f);
+    if (m.nw > mw) m.nw = mw;
+    if (m.nh > mh) m.nh = mh;
+    if (m.nw < 1) m.nw = 1;
+    if (m.nh < 1) m.nh = 1;
+    m.pad_x = (mw - m.nw) / 2; m.pad_y = (mh - m.nh) / 2;
+    m.inv_gain = 1.0f / m.gain;
+    return m;
+}
+
 constexpr int kKeyAnchorBits = 20;   // sort key: class[12] | ~conf_bits[32] | anchor[20]
 constexpr int kMaxAnchors = 1 << kKeyAnchorBits;
 constexpr int kMaxClasses = 1 << 12;

@@ -69,7 +69,7 @@ struct HaloParams {
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act, silu_tanh;
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
-    int32_t epi_variant;                             // epilogue_role specialisation (0..5 fast, 6 generic)
+    int32_t epi_variant, esets;                      // epilogue_role specialisation (0..5 fast, 6 generic); warp sets (1 or 2)
     int32_t wstream, nacc, nacc_log2, acc_cols;      // weights streamed with the patches (1) or resident (0); accumulator ring
     uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, chunk_stride, stage_stride, tmem_cols;
     int32_t cps, nst;                                // channel chunks per pipeline stage; stages per tile (= cchunks / cps)
@@ -159,7 +159,9 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
     const uint32_t warp = c.warp, lane = c.lane;
     const uint32_t q = warp & 3u;                            // TMEM lane quarter this warp may read
     const int cgp = (int)(warp - 2u) >> 2;                   // 0..3 within the quarter
-    const int set = cgp >> 1, c2 = cgp & 1;                  // tile parity this warp serves; which half of the quarter's items
+    // esets == 2: two sets of 8 warps on alternate tiles; esets == 1 (a CTA with a single tile: the latency path): all 16 on every tile
+    const int wq = 4 / p.esets;                              // warps of this quarter serving one tile
+    const int set = cgp / wq, c2 = cgp - set * wq;           // tile residue this warp serves; its share of the quarter's items
     const int row = (int)(q * 32u + lane);                   // A row == TMEM lane: h = row / 8, w = row % 8
     const int th = row >> 3, tw = row & 7;
     const int nchunk = c.ntile >> 4;
@@ -176,14 +178,15 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
     const float* bias_s = c.bias_s;
     uint32_t nstore = 0;
     // first item of this warp in every tile: item index c2 -> (sub-tile j0, chunk k0)
-    const int j0 = nchunk == 1 ? c2 : 0, k0 = nchunk == 1 ? 0 : c2;
+    int j0 = 0, k0 = c2;
+    while (k0 >= nchunk) { k0 -= nchunk; ++j0; }
     const int res_jstride = kTH * p.W * p.rpitch;            // residual elements between sub-tiles (fits 32 bits: one image row block)
     // tile walk: this set takes tiles tile0 + set*step, then every 2*step-th; (n, ty, tx) advance by a fixed decomposition
     TileWalk tw_;
-    walk_init(tw_, c.tile0 + set * c.tile_step, 2 * c.tile_step, p.tiles_x, p.tiles_y);
+    walk_init(tw_, c.tile0 + set * c.tile_step, p.esets * c.tile_step, p.tiles_x, p.tiles_y);
     // the residual (and, transitively, everything this kernel overwrites) belongs to earlier kernels of the stream
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int tile = c.tile0 + set * c.tile_step, tl = set; tile < p.num_tiles; tile += 2 * c.tile_step, tl += 2, walk_next(tw_, p.tiles_x, p.tiles_y)) {
+    for (int tile = c.tile0 + set * c.tile_step, tl = set; tile < p.num_tiles; tile += p.esets * c.tile_step, tl += p.esets, walk_next(tw_, p.tiles_x, p.tiles_y)) {
         const uint32_t acc = (uint32_t)tl & (uint32_t)(p.nacc - 1), aph = ((uint32_t)tl >> p.nacc_log2) & 1u;
         const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
         const int ox = tx * kTW + tw;
@@ -211,11 +214,11 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
         ZL_ST_BEGIN(t_epi);
         const uint32_t taddr = c.tmem_base + ((q * 32u) << 16) + acc * (uint32_t)p.acc_cols;
         int j = j0, k = k0;                                  // (sub-tile, chunk) of the pair's first item
-        for (int item = c2; item < items; item += 4) {
-            // the pair: item and item + 2
-            int jb = j, kb = k + 2;
+        for (int item = c2; item < items; item += 2 * wq) {
+            // the pair: item and item + wq
+            int jb = j, kb = k + wq;
             while (kb >= nchunk) { kb -= nchunk; ++jb; }
-            const bool have_b = item + 2 < items;
+            const bool have_b = item + wq < items;
             uint32_t v[2][16];
             tmem_ld16(taddr + (uint32_t)(j * p.nt + (k << 4)), v[0]);
             if (have_b) tmem_ld16(taddr + (uint32_t)(jb * p.nt + (kb << 4)), v[1]);
@@ -349,8 +352,8 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
                     }
                 }
             }
-            // next pair: item + 4
-            k += 4;
+            // next pair: item + 2 * wq
+            k += 2 * wq;
             while (k >= nchunk) { k -= nchunk; ++j; }
         }
         // this warp is done reading the accumulator: hand it back to the MMA warp
@@ -424,7 +427,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         mbar_init(bar_wfull, (uint32_t)kProducers);
         for (int a = 0; a < p.nacc; ++a) {
             mbar_init(bar_tfull + 8u * a, 1u);
-            mbar_init(bar_tempty + 8u * a, (uint32_t)kEpiWarps / 2u);   // one arrival per epilogue warp of the set that drains it
+            mbar_init(bar_tempty + 8u * a, (uint32_t)kEpiWarps / (uint32_t)p.esets);   // one arrival per epilogue warp of the set that drains it
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmap_w);
@@ -910,6 +913,13 @@ int32_t conv_s2d_prepare(const ConvWeights& w, const View& x, const View& y, int
 
 static const bool g_use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
 
+static int grid_for(const ConvHaloOp& o, int num_sms)
+{
+    int grid = o.num_tiles * o.nsplit;
+    if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
+    return grid;
+}
+
 int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsigned long long* stats)
 {
     static thread_local int last_dev = -1;
@@ -936,6 +946,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.patch_bytes = o.patch_bytes; p.patch_alloc = o.patch_alloc; p.subpatch_alloc = o.subpatch_alloc; p.chunk_stride = o.chunk_stride; p.stage_stride = o.stage_stride;
     p.cps = o.cps; p.nst = o.nst;
     p.wstream = o.wstream; p.nacc = o.nacc; p.acc_cols = o.acc_cols;
+    p.esets = (o.num_tiles * o.nsplit > grid_for(o, num_sms)) ? 2 : 1;      // more than one tile per CTA: two alternating sets
     p.epi_variant = 6;
     if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC")) {
         const int fmt = o.f16 ? 3 : 0;
@@ -946,8 +957,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.nacc_log2 = o.nacc == 8 ? 3 : (o.nacc == 4 ? 2 : (o.nacc == 2 ? 1 : 0));
     p.tmem_cols = o.tmem_cols;
     p.stats = stats;
-    int grid = o.num_tiles * o.nsplit;
-    if (grid > num_sms) grid = (num_sms / o.nsplit) * o.nsplit;       // every CTA keeps one slice: grid is a multiple of nsplit
+    const int grid = grid_for(o, num_sms);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = (size_t)o.smem_bytes; cfg.stream = st;
     cudaLaunchAttribute attr[1];

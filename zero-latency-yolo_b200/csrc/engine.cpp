@@ -8,6 +8,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
+
 #include <cuda_fp16.h>
 
 namespace zl {
@@ -67,7 +71,7 @@ int32_t Engine::init()
     if (cfg.num_classes < 1 || cfg.num_classes > kMaxClasses) ZL_FAIL(ZL_INVALID_ARGUMENT, "num_classes out of range");
     if (cfg.max_batch < 1 || cfg.max_batch > 256) ZL_FAIL(ZL_INVALID_ARGUMENT, "max_batch must be 1..256");
     if (cfg.precision < ZL_PRECISION_FP32 || cfg.precision > ZL_PRECISION_FP16) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad precision");
-    if (cfg.preprocess_mode != ZL_PRE_STRETCH_NEAREST) ZL_FAIL(ZL_INVALID_ARGUMENT, "only the reference's nearest-stretch preprocessing is implemented");
+    if (cfg.preprocess_mode != ZL_PRE_STRETCH_NEAREST && cfg.preprocess_mode != ZL_PRE_LETTERBOX) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad preprocess_mode");
     if (cfg.max_frame_w <= 0) cfg.max_frame_w = cfg.model_w;
     if (cfg.max_frame_h <= 0) cfg.max_frame_h = cfg.model_h;
     if (cfg.num_lanes < 1) cfg.num_lanes = 1;
@@ -85,6 +89,7 @@ int32_t Engine::init()
     if (const char* ev = getenv("ZL_DISABLE_HALO")) use_halo = !(ev[0] == '1');
     if (const char* ev = getenv("ZL_FUSE_PRE")) fuse_pre = (ev[0] == '1');
     if (const char* ev = getenv("ZL_DISABLE_STEM")) use_stem = !(ev[0] == '1');
+    if (cfg.preprocess_mode == ZL_PRE_LETTERBOX) fuse_pre = false;     // the fused A/B kernel only knows the parity sampling
     persist_min_units = 0;      // measured: the persistent kernel wins even for b=1 (p50 0.77 -> 0.44 ms), so it always runs when it can
     if (const char* ev = getenv("ZL_PERSIST_MIN_UNITS")) persist_min_units = atoi(ev);
     if (const char* ev = getenv("ZL_DEEP_K_PERSIST")) deep_k_persist = (ev[0] == '1');
@@ -106,7 +111,48 @@ int32_t Engine::init()
 }
 
 // ------------------------------------------------------------------ weights
+// load = prepare + commit.  The two halves are separate entry points so that a host serving several devices can build the
+// new weight set on EVERY device first and only then swap them all (or none): hot reload that is atomic across devices.
 int32_t Engine::load_weights(const void* blob, size_t len)
+{
+    ZL_TRY(prepare_weights(blob, len));
+    return commit_weights();
+}
+
+int32_t Engine::discard_weights()
+{
+    std::lock_guard<std::mutex> load_guard(load_mu);
+    cudaSetDevice(cfg.device);
+    pending_convs.clear();                      // ~ConvWeights frees the device buffers
+    pending_by_name.clear();
+    return ZL_OK;
+}
+
+int32_t Engine::commit_weights()
+{
+    std::lock_guard<std::mutex> load_guard(load_mu);
+    if (pending_convs.empty()) ZL_FAIL(ZL_NOT_INITIALIZED, "no prepared weights to commit");
+    ZL_CUDA(cudaSetDevice(cfg.device));
+    {
+        // swap under every lane's lock: no batch is in flight, every cached op list / graph is stale
+        std::vector<std::unique_lock<std::mutex>> locks;
+        for (auto& L : lanes) locks.emplace_back(L->mu);
+        ZL_CUDA(cudaDeviceSynchronize());
+        convs.swap(pending_convs);
+        conv_by_name.swap(pending_by_name);
+        for (auto& L : lanes) {
+            for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second);
+            L->graphs.clear();
+            L->ops.clear();
+        }
+        weights_loaded = true;
+    }
+    pending_convs.clear();                      // the previous set: ~ConvWeights frees its device buffers
+    pending_by_name.clear();
+    return ZL_OK;
+}
+
+int32_t Engine::prepare_weights(const void* blob, size_t len)
 {
     ZL_CUDA(cudaSetDevice(cfg.device));
     ParsedModel pm;
@@ -233,26 +279,15 @@ int32_t Engine::load_weights(const void* blob, size_t len)
         new_by_name[s.name] = cw.get();
         new_convs.push_back(std::move(cw));
     }
-    {
-        // swap under every lane's lock: no batch is in flight, every cached op list / graph is stale
-        std::vector<std::unique_lock<std::mutex>> locks;
-        for (auto& L : lanes) locks.emplace_back(L->mu);
-        ZL_CUDA(cudaDeviceSynchronize());
-        convs.swap(new_convs);
-        conv_by_name.swap(new_by_name);
-        for (auto& L : lanes) {
-            for (auto& kv : L->graphs) cudaGraphExecDestroy(kv.second);
-            L->graphs.clear();
-            L->ops.clear();
-        }
-        weights_loaded = true;
-    }
-    new_convs.clear();                          // the previous set: ~ConvWeights frees its device buffers
+    ZL_CUDA(cudaDeviceSynchronize());           // uploads done: the set is complete
+    pending_convs.swap(new_convs);              // a previously prepared, never committed set is dropped here
+    pending_by_name.swap(new_by_name);
     return ZL_OK;
 }
 
 // ------------------------------------------------------------------ lane buffers
 int Engine::inline_dets(int B) const { return std::min<int>(B * 64, B * num_anchors); }
+size_t Engine::wire_inline_bytes(int B) const { return (size_t)kWireHeader * B + (size_t)kWireDet * inline_dets(B); }
 
 int32_t Engine::alloc_lane(Lane& L)
 {
@@ -345,6 +380,18 @@ int32_t Engine::alloc_lane(Lane& L)
     L.h_result_bytes = (size_t)(4 + 2 * MB) * 4 + (size_t)det_cap * sizeof(DevDet);
     ZL_CUDA(cudaHostAlloc(&L.h_result, L.h_result_bytes, cudaHostAllocDefault));
     ZL_CUDA(cudaHostAlloc(&L.h_frames, (size_t)MB * slot_bytes(), cudaHostAllocDefault));
+    if (cfg.emit_wire) {
+        // N3: the reference's result wire layout, written by the device (postprocess.cu wire_pack_kernel)
+        L.wire_cap = (size_t)kWireHeader * MB + (size_t)kWireDet * det_cap;
+        ZL_CUDA(cudaMalloc(&L.d_wire, L.wire_cap));
+        ZL_CUDA(cudaMalloc(&L.d_wire_off, sizeof(uint32_t) * (MB + 1)));
+        ZL_CUDA(cudaMalloc(&L.d_wmeta, sizeof(WireMeta) * (MB + 1)));
+        ZL_CUDA(cudaMemset(L.d_wmeta, 0, sizeof(WireMeta) * (MB + 1)));
+        ZL_CUDA(cudaHostAlloc(&L.h_wire, L.wire_cap, cudaHostAllocDefault));
+        ZL_CUDA(cudaHostAlloc(&L.h_wire_off, sizeof(uint32_t) * (MB + 1), cudaHostAllocDefault));
+        ZL_CUDA(cudaHostAlloc(&L.h_wmeta, sizeof(WireMeta) * (MB + 1), cudaHostAllocDefault));
+        std::memset(L.h_wmeta, 0, sizeof(WireMeta) * (MB + 1));
+    }
     return ZL_OK;
 }
 
@@ -357,6 +404,13 @@ void Engine::free_lane(Lane& L)
     if (L.h_descs) cudaFreeHost(L.h_descs);
     if (L.h_result) cudaFreeHost(L.h_result);
     if (L.h_frames) cudaFreeHost(L.h_frames);
+    if (L.d_wire) cudaFree(L.d_wire);
+    if (L.d_wire_off) cudaFree(L.d_wire_off);
+    if (L.d_wmeta) cudaFree(L.d_wmeta);
+    if (L.h_wire) cudaFreeHost(L.h_wire);
+    if (L.h_wire_off) cudaFreeHost(L.h_wire_off);
+    if (L.h_wmeta) cudaFreeHost(L.h_wmeta);
+    L.d_wire = nullptr; L.d_wire_off = nullptr; L.d_wmeta = nullptr; L.h_wire = nullptr; L.h_wire_off = nullptr; L.h_wmeta = nullptr;
     if (L.ev0) cudaEventDestroy(L.ev0);
     if (L.ev1) cudaEventDestroy(L.ev1);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -503,8 +557,8 @@ int32_t Engine::launch_op(Lane& L, int B, const Op& op)
     const bool f16 = cfg.precision == ZL_PRECISION_FP16;
     switch (op.kind) {
         case Op::PRE:
-            if (op.y.c == 16) return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, f16 ? PRE_S2D16_F16 : PRE_S2D16_BF16, op.y.ptr);
-            return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr);
+            if (op.y.c == 16) return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, f16 ? PRE_S2D16_F16 : PRE_S2D16_BF16, op.y.ptr, cfg.preprocess_mode == ZL_PRE_LETTERBOX);
+            return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr, cfg.preprocess_mode == ZL_PRE_LETTERBOX);
         case Op::CONV_TC: return conv_tc_launch(st, op.tc);
         case Op::CONV_HALO: return conv_halo_launch(st, op.halo, num_sms);
         case Op::CONV_SIMT: return launch_conv_simt(st, *op.w, op.x, op.y, op.has_res ? &op.res : nullptr);
@@ -534,11 +588,18 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
         if (want_raw ? op.kind == Op::DECODE_FILTER : (op.kind == Op::DECODE || op.kind == Op::FILTER)) continue;
         ZL_TRY(launch_op(L, B, op));
     }
+    if (cfg.preprocess_mode == ZL_PRE_LETTERBOX)      // non-parity mode: boxes back from the letterboxed model frame to the request frame
+        ZL_TRY(launch_letterbox_unmap(st, B, L.pb.maxn, L.pb.header, L.pb.dets, L.d_descs, cfg.model_w, cfg.model_h, L.pb.cap));
+    if (cfg.emit_wire) ZL_TRY(launch_wire_pack(st, B, L.pb, L.d_wmeta, L.d_wire, (uint32_t)std::min<size_t>(L.wire_cap, 0xffffffffu), L.d_wire_off));
     if (with_d2h) {
         // header (total, cnt[], off[]) and the first inline_dets records in two fixed-size copies
         const size_t hdr = (size_t)(4 + 2 * L.pb.maxn) * 4;
         ZL_CUDA(cudaMemcpyAsync(L.h_result, L.pb.header, hdr, cudaMemcpyDeviceToHost, st));
         ZL_CUDA(cudaMemcpyAsync(L.h_result + hdr, L.pb.dets, (size_t)inline_dets(B) * sizeof(DevDet), cudaMemcpyDeviceToHost, st));
+        if (cfg.emit_wire) {           // the wire blocks: offsets and the inline window, fixed sizes (graph-capturable)
+            ZL_CUDA(cudaMemcpyAsync(L.h_wire_off, L.d_wire_off, sizeof(uint32_t) * (B + 1), cudaMemcpyDeviceToHost, st));
+            ZL_CUDA(cudaMemcpyAsync(L.h_wire, L.d_wire, wire_inline_bytes(B), cudaMemcpyDeviceToHost, st));
+        }
     }
     return ZL_OK;
 }
@@ -584,8 +645,9 @@ int32_t Engine::launch_batch(Lane& L, int B, bool want_raw)
 
 // Runs n (<= max_batch) frames on lane L.  Caller holds L.mu.
 int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
-                               bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts, bool want_raw)
+                               bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts, bool want_raw, const WireReq* wr)
 {
+    if (wr && !cfg.emit_wire) ZL_FAIL(ZL_INVALID_ARGUMENT, "engine was created without emit_wire");
     ZL_CUDA(cudaSetDevice(cfg.device));
     const int B = graph_batch_for(n);
     const size_t slot = slot_bytes();
@@ -612,6 +674,14 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
     }
     for (int i = n; i < B; ++i) L.h_descs[i] = L.h_descs[0];     // padding frames repeat frame 0; their results are ignored
     ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.h_descs, sizeof(FrameDesc) * B, cudaMemcpyHostToDevice, L.stream));
+    if (cfg.emit_wire) {
+        for (int i = 0; i < B; ++i) {
+            const int k = i < n ? i : 0;
+            L.h_wmeta[i] = WireMeta{wr && wr->frame_ids ? wr->frame_ids[k] : 0u, 0u, wr && wr->timestamps ? wr->timestamps[k] : 0ull};
+        }
+        L.h_wmeta[L.pb.maxn] = WireMeta{0u, 0u, wr ? wr->det_ts : 0ull};
+        ZL_CUDA(cudaMemcpyAsync(L.d_wmeta, L.h_wmeta, sizeof(WireMeta) * (L.pb.maxn + 1), cudaMemcpyHostToDevice, L.stream));
+    }
     ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
     ZL_TRY(launch_batch(L, B, want_raw));
     ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
@@ -629,6 +699,14 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
     if (total > (uint32_t)inline_dets(B)) {       // rare: more survivors than the inline window
         ZL_CUDA(cudaMemcpyAsync(L.h_result + hdr_b, L.pb.dets, (size_t)total * sizeof(DevDet), cudaMemcpyDeviceToHost, L.stream));
         ZL_CUDA(cudaStreamSynchronize(L.stream));
+    }
+    if (wr) {
+        const uint32_t wbytes = L.h_wire_off[n];                 // frames n..B-1 are padding: their blocks come after
+        if (wbytes > L.wire_cap) ZL_FAIL(ZL_INFERENCE_ERROR, "wire buffer overflow");
+        if (wbytes > wire_inline_bytes(B)) {
+            ZL_CUDA(cudaMemcpyAsync(L.h_wire, L.d_wire, wbytes, cudaMemcpyDeviceToHost, L.stream));
+            ZL_CUDA(cudaStreamSynchronize(L.stream));
+        }
     }
     const zl_det* all = (const zl_det*)(L.h_result + hdr_b);
     static_assert(sizeof(zl_det) == sizeof(DevDet), "layout");
@@ -725,6 +803,44 @@ int32_t Engine::infer_batch(const uint8_t* const* frames, const int32_t* ws, con
     return ZL_OK;
 }
 
+int32_t Engine::infer_batch_wire(const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n, const uint32_t* frame_ids,
+                                 const uint64_t* timestamps, uint64_t det_ts, uint8_t* out, size_t cap, uint32_t* offsets)
+{
+    if (!weights_loaded) ZL_FAIL(ZL_NOT_INITIALIZED, "weights not loaded");
+    if (!cfg.emit_wire) ZL_FAIL(ZL_INVALID_ARGUMENT, "engine was created without emit_wire");
+    if (n < 0 || (n > 0 && (!frames || !ws || !hs)) || !offsets || (!out && cap)) ZL_FAIL(ZL_INVALID_ARGUMENT, "null argument");
+    Lane* Lp = nullptr;
+    std::unique_lock<std::mutex> g;
+    for (auto& cand : lanes) {
+        std::unique_lock<std::mutex> t(cand->mu, std::try_to_lock);
+        if (t.owns_lock()) { Lp = cand.get(); g = std::move(t); break; }
+    }
+    if (!Lp) {
+        Lp = lanes[sync_rr.fetch_add(1) % lanes.size()].get();
+        g = std::unique_lock<std::mutex>(Lp->mu);
+    }
+    Lane& L = *Lp;
+    std::vector<zl_det> dets;
+    size_t total = 0;
+    bool overflow = false;
+    offsets[0] = 0;
+    for (int i0 = 0; i0 < n; i0 += cfg.max_batch) {
+        const int nb = std::min(cfg.max_batch, n - i0);
+        bool pinned = true;
+        for (int i = 0; i < nb && pinned; ++i) pinned = is_pinned(frames[i0 + i], (size_t)ws[i0 + i] * hs[i0 + i] * 3);
+        std::vector<int32_t> cnt(nb);
+        WireReq wr{frame_ids ? frame_ids + i0 : nullptr, timestamps ? timestamps + i0 : nullptr, det_ts};
+        ZL_TRY(run_lane_batch(L, frames + i0, ws + i0, hs + i0, nb, pinned, &dets, cnt.data(), false, &wr));
+        const uint32_t bytes = L.h_wire_off[nb];
+        if (total + bytes <= cap) std::memcpy(out + total, L.h_wire, bytes); else overflow = true;
+        for (int i = 0; i < nb; ++i) offsets[i0 + i + 1] = (uint32_t)(total + L.h_wire_off[i + 1]);
+        total += bytes;
+    }
+    { std::lock_guard<std::mutex> g2(smu); st_count += n; }
+    if (overflow) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "wire output capacity too small");
+    return ZL_OK;
+}
+
 int32_t Engine::preprocess_one(const uint8_t* bgr, int w, int h, size_t len, float* out_chw)
 {
     if (!bgr || !out_chw) ZL_FAIL(ZL_INVALID_ARGUMENT, "null argument");
@@ -742,7 +858,7 @@ int32_t Engine::preprocess_one(const uint8_t* bgr, int w, int h, size_t len, flo
     int32_t rc = ZL_OK;
     cudaMemcpyAsync(d_img, bgr, len, cudaMemcpyHostToDevice, L.stream);
     cudaMemcpyAsync(d_desc, &fd, sizeof(fd), cudaMemcpyHostToDevice, L.stream);
-    rc = launch_preprocess(L.stream, d_img, d_desc, 1, cfg.model_w, cfg.model_h, PRE_NCHW_F32, d_out);
+    rc = launch_preprocess(L.stream, d_img, d_desc, 1, cfg.model_w, cfg.model_h, PRE_NCHW_F32, d_out, cfg.preprocess_mode == ZL_PRE_LETTERBOX);
     cudaError_t ce = cudaMemcpyAsync(out_chw, d_out, ob, cudaMemcpyDeviceToHost, L.stream);
     cudaError_t cs = cudaStreamSynchronize(L.stream);
     cudaFree(d_img); cudaFree(d_out); cudaFree(d_desc);
@@ -1179,6 +1295,20 @@ int32_t Engine::submit(uint32_t client_id, uint32_t frame_id, uint64_t ts, int w
 void Engine::worker_main(int lane_id)
 {
     cudaSetDevice(cfg.device);
+    // ServerConfig::use_cpu_affinity / cpu_core_id / use_high_priority (the reference pins and raises its inference thread,
+    // onnx_engine.cpp:318-330): worker i of this engine goes to core cpu_core_id + i; failures are not errors
+    if (cfg.cpu_core_id >= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET((cfg.cpu_core_id + lane_id) % std::max(1, (int)std::thread::hardware_concurrency()), &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    if (cfg.high_priority) {
+        sched_param sp{};
+        sp.sched_priority = 0;
+        if (nice(-5) == -1) { /* not permitted: keep the default */ }
+        (void)sp;
+    }
     Lane& L = *lanes[lane_id];
     std::vector<Request> batch;
     std::vector<const uint8_t*> fr;
@@ -1202,9 +1332,21 @@ void Engine::worker_main(int lane_id)
         for (int i = 0; i < n; ++i) { fr[i] = h_slots + (size_t)batch[i].slot * slot_bytes(); ws[i] = batch[i].w; hs[i] = batch[i].h; }
         int32_t rc;
         std::string err;
+        std::vector<uint8_t> wire;
+        std::vector<uint32_t> woff;
         {
             std::lock_guard<std::mutex> g(L.mu);
-            rc = run_lane_batch(L, fr.data(), ws.data(), hs.data(), n, true, &dets, cnt.data());
+            if (wire_cb) {
+                std::vector<uint32_t> ids(n);
+                std::vector<uint64_t> tss(n);
+                for (int i = 0; i < n; ++i) { ids[i] = batch[i].frame_id; tss[i] = batch[i].timestamp; }
+                const uint64_t now_ms = (uint64_t)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
+                WireReq wr{ids.data(), tss.data(), now_ms};        // Detection::timestamp = wall-clock ms (onnx_engine.cpp:813-815)
+                rc = run_lane_batch(L, fr.data(), ws.data(), hs.data(), n, true, &dets, cnt.data(), false, &wr);
+                if (rc == ZL_OK) { woff.assign(L.h_wire_off, L.h_wire_off + n + 1); wire.assign(L.h_wire, L.h_wire + woff[n]); }
+            } else {
+                rc = run_lane_batch(L, fr.data(), ws.data(), hs.data(), n, true, &dets, cnt.data());
+            }
             if (rc != ZL_OK) err = get_error();
         }
         // deliver in pop order across lanes
@@ -1216,7 +1358,9 @@ void Engine::worker_main(int lane_id)
         size_t k = 0;
         for (int i = 0; i < n; ++i) {
             const int c = rc == ZL_OK ? cnt[i] : 0;
-            if (cb) cb(cb_user, batch[i].client_id, batch[i].frame_id, batch[i].timestamp, rc, c ? dets.data() + k : nullptr, c);
+            if (wire_cb) wire_cb(wire_user, batch[i].client_id, batch[i].frame_id, batch[i].timestamp, rc,
+                                 rc == ZL_OK ? wire.data() + woff[i] : nullptr, rc == ZL_OK ? (size_t)(woff[i + 1] - woff[i]) : 0);
+            else if (cb) cb(cb_user, batch[i].client_id, batch[i].frame_id, batch[i].timestamp, rc, c ? dets.data() + k : nullptr, c);
             k += c;
         }
         {

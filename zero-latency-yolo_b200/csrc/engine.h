@@ -49,6 +49,8 @@ struct Request {
     std::chrono::steady_clock::time_point t_submit;
 };
 
+struct WireReq { const uint32_t* frame_ids; const uint64_t* timestamps; uint64_t det_ts; };   // per-frame header fields + the batch's Detection::timestamp
+
 struct Lane {
     int id = 0;
     cudaStream_t stream = nullptr;
@@ -67,6 +69,10 @@ struct Lane {
     FrameDesc* h_descs = nullptr;
     uint8_t* h_result = nullptr; size_t h_result_bytes = 0;
     uint8_t* h_frames = nullptr;                // staging for non-pinned sync inputs: [max_batch] slots
+    // N3 (cfg.emit_wire): result wire blocks written by the device
+    uint8_t* d_wire = nullptr; uint32_t* d_wire_off = nullptr; WireMeta* d_wmeta = nullptr;
+    uint8_t* h_wire = nullptr; uint32_t* h_wire_off = nullptr; WireMeta* h_wmeta = nullptr;
+    size_t wire_cap = 0;
     // per batch size
     std::map<int, std::vector<Op>> ops;
     std::map<int, cudaGraphExec_t> graphs;
@@ -79,7 +85,10 @@ public:
     explicit Engine(const zl_config& cfg);
     ~Engine();
     int32_t init();
-    int32_t load_weights(const void* blob, size_t len);
+    int32_t load_weights(const void* blob, size_t len);        // prepare + commit
+    int32_t prepare_weights(const void* blob, size_t len);     // parse, validate, upload next to the live set (serving continues)
+    int32_t commit_weights();                                  // atomic swap under the lanes' locks
+    int32_t discard_weights();
     int32_t warmup(int iters);
     int32_t start_workers();
     void stop_workers();
@@ -91,6 +100,8 @@ public:
 
     int32_t infer_batch(const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
                         zl_det* out, int cap, int32_t* counts, int32_t* offsets, float* raw_out);
+    int32_t infer_batch_wire(const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n, const uint32_t* frame_ids,
+                             const uint64_t* timestamps, uint64_t det_ts, uint8_t* out, size_t cap, uint32_t* offsets);
     int32_t preprocess_one(const uint8_t* bgr, int w, int h, size_t len, float* out_chw);
     int32_t decode_nms(const float* raw, int n, int nc, int A, const int32_t* iw, const int32_t* ih, float conf, float iou,
                        zl_det* out, int cap, int32_t* counts, int32_t* offsets,
@@ -107,6 +118,8 @@ public:
     zl_config cfg;
     zl_result_fn cb = nullptr;
     void* cb_user = nullptr;
+    zl_wire_fn wire_cb = nullptr;   // replaces cb when set (needs cfg.emit_wire)
+    void* wire_user = nullptr;
     int num_anchors = 0;
     int num_sms = 148;
     bool use_halo = true;
@@ -127,15 +140,18 @@ private:
     int32_t launch_batch(Lane& L, int B, bool want_raw = false);   // graph if enabled, else direct
     int graph_batch_for(int n) const;
     int32_t run_lane_batch(Lane& L, const uint8_t* const* frames, const int32_t* ws, const int32_t* hs, int n,
-                           bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts, bool want_raw = false);
+                           bool frames_pinned, std::vector<zl_det>* dets, int32_t* counts, bool want_raw = false, const WireReq* wr = nullptr);
     void worker_main(int lane_id);
     size_t slot_bytes() const { return (size_t)cfg.max_frame_w * cfg.max_frame_h * 3; }
     int inline_dets(int B) const;
+    size_t wire_inline_bytes(int B) const;
 
     ModelDef md;
     std::mutex load_mu;                            // one load_weights at a time
     std::vector<std::unique_ptr<ConvWeights>> convs;
     std::map<std::string, ConvWeights*> conv_by_name;
+    std::vector<std::unique_ptr<ConvWeights>> pending_convs;   // prepared, not yet committed
+    std::map<std::string, ConvWeights*> pending_by_name;
     float* d_class_weights = nullptr;
     std::vector<std::unique_ptr<Lane>> lanes;
 

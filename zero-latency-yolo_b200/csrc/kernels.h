@@ -37,7 +37,10 @@ enum PreLayout : int32_t {
     PRE_S2D16_F16 = 5
 };
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
-                          int32_t mw, int32_t mh, int32_t layout, void* out);
+                          int32_t mw, int32_t mh, int32_t layout, void* out, int32_t letterbox = 0);
+// ZL_PRE_LETTERBOX: the kept boxes of a batch mapped back from the letterboxed model frame to the request frame.
+int32_t launch_letterbox_unmap(cudaStream_t st, int32_t n, int32_t maxn, const uint32_t* header, DevDet* dets, const FrameDesc* descs,
+                               int32_t mw, int32_t mh, uint32_t cap);
 
 // ---------------------------------------------------------------- convs
 // fp32 CUDA-core implicit GEMM (exact mode) — any cin/cout, k in {1,3}, stride in {1,2}.
@@ -143,6 +146,12 @@ int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, 
 // applyNMS (onnx_engine.cpp:837-878): per-frame key sort + per-class greedy bitmask suppression.
 int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb);
 int32_t nms_configure();   // one-time cudaFuncSetAttribute calls
+
+// Result wire layout on the device: per frame {frame_id u32, timestamp u64, count u16} + count x 40-byte
+// Detection, packed back to back in batch order (src/common/protocol.h:541-567, src/common/types.h:20-26).
+struct WireMeta { uint32_t frame_id; uint32_t pad; uint64_t timestamp; };     // meta[n] per frame; meta[maxn].timestamp = Detection::timestamp of the batch
+constexpr int kWireHeader = 14, kWireDet = 40;
+int32_t launch_wire_pack(cudaStream_t st, int32_t n, const PostBuffers& pb, const WireMeta* meta, uint8_t* wire, uint32_t wire_cap, uint32_t* wire_off);
 
 // ---------------------------------------------------------------- TMA helper
 int32_t make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,

@@ -566,7 +566,61 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
 
 int g_nms_smem_keys = 0;   // key capacity (elements) of the smem sort buffer
 
+// ---- N3: the reference's result wire layout, written by the device -----------------------------------------------------
+// One CTA per batch.  Phase 1: exclusive scan of the per-frame block lengths (14 + 40 * count) in FRAME order, so the
+// blocks are laid out deterministically whatever order the NMS CTAs finished in.  Phase 2: one warp per frame writes the
+// 14-byte header and the records with 16-bit stores (a block starts at an even, otherwise unaligned, offset).
+__device__ __forceinline__ void st16(uint8_t* p, uint32_t v) { *reinterpret_cast<uint16_t*>(p) = (uint16_t)v; }
+__device__ __forceinline__ void st32u(uint8_t* p, uint32_t v) { st16(p, v & 0xffffu); st16(p + 2, v >> 16); }
+
+__global__ void __launch_bounds__(256)
+wire_pack_kernel(int n, int maxn, const uint32_t* __restrict__ header, const DevDet* __restrict__ dets, const WireMeta* __restrict__ meta,
+                 uint8_t* __restrict__ wire, uint32_t wire_cap, uint32_t* __restrict__ wire_off)
+{
+    __shared__ uint32_t s_off[257];
+    const int tid = threadIdx.x;
+    const uint32_t* h_cnt = header + 4;
+    const uint32_t* h_off = header + 4 + maxn;
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < n; ++i) { s_off[i] = run; run += (uint32_t)kWireHeader + (uint32_t)kWireDet * h_cnt[i]; }
+        s_off[n] = run;
+    }
+    __syncthreads();
+    for (int i = tid; i <= n; i += blockDim.x) wire_off[i] = s_off[i];
+    const uint64_t det_ts = meta[maxn].timestamp;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int f = warp; f < n; f += (int)blockDim.x >> 5) {
+        const uint32_t cnt = h_cnt[f], src = h_off[f], base = s_off[f];
+        if (lane == 0 && base + kWireHeader <= wire_cap) {
+            uint8_t* o = wire + base;
+            st32u(o, meta[f].frame_id);
+            st32u(o + 4, (uint32_t)meta[f].timestamp); st32u(o + 8, (uint32_t)(meta[f].timestamp >> 32));
+            st16(o + 12, cnt);                                       // static_cast<uint16_t>(detections.size())
+        }
+        for (uint32_t j = lane; j < cnt; j += 32) {
+            const uint32_t at = base + kWireHeader + j * kWireDet;
+            if (at + kWireDet > wire_cap) break;
+            const DevDet d = dets[src + j];
+            uint8_t* o = wire + at;
+            st32u(o, __float_as_uint(d.x)); st32u(o + 4, __float_as_uint(d.y)); st32u(o + 8, __float_as_uint(d.w)); st32u(o + 12, __float_as_uint(d.h));
+            st32u(o + 16, __float_as_uint(d.conf)); st32u(o + 20, (uint32_t)d.cls);
+            st32u(o + 24, 0u);                                       // track_id = 0 (onnx_engine.cpp:812)
+            st32u(o + 28, 0u);                                       // struct padding
+            st32u(o + 32, (uint32_t)det_ts); st32u(o + 36, (uint32_t)(det_ts >> 32));
+        }
+    }
+}
+
 }  // namespace
+
+int32_t launch_wire_pack(cudaStream_t st, int32_t n, const PostBuffers& pb, const WireMeta* meta, uint8_t* wire, uint32_t wire_cap, uint32_t* wire_off)
+{
+    if (n < 1 || n > 256) ZL_FAIL(ZL_INVALID_ARGUMENT, "wire_pack: batch must be 1..256");
+    wire_pack_kernel<<<1, 256, 0, st>>>(n, pb.maxn, pb.header, pb.dets, meta, wire, wire_cap, wire_off);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
 
 int32_t launch_dfl_decode(cudaStream_t st, const HeadLevel lv[3], int32_t n, int32_t nc, int32_t A, float* raw, bool precise)
 {

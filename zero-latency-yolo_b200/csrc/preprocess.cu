@@ -21,10 +21,41 @@ __device__ __forceinline__ int src_index(int i, float scale, int src_dim) {
     return min(s, src_dim - 1);
 }
 
+// Where model pixel (x, y) samples the frame.  Parity mode: the reference's independent stretch of both axes.
+// Letterbox: one gain, centred, border = 114 (returns false: the pixel is padding).
+struct Sampler {
+    float scale_w, scale_h;
+    int w, h, pad_x, pad_y, nw, nh;
+    bool letterbox;
+    __device__ __forceinline__ Sampler(const FrameDesc& d, int mw, int mh, bool lb) : w(d.w), h(d.h), letterbox(lb) {
+        if (!lb) {
+            scale_w = __fdiv_rn((float)d.w, (float)mw);
+            scale_h = __fdiv_rn((float)d.h, (float)mh);
+            pad_x = pad_y = 0; nw = mw; nh = mh;
+        } else {
+            const LetterboxMap m = letterbox_map(d.w, d.h, mw, mh);
+            pad_x = m.pad_x; pad_y = m.pad_y; nw = m.nw; nh = m.nh;
+            scale_w = __fdiv_rn((float)d.w, (float)m.nw);
+            scale_h = __fdiv_rn((float)d.h, (float)m.nh);
+        }
+    }
+    __device__ __forceinline__ bool row(int y, int* sy) const {
+        if (letterbox && (y < pad_y || y >= pad_y + nh)) return false;
+        *sy = src_index(y - pad_y, scale_h, h);
+        return true;
+    }
+    __device__ __forceinline__ bool col(int x, int* sx) const {
+        if (letterbox && (x < pad_x || x >= pad_x + nw)) return false;
+        *sx = src_index(x - pad_x, scale_w, w);
+        return true;
+    }
+};
+constexpr float kLetterboxFill = 114.0f;
+
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs,
-                  int mw, int mh, void* __restrict__ out)
+                  int mw, int mh, void* __restrict__ out, int letterbox)
 {
     const int f = blockIdx.y;
     const int wq = (mw + 3) >> 2;
@@ -35,21 +66,25 @@ preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restri
     const FrameDesc d = descs[f];
     if (d.w <= 0 || d.h <= 0) return;                 // unused batch slot
     const uint8_t* __restrict__ img = staging + d.offset;
-    const float scale_w = __fdiv_rn((float)d.w, (float)mw);
-    const float scale_h = __fdiv_rn((float)d.h, (float)mh);
-    const int sy = src_index(y, scale_h, d.h);
+    const Sampler sm(d, mw, mh, letterbox != 0);
+    int sy = 0;
+    const bool row_ok = sm.row(y, &sy);
     const uint8_t* __restrict__ row = img + (size_t)sy * d.w * 3;
 
     float r[4], g[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int x = min(x0 + i, mw - 1);
-        const int sx = src_index(x, scale_w, d.w);
-        const uint8_t* px = row + (size_t)sx * 3;
-        // source is BGR; the reference reads channel 2-c for output channel c
-        b[i] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
-        g[i] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
-        r[i] = __fdiv_rn((float)__ldg(px + 2), 255.0f);
+        int sx = 0;
+        if (row_ok && sm.col(x, &sx)) {
+            const uint8_t* px = row + (size_t)sx * 3;
+            // source is BGR; the reference reads channel 2-c for output channel c
+            b[i] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
+            g[i] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
+            r[i] = __fdiv_rn((float)__ldg(px + 2), 255.0f);
+        } else {
+            b[i] = g[i] = r[i] = __fdiv_rn(kLetterboxFill, 255.0f);
+        }
     }
     const int nvalid = min(4, mw - x0);
     if (LAYOUT == PRE_NCHW_F32) {
@@ -85,7 +120,7 @@ preprocess_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restri
 // (k = (dy*2+dx)*3 + channel, channels R,G,B; 12..15 = 0), one 32-byte store.  Same sampling and rounding as above.
 template <bool F16>
 __global__ void __launch_bounds__(256)
-preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs, int mw, int mh, uint4* __restrict__ out)
+preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs, int mw, int mh, uint4* __restrict__ out, int letterbox)
 {
     const int f = blockIdx.y;
     const int W2 = mw >> 1, H2 = mh >> 1;
@@ -95,19 +130,24 @@ preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __re
     if (d.w <= 0 || d.h <= 0) return;
     const int Y = item / W2, X = item - Y * W2;
     const uint8_t* __restrict__ img = staging + d.offset;
-    const float scale_w = __fdiv_rn((float)d.w, (float)mw);
-    const float scale_h = __fdiv_rn((float)d.h, (float)mh);
+    const Sampler sm(d, mw, mh, letterbox != 0);
     float v[12];
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-        const int sy = src_index(2 * Y + dy, scale_h, d.h);
+        int sy = 0;
+        const bool row_ok = sm.row(2 * Y + dy, &sy);
         const uint8_t* __restrict__ row = img + (size_t)sy * d.w * 3;
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
-            const uint8_t* px = row + (size_t)src_index(2 * X + dx, scale_w, d.w) * 3;
-            v[(dy * 2 + dx) * 3 + 0] = __fdiv_rn((float)__ldg(px + 2), 255.0f);     // R = byte 2
-            v[(dy * 2 + dx) * 3 + 1] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
-            v[(dy * 2 + dx) * 3 + 2] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
+            int sx = 0;
+            if (row_ok && sm.col(2 * X + dx, &sx)) {
+                const uint8_t* px = row + (size_t)sx * 3;
+                v[(dy * 2 + dx) * 3 + 0] = __fdiv_rn((float)__ldg(px + 2), 255.0f);     // R = byte 2
+                v[(dy * 2 + dx) * 3 + 1] = __fdiv_rn((float)__ldg(px + 1), 255.0f);
+                v[(dy * 2 + dx) * 3 + 2] = __fdiv_rn((float)__ldg(px + 0), 255.0f);
+            } else {
+                v[(dy * 2 + dx) * 3 + 0] = v[(dy * 2 + dx) * 3 + 1] = v[(dy * 2 + dx) * 3 + 2] = __fdiv_rn(kLetterboxFill, 255.0f);
+            }
         }
     }
     uint32_t w[8];
@@ -119,27 +159,57 @@ preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __re
     o[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// The kept boxes of a letterboxed batch, mapped back to the request frame: the filter normalised model-pixel boxes by the
+// frame's width / height like the reference does; undo that, remove the padding and the gain, normalise again.
+__global__ void letterbox_unmap_kernel(int n, int maxn, const uint32_t* __restrict__ header, DevDet* __restrict__ dets,
+                                       const FrameDesc* __restrict__ descs, int mw, int mh, uint32_t cap)
+{
+    const int f = blockIdx.x;
+    if (f >= n) return;
+    const uint32_t cnt = header[4 + f], off = header[4 + maxn + f];
+    const FrameDesc d = descs[f];
+    const LetterboxMap m = letterbox_map(d.w, d.h, mw, mh);
+    const float fw = (float)d.w, fh = (float)d.h;
+    for (uint32_t i = threadIdx.x; i < cnt && off + i < cap; i += blockDim.x) {
+        DevDet t = dets[off + i];
+        t.x = ((t.x * fw - (float)m.pad_x) * m.inv_gain) / fw;
+        t.y = ((t.y * fh - (float)m.pad_y) * m.inv_gain) / fh;
+        t.w = (t.w * fw * m.inv_gain) / fw;
+        t.h = (t.h * fh * m.inv_gain) / fh;
+        dets[off + i] = t;
+    }
+}
+
 }  // namespace
 
+int32_t launch_letterbox_unmap(cudaStream_t st, int32_t n, int32_t maxn, const uint32_t* header, DevDet* dets, const FrameDesc* descs,
+                               int32_t mw, int32_t mh, uint32_t cap)
+{
+    if (n <= 0) return ZL_OK;
+    letterbox_unmap_kernel<<<n, 128, 0, st>>>(n, maxn, header, dets, descs, mw, mh, cap);
+    ZL_CUDA(cudaGetLastError());
+    return ZL_OK;
+}
+
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
-                          int32_t mw, int32_t mh, int32_t layout, void* out)
+                          int32_t mw, int32_t mh, int32_t layout, void* out, int32_t letterbox)
 {
     if (n <= 0) return ZL_OK;
     if (layout == PRE_S2D16_BF16 || layout == PRE_S2D16_F16) {
         if ((mw & 1) || (mh & 1)) ZL_FAIL(ZL_INVALID_ARGUMENT, "s2d preprocess needs even model dims");
         dim3 g(ceil_div((mw / 2) * (mh / 2), 256), n);
-        if (layout == PRE_S2D16_F16) preprocess_s2d_kernel<true><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out);
-        else preprocess_s2d_kernel<false><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out);
+        if (layout == PRE_S2D16_F16) preprocess_s2d_kernel<true><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out, letterbox);
+        else preprocess_s2d_kernel<false><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out, letterbox);
         ZL_CUDA(cudaGetLastError());
         return ZL_OK;
     }
     const int threads = 256;
     dim3 grid(ceil_div(ceil_div(mw, 4) * mh, threads), n);
     switch (layout) {
-        case PRE_NCHW_F32: preprocess_kernel<PRE_NCHW_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
-        case PRE_NHWC4_F32: preprocess_kernel<PRE_NHWC4_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
-        case PRE_NHWC4_BF16: preprocess_kernel<PRE_NHWC4_BF16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
-        case PRE_NHWC4_F16: preprocess_kernel<PRE_NHWC4_F16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out); break;
+        case PRE_NCHW_F32: preprocess_kernel<PRE_NCHW_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out, letterbox); break;
+        case PRE_NHWC4_F32: preprocess_kernel<PRE_NHWC4_F32><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out, letterbox); break;
+        case PRE_NHWC4_BF16: preprocess_kernel<PRE_NHWC4_BF16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out, letterbox); break;
+        case PRE_NHWC4_F16: preprocess_kernel<PRE_NHWC4_F16><<<grid, threads, 0, st>>>(staging, descs, mw, mh, out, letterbox); break;
         default: ZL_FAIL(ZL_INVALID_ARGUMENT, "bad preprocess layout");
     }
     ZL_CUDA(cudaGetLastError());

@@ -33,6 +33,8 @@ public:
 private:
     static void onResult(void* user, uint32_t client_id, uint32_t frame_id, uint64_t timestamp, int32_t status,
                          const zl_det* dets, int32_t n);
+    static void onWire(void* user, uint32_t client_id, uint32_t frame_id, uint64_t timestamp, int32_t status,
+                       const uint8_t* body, size_t bytes);
     static ErrorCode toErrorCode(int32_t rc) { return static_cast<ErrorCode>(rc); }
     void modelMonitorThreadFunc();                                          // onnx_engine.cpp:473-515
 
@@ -43,6 +45,8 @@ private:
     std::atomic<uint64_t> callback_errors_{0};
     std::string model_hash_;
     std::atomic<uint32_t> model_version_{1};
+    uint64_t reload_failures_ = 0;          // under monitor_mu_
+    std::string reload_error_;
     mutable std::mutex monitor_mu_;
     std::condition_variable monitor_cv_;
     std::thread monitor_thread_;

@@ -47,7 +47,22 @@ static int run_cpu() {
                           "avg_preprocessing_time_ms", "avg_postprocessing_time_ms", "worker_threads", "fp_mode", "graph_captured"})
         CHECK(st.count(k) == 1);
     CHECK(st["running"] == "false" && st["simulation_mode"] == "false");
+    CHECK(st.count("model_reload_failures") == 1 && st.count("wire_results") == 1);
     CHECK(eng->getQueueSize() == 0);
+    // model_hash is SHA-256 like the reference's calculateModelHash (onnx_engine.cpp:1087-1124): FIPS 180-4 vectors
+    {
+        const char* tmp = "/tmp/zl_host_test_sha.bin";
+        { std::ofstream o(tmp, std::ios::binary | std::ios::trunc); o << "abc"; }
+        ServerConfig hc; hc.model_path = tmp;
+        auto he = mgr.createEngine("b200", hc);
+        (void)he->initialize();                                      // fails (not a model / no GPU) but has hashed the file
+        CHECK(he->getStatus()["model_hash"] == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad");
+        { std::ofstream o(tmp, std::ios::binary | std::ios::trunc); o << std::string(1000000, 'a'); }
+        auto he2 = mgr.createEngine("b200", hc);
+        (void)he2->initialize();
+        CHECK(he2->getStatus()["model_hash"] == "cdc76e5c9914fb9281a1c7e284d73e67f1809a48a497200e046d39ccc7112cd0");
+        std::remove(tmp);
+    }
     CHECK(eng->shutdown().isOk());
     // an existing file that is not a model + no GPU: still a clean error, never a fallback
     cfg.model_path = "/proc/self/cmdline";
@@ -73,6 +88,19 @@ static int run_gpu(int argc, char** argv) {
     cfg.b200.max_batch = 4;
     cfg.b200.max_frame_width = w; cfg.b200.max_frame_height = h;
     cfg.max_queue_size = 64;
+    cfg.b200.wire_results = !(argc >= 11 && std::strcmp(argv[10], "host") == 0);   // default: 40-byte records written by the device
+    std::atomic<int> ev_start{0}, ev_stop{0}, ev_req{0}, ev_done{0};
+    std::atomic<bool> ev_ids_ok{true};
+    EventBus::getInstance().subscribe(events::SYSTEM_STARTUP, [&](const Event& e) { if (e.getSource() == "B200InferenceEngine") ev_start++; });
+    EventBus::getInstance().subscribe(events::SYSTEM_SHUTDOWN, [&](const Event& e) { if (e.getSource() == "B200InferenceEngine") ev_stop++; });
+    EventBus::getInstance().subscribe(events::INFERENCE_REQUESTED, [&](const Event& e) {
+        ev_req++;
+        if (static_cast<const InferenceEvent&>(e).getClientId() != 42) ev_ids_ok = false;
+    });
+    EventBus::getInstance().subscribe(events::INFERENCE_COMPLETED, [&](const Event& e) {
+        ev_done++;
+        if (static_cast<const InferenceEvent&>(e).getClientId() != 42) ev_ids_ok = false;
+    });
     std::vector<uint8_t> frames((size_t)n * w * h * 3);
     { std::ifstream f(frames_path, std::ios::binary); CHECK(f.read((char*)frames.data(), frames.size())); }
 
@@ -80,6 +108,8 @@ static int run_gpu(int argc, char** argv) {
     CHECK(eng != nullptr);
     auto ri = eng->initialize();
     if (ri.hasError()) { std::fprintf(stderr, "initialize: %s\n", ri.error().toString().c_str()); return 1; }
+    CHECK(ev_start == 1);                                                // SYSTEM_STARTUP (onnx_engine.cpp:160-162)
+    CHECK(eng->getStatus()["wire_results"] == (cfg.b200.wire_results ? "device" : "host"));
 
     std::mutex mu;
     std::condition_variable cv;
@@ -122,7 +152,7 @@ static int run_gpu(int argc, char** argv) {
     monitor.join();
     // bad frame length -> INVALID_INPUT (onnx_engine.cpp:659-665)
     InferenceRequest bad;
-    bad.width = (uint16_t)w; bad.height = (uint16_t)h; bad.data.assign(10, 0);
+    bad.client_id = 42; bad.width = (uint16_t)w; bad.height = (uint16_t)h; bad.data.assign(10, 0);
     auto rb = eng->submitInference(bad);
     CHECK(rb.hasError() && rb.error().code == ErrorCode::INVALID_INPUT);
     CHECK(cb_thread != submit_thread);                                   // callbacks come from an engine-owned thread
@@ -146,6 +176,9 @@ static int run_gpu(int argc, char** argv) {
     }
     CHECK(eng->shutdown().isOk());
     CHECK(eng->submitInference(bad).error().code == ErrorCode::NOT_INITIALIZED);
+    // the four events of the reference engine (onnx_engine.cpp:160-162,214-216,229-231,359-363); the rejected frame was
+    // announced too, like in the reference, which publishes before it looks at the request
+    CHECK(ev_stop == 1 && ev_req >= total && ev_done == total && ev_ids_ok);
     std::printf("host_test gpu: ok, %d frames, avg latency %s ms, graphs %s\n", total, st["avg_inference_time_ms"].c_str(), st["graph_captured"].c_str());
     return 0;
 }
@@ -197,6 +230,8 @@ static int run_reload(int argc, char** argv) {
     const GameState c = infer(1000);
     CHECK(c.detections.size() == b.detections.size());
     CHECK(eng->getStatus()["model_version"] == "2");
+    CHECK(eng->getStatus()["model_reload_failures"] == "1" && !eng->getStatus()["model_reload_error"].empty());   // visible, not silent
+    CHECK(eng->getStatus()["model_hash"] != hash_a);
     CHECK(eng->shutdown().isOk());
     std::remove(live.c_str());
     std::printf("host_test reload: ok (%zu -> %zu detections)\n", a.detections.size(), b.detections.size());

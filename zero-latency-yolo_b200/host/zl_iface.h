@@ -13,11 +13,14 @@
 #pragma once
 #ifdef ZL_USE_REFERENCE_HEADERS
 #include "inference/inference_engine.h"
+#include "common/event_bus.h"
 #else
 #include <cstdint>
 #include <functional>
+#include <chrono>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -97,6 +100,7 @@ struct B200Config {
     int num_lanes = 2;
     int batch_window_us = 0;
     bool use_class_weights = false;     // false == the reference's effective behaviour
+    bool wire_results = true;           // detections arrive as the reference's 40-byte wire records, written by the device
     bool use_model_monitor = false;     // hot reload: the reference's optimization.use_model_monitor (onnx_engine.cpp:38,145)
     int model_check_interval_ms = 10000; // the reference checks every 10 s (onnx_engine.cpp:480)
     std::vector<float> class_weights;
@@ -153,6 +157,59 @@ public:
 private:
     std::map<std::string, std::shared_ptr<IInferenceEngineFactory>> factories_;
 };
+
+// ---- the slice of src/common/event_bus.h:15-176 the engine publishes to (same names and signatures) ----
+using EventType = std::string;
+namespace events {
+constexpr const char* SYSTEM_STARTUP = "SYSTEM_STARTUP";            // event_bus.h:17
+constexpr const char* SYSTEM_SHUTDOWN = "SYSTEM_SHUTDOWN";          // event_bus.h:18
+constexpr const char* INFERENCE_REQUESTED = "INFERENCE_REQUESTED";  // event_bus.h:25
+constexpr const char* INFERENCE_COMPLETED = "INFERENCE_COMPLETED";  // event_bus.h:26
+}  // namespace events
+
+class Event {
+public:
+    explicit Event(EventType type) : type_(std::move(type)), timestamp_(std::chrono::system_clock::now()) {}
+    virtual ~Event() = default;
+    const EventType& getType() const { return type_; }
+    const std::chrono::system_clock::time_point& getTimestamp() const { return timestamp_; }
+    void setSource(const std::string& s) { source_ = s; }
+    const std::string& getSource() const { return source_; }
+    void setData(const std::string& k, const std::string& v) { data_[k] = v; }
+    std::string getData(const std::string& k) const { auto it = data_.find(k); return it == data_.end() ? std::string() : it->second; }
+private:
+    EventType type_;
+    std::chrono::system_clock::time_point timestamp_;
+    std::string source_;
+    std::unordered_map<std::string, std::string> data_;
+};
+
+class InferenceEvent : public Event {
+public:
+    InferenceEvent(const EventType& type, uint32_t client_id, uint32_t frame_id) : Event(type), client_id_(client_id), frame_id_(frame_id) {}
+    uint32_t getClientId() const { return client_id_; }
+    uint32_t getFrameId() const { return frame_id_; }
+private:
+    uint32_t client_id_, frame_id_;
+};
+
+using EventHandler = std::function<void(const Event&)>;
+
+class EventBus {
+public:
+    static EventBus& getInstance() { static EventBus b; return b; }
+    void subscribe(const EventType& type, EventHandler handler) { std::lock_guard<std::mutex> g(mu_); handlers_[type].push_back(std::move(handler)); }
+    void publish(const Event& event) {
+        std::vector<EventHandler> copy;
+        { std::lock_guard<std::mutex> g(mu_); auto it = handlers_.find(event.getType()); if (it != handlers_.end()) copy = it->second; }
+        for (const auto& h : copy) { try { h(event); } catch (...) {} }
+    }
+    void publishInferenceEvent(const EventType& type, uint32_t client_id, uint32_t frame_id) { InferenceEvent e(type, client_id, frame_id); publish(e); }
+private:
+    std::mutex mu_;
+    std::unordered_map<EventType, std::vector<EventHandler>> handlers_;
+};
+inline void publishEvent(const Event& e) { EventBus::getInstance().publish(e); }
 
 #define REGISTER_INFERENCE_ENGINE(factory_class)                                                        \
     namespace {                                                                                         \

@@ -31,7 +31,7 @@ class Config(C.Structure):
                 ("class_weights", C.POINTER(C.c_float)), ("max_batch", C.c_int32),
                 ("max_frame_w", C.c_int32), ("max_frame_h", C.c_int32), ("preprocess_mode", C.c_int32),
                 ("queue_depth", C.c_int32), ("num_lanes", C.c_int32), ("use_graph", C.c_int32),
-                ("batch_window_us", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("batch_window_us", C.c_int32), ("emit_wire", C.c_int32), ("cpu_core_id", C.c_int32), ("high_priority", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Stats(C.Structure):
@@ -49,11 +49,13 @@ class OpProfile(C.Structure):
 
 
 RESULT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32, C.c_void_p, C.c_int32)
+WIRE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32, C.c_void_p, C.c_size_t)
+WIRE_HEADER_BYTES, WIRE_DET_BYTES = 14, 40
 
 EXPORTS = [
     "zl_config_default", "zl_engine_create", "zl_engine_destroy", "zl_engine_load_weights",
-    "zl_engine_load_weights_mem", "zl_engine_warmup", "zl_engine_set_callback", "zl_engine_submit",
-    "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
+    "zl_engine_load_weights_mem", "zl_engine_prepare_weights", "zl_engine_commit_weights", "zl_engine_discard_weights", "zl_engine_warmup", "zl_engine_set_callback", "zl_engine_submit",
+    "zl_engine_set_wire_callback", "zl_infer_batch_wire", "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
     "zl_engine_run_resident", "zl_engine_profile", "zl_engine_profile_stalls", "zl_bench_e2e", "zl_bench_h2d", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
     "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
@@ -83,9 +85,14 @@ def lib():
             "zl_engine_destroy": (i32, [vp]),
             "zl_engine_load_weights": (i32, [vp, C.c_char_p]),
             "zl_engine_load_weights_mem": (i32, [vp, vp, sz]),
+            "zl_engine_prepare_weights": (i32, [vp, C.c_char_p]),
+            "zl_engine_commit_weights": (i32, [vp]),
+            "zl_engine_discard_weights": (i32, [vp]),
             "zl_engine_warmup": (i32, [vp, i32]),
             "zl_engine_set_callback": (i32, [vp, RESULT_FN, vp]),
             "zl_engine_submit": (i32, [vp, u32, u32, u64, i32, i32, vp, sz, i32]),
+            "zl_engine_set_wire_callback": (i32, [vp, WIRE_FN, vp]),
+            "zl_infer_batch_wire": (i32, [vp, vp, vp, vp, i32, vp, vp, u64, vp, sz, vp]),
             "zl_engine_queue_size": (sz, [vp]),
             "zl_engine_drain": (i32, [vp]),
             "zl_engine_get_stats": (i32, [vp, C.POINTER(Stats)]),
@@ -142,7 +149,7 @@ def pinned_array(shape, dtype=np.uint8):
 class Engine:
     def __init__(self, model_w=416, model_h=416, nc=4, scale="n", precision=BF16, conf=0.5, iou=0.45,
                  max_batch=1, device=0, max_frame=(0, 0), queue_depth=8, num_lanes=1, use_graph=1,
-                 batch_window_us=0, class_weights=None):
+                 batch_window_us=0, class_weights=None, emit_wire=False, letterbox=False):
         L = lib()
         cfg = Config()
         L.zl_config_default(C.byref(cfg))
@@ -151,6 +158,8 @@ class Engine:
         cfg.conf_threshold, cfg.iou_threshold = conf, iou
         cfg.max_batch, cfg.max_frame_w, cfg.max_frame_h = max_batch, max_frame[0], max_frame[1]
         cfg.queue_depth, cfg.num_lanes, cfg.use_graph, cfg.batch_window_us = queue_depth, num_lanes, use_graph, batch_window_us
+        cfg.emit_wire = 1 if emit_wire else 0
+        cfg.preprocess_mode = 1 if letterbox else 0          # ZL_PRE_LETTERBOX is NOT a parity mode (the reference stretches)
         self._cw = None
         if class_weights is not None:
             self._cw = np.ascontiguousarray(class_weights, np.float32)
@@ -179,6 +188,15 @@ class Engine:
     def load_weights(self, path: str):
         _check(lib().zl_engine_load_weights(self.h, path.encode()))
 
+    def prepare_weights(self, path: str):
+        _check(lib().zl_engine_prepare_weights(self.h, path.encode()))
+
+    def commit_weights(self):
+        _check(lib().zl_engine_commit_weights(self.h))
+
+    def discard_weights(self):
+        _check(lib().zl_engine_discard_weights(self.h))
+
     def warmup(self, iters=3):
         _check(lib().zl_engine_warmup(self.h, iters))
 
@@ -200,6 +218,25 @@ class Engine:
         offs = np.zeros(n, np.int32)
         _check(lib().zl_infer_batch(self.h, ptrs, _ptr(ws), _ptr(hs), n, _ptr(dets), cap, _ptr(counts), _ptr(offs)))
         return [dets[offs[i]:offs[i] + counts[i]].copy() for i in range(n)]
+
+    def infer_wire(self, frames, frame_ids, timestamps, det_timestamp_ms):
+        """Results in the reference's wire layout (DetectionResultPacket body per frame).  Returns a list of bytes objects."""
+        frames, ptrs, ws, hs, n = self._frame_args(frames)
+        ids = np.ascontiguousarray(frame_ids, np.uint32)
+        tss = np.ascontiguousarray(timestamps, np.uint64)
+        cap = n * (WIRE_HEADER_BYTES + WIRE_DET_BYTES * self.A)
+        out = np.empty(cap, np.uint8)
+        offs = np.zeros(n + 1, np.uint32)
+        _check(lib().zl_infer_batch_wire(self.h, ptrs, _ptr(ws), _ptr(hs), n, _ptr(ids), _ptr(tss), int(det_timestamp_ms), _ptr(out), cap, _ptr(offs)))
+        return [out[offs[i]:offs[i + 1]].tobytes() for i in range(n)]
+
+    def set_wire_callback(self, fn):
+        """fn(client_id, frame_id, timestamp, status, body bytes)"""
+        def tramp(user, cid, fid, ts, status, bptr, nbytes):
+            body = bytes((C.c_uint8 * nbytes).from_address(bptr)) if nbytes and bptr else b""
+            fn(cid, fid, ts, status, body)
+        self._wcb = WIRE_FN(tramp)
+        _check(lib().zl_engine_set_wire_callback(self.h, self._wcb, None))
 
     def forward_raw(self, frames):
         frames, ptrs, ws, hs, n = self._frame_args(frames)
