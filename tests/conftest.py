@@ -16,7 +16,7 @@ def pytest_configure(config):
 def built_lib():
     """The in-tree shared library; built on demand (nvcc cross-compiles without a GPU)."""
     import zlb200
-    if not os.path.exists(zlb200.LIB_PATH):
+    if not os.path.exists(zlb200.LIB_PATH) or not os.path.exists(zlb200.TEST_LIB_PATH):
         import subprocess
         subprocess.check_call(["bash", os.path.join(ROOT, "zero-latency-yolo_b200", "csrc", "build.sh")])
     return zlb200.lib()

@@ -29,6 +29,18 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(built_lib, s), f"{s} missing from libzl_b200.so"
 
 
+def test_test_hooks_are_not_in_the_product_library(built_lib):
+    """zl_test_conv / zl_probe_* live in libzl_b200_test.so (include/zl_b200_test.h), never in the drop-in library."""
+    import zlb200
+    hdr = open(os.path.join(ROOT, "include", "zl_b200_test.h")).read()
+    decl = sorted(set(re.findall(r"ZL_API\s+[\w\s\*]+?\b(zl_\w+)\s*\(", hdr)))
+    assert decl == sorted(zlb200.TEST_EXPORTS)
+    t = zlb200.testlib()
+    for s in decl:
+        assert hasattr(t, s), f"{s} missing from libzl_b200_test.so"
+        assert not hasattr(built_lib, s), f"{s} must not be exported by libzl_b200.so"
+
+
 def test_error_codes_match_reference_values():
     # src/common/result.h:14-48
     hdr = open(os.path.join(ROOT, "include", "zl_b200.h")).read()

@@ -15,6 +15,9 @@
 #include <cfloat>
 #include <type_traits>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace zl {
@@ -298,7 +301,8 @@ decode_filter_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2,
 
 // ============================================================= N1: NMS
 constexpr int kNmsThreads = 1024;
-constexpr int kMaxLargeSeg = 512;     // queue slots for class segments with more than 32 candidates
+constexpr int kMaxLargeSeg = 512;
+constexpr int kWholeCtaSeg = 512;     // class segments larger than this are swept by all 1024 threads, one segment at a time     // queue slots for class segments with more than 32 candidates
 
 // calculateIoU (onnx_engine.cpp:881-909) with IEEE single ops in the reference's order.
 __device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
@@ -315,6 +319,30 @@ __device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
     return uni > 0.0f ? __fdiv_rn(inter, uni) : 0.0f;
 }
 
+// Phase timestamps of the slowest-looking CTA (debug aid, ZL_NMS_DEBUG=1 prints them): written by thread 0 of the CTA
+// whose frame index is g_nms_dbg_frame.
+__device__ long long g_nms_dbg[8];
+__device__ int g_nms_dbg_frame = 0;
+#define ZL_NMS_STAMP(k) do { if (tid == 0 && f == g_nms_dbg_frame) g_nms_dbg[k] = clock64(); } while (0)
+
+// `calculateIoU(a, b) > thr` (onnx_engine.cpp:871,881-909), decided EXACTLY but usually without the IEEE division: boxes that
+// do not overlap have IoU 0 (never > thr for thr >= 0); otherwise a reciprocal estimate of inter/union settles every case
+// that is not within 1e-5 of the threshold, and only the knife edges pay for __fdiv_rn.  Same operation order as iou_ref.
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+    const float ahw = __fmul_rn(a.z, 0.5f), ahh = __fmul_rn(a.w, 0.5f);
+    const float bhw = __fmul_rn(b.z, 0.5f), bhh = __fmul_rn(b.w, 0.5f);
+    const float xo = fmaxf(0.0f, __fsub_rn(fminf(__fadd_rn(a.x, ahw), __fadd_rn(b.x, bhw)), fmaxf(__fsub_rn(a.x, ahw), __fsub_rn(b.x, bhw))));
+    const float yo = fmaxf(0.0f, __fsub_rn(fminf(__fadd_rn(a.y, ahh), __fadd_rn(b.y, bhh)), fmaxf(__fsub_rn(a.y, ahh), __fsub_rn(b.y, bhh))));
+    const float inter = __fmul_rn(xo, yo);
+    if (!(inter > 0.0f) && thr >= 0.0f) return false;            // IoU is 0 (or the union guard returns 0): not > thr
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(a.z, a.w), __fmul_rn(b.z, b.w)), inter);
+    if (!(uni > 0.0f)) return 0.0f > thr;
+    const float q = inter * __frcp_rn(uni);                      // within a few ulp of the correctly rounded quotient
+    if (q > thr + 1e-5f) return true;
+    if (q < thr - 1e-5f) return false;
+    return __fdiv_rn(inter, uni) > thr;
+}
+
 // One CTA per frame.  Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | scan scratch.
 __global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
@@ -324,7 +352,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     extern __shared__ __align__(16) uint8_t nms_smem[];
     __shared__ uint32_t s_warp_tot[32];
     __shared__ uint32_t s_base;
-    __shared__ int s_nlarge, s_qhead, s_gq[8];
+    __shared__ int s_nlarge, s_qhead, s_gq[8], s_nk[8], s_kidx[8][32];
     __shared__ int s_large[2 * kMaxLargeSeg];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -354,6 +382,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     for (int i = tid; i < nwords; i += kNmsThreads) removed[i] = 0u;
     __syncthreads();
 
+    ZL_NMS_STAMP(0);
     // ---- bitonic sort, ascending.  Comparator strides >= 32 go through memory with a block barrier per step; the five
     // innermost strides (16..1) of every merge stay inside aligned 32-key groups, so a warp runs them in registers with
     // shuffles (no memory traffic, no barrier): 21 block barriers instead of 66 for 2048 keys.
@@ -403,6 +432,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     }
     const uint64_t* K = in_smem ? skeys : gkeys;
 
+    ZL_NMS_STAMP(1);
     // ---- gather boxes into sorted order: shared memory when they fit (the greedy sweep below is a chain of
     // dependent box reads, so its latency is the box read latency), else the global scratch
     float4* sb = (n <= box_cap_smem)
@@ -411,6 +441,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     for (int i = tid; i < n; i += kNmsThreads) sb[i] = box_by_anchor[(size_t)f * A + key_anchor(K[i])];
     __syncthreads();
 
+    ZL_NMS_STAMP(2);
     // ---- greedy per-class suppression (applyNMS, onnx_engine.cpp:856-875), exact, in two phases.
     // A class segment is a run of equal class ids in the sorted list.  The reference's loop is a serial chain over the
     // KEPT candidates of a segment; each link tests the still-alive later candidates, which is the parallel part.
@@ -447,15 +478,57 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
                 float4 bt;
                 bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
                 bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
-                const bool sup = ((cur >> lane) & 1u) && iou_ref(bt, bi) > iou_thr;     // strict '>' (onnx_engine.cpp:871)
+                const bool sup = ((cur >> lane) & 1u) && iou_gt(bt, bi, iou_thr);     // strict '>' (onnx_engine.cpp:871)
                 cur &= ~__ballot_sync(0xffffffffu, sup);
             }
             if (valid && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
         }
         __syncthreads();
+        ZL_NMS_STAMP(3);
         const int nlarge = min(s_nlarge, kMaxLargeSeg);
         const bool overflow = s_nlarge > kMaxLargeSeg;                      // more large segments than queue slots: handled below
         const int grp = warp >> 2, gtid = tid & 127;                        // 8 groups of 128 threads
+        // Very large segments (one class holding hundreds of candidates) first, one at a time, with the WHOLE CTA sweeping:
+        // a 128-thread group would leave the other seven idle behind it.
+        for (int q = 0; q < nlarge; ++q) {
+            const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
+            if (e0 - s0 <= kWholeCtaSeg) continue;
+            for (int b0 = s0; b0 < e0; b0 += 32) {
+                if (warp == 0) {
+                    const int i = b0 + lane;
+                    const bool valid = i < e0;
+                    const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool alive = valid && (((removed[i >> 5] >> (i & 31)) & 1u) == 0u);
+                    uint32_t cur = __ballot_sync(0xffffffffu, alive);
+                    uint32_t kept = 0u;
+                    while (cur != 0u) {
+                        const int t = __ffs(cur) - 1;
+                        kept |= 1u << t;
+                        cur &= ~(1u << t);
+                        float4 bt;
+                        bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
+                        bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
+                        const bool sup = ((cur >> lane) & 1u) && iou_gt(bt, bi, iou_thr);
+                        cur &= ~__ballot_sync(0xffffffffu, sup);
+                    }
+                    if (alive && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
+                    if ((kept >> lane) & 1u) s_kidx[0][__popc(kept & ((1u << lane) - 1u))] = i;
+                    if (lane == 0) s_nk[0] = __popc(kept);
+                }
+                __syncthreads();
+                const int nk = s_nk[0];
+                if (nk > 0) {
+                    for (int j = b0 + 32 + tid; j < e0; j += kNmsThreads) {
+                        if (((removed[j >> 5] >> (j & 31)) & 1u) != 0u) continue;
+                        const float4 bj = sb[j];
+                        for (int t = 0; t < nk; ++t) {
+                            if (iou_gt(sb[s_kidx[0][t]], bj, iou_thr)) { atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31)); break; }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
         for (;;) {
             int q = 0;
             if (gtid == 0) q = atomicAdd(&s_qhead, 1);
@@ -466,26 +539,47 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
             asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
             if (q >= nlarge) break;
             const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
-            int i = s0;
-            while (i < e0) {
-                const float4 bi = sb[i];
-                for (int j = i + 1 + gtid; j < e0; j += 128) {
-                    if (((removed[j >> 5] >> (j & 31)) & 1u) == 0u && iou_ref(bi, sb[j]) > iou_thr)
-                        atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31));
+            if (e0 - s0 > kWholeCtaSeg) continue;                          // done above by the whole CTA
+            // Blocked greedy sweep, exact: the segment is walked in blocks of 32 candidates.  By the time a block is reached
+            // every candidate in it has been tested against the kept boxes of ALL earlier blocks, so (a) the group's first
+            // warp resolves the block internally with boxes in registers (one shuffle + one IoU per link, like phase 1) and
+            // (b) all 128 threads then test the later candidates against the block's kept boxes in parallel.  The serial
+            // chain costs ~100 cycles per kept box instead of two named barriers (~800 cycles): the round-2 profile had this
+            // loop at 220 us on frames with a 800-candidate class.
+            for (int b0 = s0; b0 < e0; b0 += 32) {
+                if ((gtid >> 5) == 0) {
+                    const int i = b0 + lane;
+                    const bool valid = i < e0;
+                    const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const bool alive = valid && (((removed[i >> 5] >> (i & 31)) & 1u) == 0u);
+                    uint32_t cur = __ballot_sync(0xffffffffu, alive);            // alive, not yet decided
+                    uint32_t kept = 0u;
+                    while (cur != 0u) {
+                        const int t = __ffs(cur) - 1;
+                        kept |= 1u << t;
+                        cur &= ~(1u << t);
+                        float4 bt;
+                        bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
+                        bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
+                        const bool sup = ((cur >> lane) & 1u) && iou_gt(bt, bi, iou_thr);     // strict '>' (onnx_engine.cpp:871)
+                        cur &= ~__ballot_sync(0xffffffffu, sup);
+                    }
+                    if (alive && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
+                    if ((kept >> lane) & 1u) s_kidx[grp][__popc(kept & ((1u << lane) - 1u))] = i;
+                    if (lane == 0) s_nk[grp] = __popc(kept);
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-                // next candidate that survived everything before it (uniform across the group)
-                ++i;
-                while (i < e0) {
-                    const uint32_t wv = removed[i >> 5] >> (i & 31);
-                    const uint32_t alive = ~wv;
-                    if (alive == 0u) { i = (i | 31) + 1; continue; }
-                    const int skip = __ffs(alive) - 1;
-                    if ((i & 31) + skip > 31) { i = (i | 31) + 1; continue; }
-                    i += skip;
-                    break;
+                const int nk = s_nk[grp];
+                if (nk > 0) {
+                    for (int j = b0 + 32 + gtid; j < e0; j += 128) {
+                        if (((removed[j >> 5] >> (j & 31)) & 1u) != 0u) continue;
+                        const float4 bj = sb[j];
+                        for (int t = 0; t < nk; ++t) {
+                            if (iou_gt(sb[s_kidx[grp][t]], bj, iou_thr)) { atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31)); break; }
+                        }
+                    }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");   // everyone has read the flags before the next sweep writes
+                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");       // flags and s_kidx settled before the next block
             }
         }
         if (overflow) {
@@ -509,7 +603,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
                     for (int j0 = (i + 1) & ~31; j0 < end; j0 += 32) {
                         const int j = j0 + lane;
                         bool sup = false;
-                        if (j > i && j < end && !((removed[j >> 5] >> (j & 31)) & 1u)) sup = iou_ref(bi, sb[j]) > iou_thr;
+                        if (j > i && j < end && !((removed[j >> 5] >> (j & 31)) & 1u)) sup = iou_gt(bi, sb[j], iou_thr);
                         const unsigned bal = __ballot_sync(0xffffffffu, sup);
                         if (bal != 0u && lane == 0) atomicOr(const_cast<uint32_t*>(&removed[j0 >> 5]), bal);
                     }
@@ -520,6 +614,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     }
     __syncthreads();
 
+    ZL_NMS_STAMP(4);
     // ---- ordered compaction of survivors
     uint32_t kept_total = 0;
     for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
@@ -562,6 +657,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
         running += tot;
         __syncthreads();
     }
+    ZL_NMS_STAMP(5);
 }
 
 int g_nms_smem_keys = 0;   // key capacity (elements) of the smem sort buffer
@@ -690,6 +786,16 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
     nms_kernel<<<n, kNmsThreads, smem, st>>>(A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, pb.box_by_anchor, pb.sorted_box, pb.cand_count,
                                             pb.header, pb.dets, pb.maxn, pb.cap);
     ZL_CUDA(cudaGetLastError());
+    static const char* dbg = getenv("ZL_NMS_DEBUG");
+    if (dbg) {
+        long long h[8] = {0};
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_nms_dbg, sizeof(h));
+        fprintf(stderr, "nms frame %d phases (cycles): sort %lld gather %lld small-seg %lld large-seg %lld compact %lld\n", atoi(dbg), h[1] - h[0], h[2] - h[1], h[3] - h[2],
+                h[4] - h[3], h[5] - h[4]);
+        const int fr = atoi(dbg);
+        cudaMemcpyToSymbol(g_nms_dbg_frame, &fr, sizeof(int));
+    }
     return ZL_OK;
 }
 

@@ -13,6 +13,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "lib", "libzl_b200.so")
+TEST_LIB_PATH = os.path.join(_PKG, "lib", "libzl_b200_test.so")     # engine objects + unit-test / measurement hooks (include/zl_b200_test.h)
 
 OK, INVALID_ARGUMENT, NOT_INITIALIZED = 0, 2, 3
 INFERENCE_ERROR, MODEL_NOT_FOUND, MODEL_LOAD_FAILED, INVALID_INPUT = 200, 201, 202, 203
@@ -58,8 +59,9 @@ EXPORTS = [
     "zl_engine_set_wire_callback", "zl_infer_batch_wire", "zl_engine_queue_size", "zl_engine_drain", "zl_engine_get_stats", "zl_infer_batch", "zl_preprocess",
     "zl_forward_raw", "zl_decode_nms", "zl_engine_num_anchors", "zl_engine_upload_resident",
     "zl_engine_run_resident", "zl_engine_profile", "zl_engine_profile_stalls", "zl_bench_e2e", "zl_bench_h2d", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
-    "zl_test_conv", "zl_probe_umma", "zl_probe_tma", "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
+    "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
+TEST_EXPORTS = ["zl_test_conv", "zl_probe_umma", "zl_probe_tma"]     # libzl_b200_test.so only
 
 
 class ZlError(RuntimeError):
@@ -110,9 +112,6 @@ def lib():
             "zl_bench_latency": (i32, [vp, vp, i32, i32, i32, i32, vp]),
             "zl_bench_preprocess": (i32, [vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(C.c_double)]),
             "zl_bench_decode_nms": (i32, [vp, vp, i32, i32, i32, f32, f32, i32, C.POINTER(f32), C.POINTER(f32), C.POINTER(C.c_int64)]),
-            "zl_test_conv": (i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
-            "zl_probe_umma": (i32, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-            "zl_probe_tma": (i32, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, u32, vp, u32, C.POINTER(i32)]),
             "zl_model_probe": (i32, [vp, sz, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(u64)]),
             "zl_host_alloc": (vp, [sz]),
             "zl_host_free": (None, [vp]),
@@ -125,6 +124,30 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+_testlib = None
+
+
+def testlib():
+    """The test library: the same engine objects plus the unit-test hooks the product library does not export."""
+    global _testlib
+    if _testlib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise ZlError(SYSTEM_ERROR, f"{TEST_LIB_PATH} not built — run __graft_entry__.build()")
+        L = C.CDLL(TEST_LIB_PATH)
+        vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
+        L.zl_test_conv.restype, L.zl_test_conv.argtypes = i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.zl_probe_umma.restype, L.zl_probe_umma.argtypes = i32, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.zl_probe_tma.restype, L.zl_probe_tma.argtypes = i32, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, u32, vp, u32, C.POINTER(i32)]
+        L.zl_last_error.restype, L.zl_last_error.argtypes = C.c_char_p, []
+        _testlib = L
+    return _testlib
+
+
+def _check_t(rc):
+    if rc != OK:
+        raise ZlError(rc, (testlib().zl_last_error() or b"").decode(errors="replace"))
 
 
 def _check(rc):
@@ -357,14 +380,14 @@ def test_conv(x_nhwc, w_ohwi, bias, stride=1, act=True, res=None, impl=0, device
     y = np.zeros((n, ho, wo, cout), np.float32)
     r = np.ascontiguousarray(res, np.float32) if res is not None else None
     flags = (1 if act else 0) | (2 if out_f32 else 0) | (4 if fp16 else 0) | (ntile_hint << 8)
-    _check(lib().zl_test_conv(device, impl, _ptr(x), n, h, wd, cin, _ptr(w), _ptr(b), cout, k, stride, flags,
+    _check_t(testlib().zl_test_conv(device, impl, _ptr(x), n, h, wd, cin, _ptr(w), _ptr(b), cout, k, stride, flags,
                               _ptr(r) if r is not None else None, _ptr(y)))
     return y
 
 
 def probe_umma(N, swz=128, sbo=None, nacc=1, count=512, shift_rows=0, ksteps=4, grid=1, device=0):
     a, b = C.c_int64(), C.c_int64()
-    _check(lib().zl_probe_umma(device, N, swz, sbo if sbo is not None else 8 * swz, nacc, count, shift_rows, ksteps, grid, C.byref(a), C.byref(b)))
+    _check_t(testlib().zl_probe_umma(device, N, swz, sbo if sbo is not None else 8 * swz, nacc, count, shift_rows, ksteps, grid, C.byref(a), C.byref(b)))
     return a.value / count, b.value / count
 
 
@@ -374,7 +397,7 @@ def probe_tma(x_f16, box, estride, swizzle, coords, expect_bytes, dump_bytes, de
     n, h, w, c = x.shape
     dump = np.zeros(dump_bytes, np.uint8)
     done = C.c_int32()
-    _check(lib().zl_probe_tma(device, _ptr(x), n, h, w, c, box[0], box[1], box[2], estride, swizzle,
+    _check_t(testlib().zl_probe_tma(device, _ptr(x), n, h, w, c, box[0], box[1], box[2], estride, swizzle,
                               coords[0], coords[1], coords[2], coords[3], expect_bytes, _ptr(dump), dump_bytes, C.byref(done)))
     return done.value, dump.view(np.float16)
 
