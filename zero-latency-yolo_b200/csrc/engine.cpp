@@ -89,6 +89,7 @@ int32_t Engine::init()
     if (const char* ev = getenv("ZL_DISABLE_HALO")) use_halo = !(ev[0] == '1');
     if (const char* ev = getenv("ZL_FUSE_PRE")) fuse_pre = (ev[0] == '1');
     if (const char* ev = getenv("ZL_DISABLE_STEM")) use_stem = !(ev[0] == '1');
+    if (const char* ev = getenv("ZL_FUSE_STEMS")) fuse_stems = (ev[0] == '1');
     if (cfg.preprocess_mode == ZL_PRE_LETTERBOX) fuse_pre = false;     // the fused A/B kernel only knows the parity sampling
     persist_min_units = 0;      // measured: the persistent kernel wins even for b=1 (p50 0.77 -> 0.44 ms), so it always runs when it can
     if (const char* ev = getenv("ZL_PERSIST_MIN_UNITS")) persist_min_units = atoi(ev);
@@ -279,6 +280,28 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
         new_by_name[s.name] = cw.get();
         new_convs.push_back(std::move(cw));
     }
+    // fused Detect stems (16-bit modes): rows of cv2.l.0 followed by rows of cv3.l.0, one [cb + cc][9 * cin] tensor
+    if (bf16 && md.cb + md.cc <= 256) {
+        for (int l = 0; l < 3; ++l) {
+            const std::string sl = std::to_string(l);
+            const ConvWeights* a = new_by_name["model.22.cv2." + sl + ".0.conv"];
+            const ConvWeights* b = new_by_name["model.22.cv3." + sl + ".0.conv"];
+            if (!a || !b || !a->w_tc || !b->w_tc || a->ktot != b->ktot) continue;
+            std::unique_ptr<ConvWeights> cw(new ConvWeights());
+            cw->name = "model.22.stem." + sl; cw->cin = a->cin; cw->cout = a->cout + b->cout; cw->k = 3; cw->stride = 1; cw->act = 1;
+            cw->cout_pad = round_up(cw->cout, 16); cw->ktot = a->ktot;
+            ZL_CUDA(cudaMalloc(&cw->w_tc, (size_t)cw->cout_pad * cw->ktot * 2));
+            ZL_CUDA(cudaMemset(cw->w_tc, 0, (size_t)cw->cout_pad * cw->ktot * 2));
+            ZL_CUDA(cudaMemcpy(cw->w_tc, a->w_tc, (size_t)a->cout * a->ktot * 2, cudaMemcpyDeviceToDevice));
+            ZL_CUDA(cudaMemcpy(reinterpret_cast<char*>(cw->w_tc) + (size_t)a->cout * a->ktot * 2, b->w_tc, (size_t)b->cout * b->ktot * 2, cudaMemcpyDeviceToDevice));
+            ZL_CUDA(cudaMalloc(&cw->bias, (size_t)cw->cout_pad * 4));
+            ZL_CUDA(cudaMemset(cw->bias, 0, (size_t)cw->cout_pad * 4));
+            ZL_CUDA(cudaMemcpy(cw->bias, a->bias, (size_t)a->cout * 4, cudaMemcpyDeviceToDevice));
+            ZL_CUDA(cudaMemcpy(cw->bias + a->cout, b->bias, (size_t)b->cout * 4, cudaMemcpyDeviceToDevice));
+            new_by_name[cw->name] = cw.get();
+            new_convs.push_back(std::move(cw));
+        }
+    }
     ZL_CUDA(cudaDeviceSynchronize());           // uploads done: the set is complete
     pending_convs.swap(new_convs);              // a previously prepared, never committed set is dropped here
     pending_by_name.swap(new_by_name);
@@ -327,8 +350,10 @@ int32_t Engine::alloc_lane(Lane& L)
     for (int l = 0; l < 3; ++l) {
         const int hh = H / (8 << l), ww = W / (8 << l);
         const std::string s = std::to_string(l);
-        add("HB1_" + s, hh, ww, md.cb, adt); add("HB2_" + s, hh, ww, md.cb, adt); add("BOX_" + s, hh, ww, 64, DT_F32);
-        add("HC1_" + s, hh, ww, md.cc, adt); add("HC2_" + s, hh, ww, md.cc, adt); add("CLS_" + s, hh, ww, ncp, DT_F32);
+        // HBC1 = [ cv2.l.0 output (cb) | cv3.l.0 output (cc) ]: the two Detect stems read the same map, so in the 16-bit modes
+        // they run as ONE conv of width cb + cc (one wide MMA costs far less than two narrow ones: umma_probe)
+        add("HBC1_" + s, hh, ww, md.cb + md.cc, adt); add("HB2_" + s, hh, ww, md.cb, adt); add("BOX_" + s, hh, ww, 64, DT_F32);
+        add("HC2_" + s, hh, ww, md.cc, adt); add("CLS_" + s, hh, ww, ncp, DT_F32);
     }
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t total = 0;
@@ -528,14 +553,17 @@ int32_t Engine::build_ops(Lane& L, int B)
     const char* outs[3] = {"O3", "O4", "O5"};
     for (int l = 0; l < 3; ++l) {
         const std::string s = std::to_string(l), b = "model.22.cv2." + s;
-        conv(b + ".0.conv", buf(outs[l]), buf("HB1_" + s), nullptr);
-        conv(b + ".1.conv", buf("HB1_" + s), buf("HB2_" + s), nullptr);
+        const bool fused = bf16 && fuse_stems && conv_by_name.count("model.22.stem." + s) != 0;
+        if (fused) conv("model.22.stem." + s, buf(outs[l]), buf("HBC1_" + s), nullptr);
+        else conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(0, md.cb), nullptr);
+        conv(b + ".1.conv", buf("HBC1_" + s).slice(0, md.cb), buf("HB2_" + s), nullptr);
         conv(b + ".2", buf("HB2_" + s), buf("BOX_" + s), nullptr);
     }
     for (int l = 0; l < 3; ++l) {
         const std::string s = std::to_string(l), b = "model.22.cv3." + s;
-        conv(b + ".0.conv", buf(outs[l]), buf("HC1_" + s), nullptr);
-        conv(b + ".1.conv", buf("HC1_" + s), buf("HC2_" + s), nullptr);
+        const bool fused = bf16 && fuse_stems && conv_by_name.count("model.22.stem." + s) != 0;
+        if (!fused) conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(md.cb, md.cc), nullptr);
+        conv(b + ".1.conv", buf("HBC1_" + s).slice(md.cb, md.cc), buf("HC2_" + s), nullptr);
         View cls = buf("CLS_" + s); cls.c = md.nc;
         conv(b + ".2", buf("HC2_" + s), cls, nullptr);
     }

@@ -125,6 +125,7 @@ public:
     bool use_halo = true;
     int persist_min_units = 0;     // a layer goes to the persistent kernel when it has at least this many (tile, N-slice) work units ...
     bool deep_k_persist = false;   // ... or (experiment) when its K loop is deep
+    bool fuse_stems = true;    // Detect stems cv2.l.0 + cv3.l.0 as one conv of width cb + cc (16-bit modes)
     bool use_stem = true;      // layer 0 on tensor cores (2x2 conv over the space-to-depth image the preprocess kernel writes)
     bool fuse_pre = false;     // P1 fused into layer 0 (bit-identical, measured slower than the two-kernel path: scattered byte loads)
     bool weights_loaded = false;
