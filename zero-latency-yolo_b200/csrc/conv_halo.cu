@@ -740,14 +740,18 @@ static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int
     base.pw = s2 ? kTW + 1 : (w.k == 3 ? kTW + 2 : kTW);
     base.prow_extra = s2 ? 1 : (w.k == 3 ? 2 : 0);
     base.npatch = s2 ? 4 : 1;
-    base.sub = halo_sub(w, base.yv.h);
-    base.tiles = ceil_div(base.yv.w, kTW) * ceil_div(base.yv.h, kTH * base.sub) * base.yv.n;
+    const int sub_default = halo_sub(w, base.yv.h);
+    static const int sub_search = [] { const char* e = getenv("ZL_SUB_SEARCH"); return e ? atoi(e) : 0; }();   // 1 = let the cost model pick sub too (measured: no gain, so the rule stays "by Cout only")
     const uint32_t budget = 227u * 1024u;
     const uint32_t fixed0 = 3072u + (uint32_t)kEpiWarps * (y.dtype == DT_F32 ? 4096u : 2048u);
     static const int force_stream = [] { const char* e = getenv("ZL_WSTREAM"); return e ? atoi(e) : -1; }();   // A/B: 0 never, 1 whenever possible
     bool found = false;
-    for (int kc : {conv_kc(w, y.dtype == DT_F32)}) {        // fixed per layer: the accumulation order must not depend on the plan
+    const int kc = conv_kc(w, y.dtype == DT_F32);              // fixed per layer: the accumulation order must not depend on the plan
+    for (int sub : {1, 2, 4}) {                              // sub-tiles per tile: the per-tile overheads against shared memory and TMEM
+        if (sub_search ? (sub > 1 && kTH * sub > round_up(base.yv.h, kTH)) : sub != sub_default) continue;
         PersistPlan pl = base;
+        pl.sub = sub;
+        pl.tiles = ceil_div(base.yv.w, kTW) * ceil_div(base.yv.h, kTH * sub) * base.yv.n;
         pl.kc = kc;
         pl.cchunks = w.cin / kc;
         pl.patch_bytes = (uint32_t)pl.pw * (kTH * pl.sub + pl.prow_extra) * kc * 2;      // one (sub-)patch
@@ -786,12 +790,12 @@ static bool persist_plan(const ConvWeights& w, const View& x, const View& y, int
                     const double units = (double)pl.tiles * nsplit;
                     const int ctas = units < num_sms ? (int)units : (num_sms / nsplit) * nsplit;
                     const double waves = std::ceil(units / std::max(ctas, 1));
-                    const double mma = (double)pl.sub * pl.taps * (w.cin / 16) * mma_cycles(nt) + 250.0 * nst;
+                    const double mma = (double)pl.sub * pl.taps * (w.cin / 16) * mma_cycles(nt) + 250.0 * nst + 600.0;   // + per-tile hand-over (accumulator wait, commits)
                     const double stage_bytes = (double)(pl.patch_bytes * pl.npatch + (mode ? pl.wchunk_bytes : 0u)) * cps;
                     const int np = std::min(kProducers, stages);
                     const double stage_cyc = std::max(stage_bytes / 48.0, (500.0 + 130.0 * cps * (pl.npatch + mode)) / np);
                     const double load = nst * stage_cyc;
-                    const double epi = 350.0 + 90.0 * pl.sub * (nt / 16) / 4.0;             // per-tile epilogue floor of one warp quarter group
+                    const double epi = 500.0 + 250.0 * pl.sub * (nt / 16) / 4.0;            // per-tile epilogue: ~1000 cycles per item and warp, 8 warps per tile
                     const double fill = stage_cyc * 0.5;                                      // the first stage of a CTA is exposed
                     const double prologue = mode ? 1500.0 : 1500.0 + (double)pl.cchunks * pl.wchunk_bytes / 48.0;
                     pl.cost = prologue + fill + waves * std::max(std::max(mma, load), epi);
