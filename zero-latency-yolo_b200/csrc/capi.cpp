@@ -1,6 +1,7 @@
 // capi.cpp — the extern "C" surface declared in include/zl_b200.h.
 // No exception may cross this boundary (the reference wraps every engine call in
 // try/catch and returns Result::error, onnx_engine.cpp:165-169,621-645).
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_fp16.h>
@@ -341,7 +342,10 @@ int32_t zl_model_probe(const void* blob, size_t len, int32_t* scale, int32_t* nu
 void* zl_host_alloc(size_t bytes)
 {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); zl::set_error("cudaHostAlloc failed"); return nullptr; }
+    // Frame staging memory is written by the CPU and read only by the copy engine.  ZL_PINNED_WC=1 makes it write-combined
+    // (no cache snooping on the DMA reads) — an A/B switch for hosts whose pinned-copy bandwidth, not the GPU, bounds e2e.
+    static const bool wc = [] { const char* e = getenv("ZL_PINNED_WC"); return e && e[0] == '1'; }();
+    if (cudaHostAlloc(&p, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); zl::set_error("cudaHostAlloc failed"); return nullptr; }
     zl::register_pinned_range(p, bytes);
     return p;
 }

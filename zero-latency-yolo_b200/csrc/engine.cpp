@@ -1223,7 +1223,8 @@ int32_t Engine::bench_h2d(size_t bytes, int iters, double* gbs)
     if (bytes == 0 || iters < 1 || !gbs) ZL_FAIL(ZL_INVALID_ARGUMENT, "bad argument");
     ZL_CUDA(cudaSetDevice(cfg.device));
     void* h = nullptr; void* d = nullptr;
-    ZL_CUDA(cudaHostAlloc(&h, bytes, cudaHostAllocDefault));
+    static const bool wc = [] { const char* e = getenv("ZL_PINNED_WC"); return e && e[0] == '1'; }();
+    ZL_CUDA(cudaHostAlloc(&h, bytes, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
     if (cudaMalloc(&d, bytes) != cudaSuccess) { cudaFreeHost(h); ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "bench_h2d: out of device memory"); }
     std::memset(h, 1, bytes);
     Lane& L = *lanes[0];
