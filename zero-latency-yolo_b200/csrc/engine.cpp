@@ -585,7 +585,7 @@ int32_t Engine::launch_op(Lane& L, int B, const Op& op)
     const bool f16 = cfg.precision == ZL_PRECISION_FP16;
     switch (op.kind) {
         case Op::PRE:
-            if (op.y.c == 16) return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, f16 ? PRE_S2D16_F16 : PRE_S2D16_BF16, op.y.ptr, cfg.preprocess_mode == ZL_PRE_LETTERBOX);
+            if (op.y.c == 16) return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, f16 ? PRE_S2D16_F16 : PRE_S2D16_BF16, op.y.ptr, cfg.preprocess_mode == ZL_PRE_LETTERBOX, L.same_size);
             return launch_preprocess(st, L.staging, L.d_descs, B, cfg.model_w, cfg.model_h, bf16 ? (f16 ? PRE_NHWC4_F16 : PRE_NHWC4_BF16) : PRE_NHWC4_F32, op.y.ptr, cfg.preprocess_mode == ZL_PRE_LETTERBOX);
         case Op::CONV_TC: return conv_tc_launch(st, op.tc);
         case Op::CONV_HALO: return conv_halo_launch(st, op.halo, num_sms);
@@ -639,9 +639,12 @@ int Engine::graph_batch_for(int n) const
     return std::min(b, cfg.max_batch);
 }
 
+// One graph per (batch size, "every frame already has the model's size"): the second half picks the preprocess kernel.
+static inline int graph_key(int B, bool same_size) { return B | (same_size ? 1 << 20 : 0); }
+
 int32_t Engine::ensure_graph(Lane& L, int B)
 {
-    if (L.graphs.count(B)) return ZL_OK;
+    if (L.graphs.count(graph_key(B, L.same_size))) return ZL_OK;
     // one un-captured pass first: lazy module load, cudaFuncSetAttribute and op building stay out of the capture
     ZL_TRY(run_ops(L, B, true));
     ZL_CUDA(cudaStreamSynchronize(L.stream));
@@ -655,7 +658,7 @@ int32_t Engine::ensure_graph(Lane& L, int B)
     ce = cudaGraphInstantiate(&ge, g, 0);
     cudaGraphDestroy(g);
     if (ce != cudaSuccess) ZL_FAIL(ZL_INFERENCE_ERROR, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
-    L.graphs[B] = ge;
+    L.graphs[graph_key(B, L.same_size)] = ge;
     { std::lock_guard<std::mutex> g2(smu); graph_captured++; }
     return ZL_OK;
 }
@@ -665,7 +668,7 @@ int32_t Engine::launch_batch(Lane& L, int B, bool want_raw)
     if (want_raw) return run_ops(L, B, true, true);
     if (cfg.use_graph) {
         ZL_TRY(ensure_graph(L, B));
-        ZL_CUDA(cudaGraphLaunch(L.graphs[B], L.stream));
+        ZL_CUDA(cudaGraphLaunch(L.graphs[graph_key(B, L.same_size)], L.stream));
         return ZL_OK;
     }
     return run_ops(L, B, true);
@@ -682,11 +685,14 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
     // Frames that sit back to back in pinned host memory and fill their slots exactly (the bench's batches, the async
     // path's slot ring when consecutive) go up in ONE copy; anything else is one copy per frame.
     bool one_copy = frames_pinned && n > 1;
+    bool same = true;
     for (int i = 0; i < n; ++i) {
         const size_t bytes = (size_t)ws[i] * hs[i] * 3;
         if (ws[i] <= 0 || hs[i] <= 0 || bytes > slot) ZL_FAIL(ZL_INVALID_INPUT, "frame larger than max_frame_w x max_frame_h");
         if (bytes != slot || (i > 0 && frames[i] != frames[i - 1] + slot)) one_copy = false;
+        if (ws[i] != cfg.model_w || hs[i] != cfg.model_h) same = false;
     }
+    L.same_size = same && (slot % 8) == 0;          // frames start at multiples of the slot size: the fast kernel's 8-byte loads stay aligned
     if (one_copy) ZL_CUDA(cudaMemcpyAsync(L.staging, frames[0], (size_t)n * slot, cudaMemcpyHostToDevice, L.stream));
     for (int i = 0; i < n; ++i) {
         const size_t bytes = (size_t)ws[i] * hs[i] * 3;
@@ -1003,6 +1009,9 @@ int32_t Engine::upload_resident(int set, const uint8_t* const* frames, const int
         }
         ZL_CUDA(cudaMemcpy(L.d_res_descs + (size_t)set * cfg.max_batch, hd, sizeof(FrameDesc) * n, cudaMemcpyHostToDevice));
         L.resident_n[set] = n;
+        bool same = (slot % 8) == 0;
+        for (int i = 0; i < n; ++i) same = same && ws[i] == cfg.model_w && hs[i] == cfg.model_h;
+        L.resident_same[set] = same;
     }
     return ZL_OK;
 }
@@ -1021,6 +1030,9 @@ int32_t Engine::run_resident(int n_sets, int steps, float* total_ms, int64_t* la
     const int B = graph_batch_for(n);
     if (B != n) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident batch must be a power of two or max_batch");
     const int nl = (int)lanes.size();
+    bool rsame = true;
+    for (int s = 0; s < n_sets; ++s) rsame = rsame && L0.resident_same[s];
+    for (auto& Lp : lanes) Lp->same_size = rsame;
     if (cfg.use_graph) for (auto& Lp : lanes) ZL_TRY(ensure_graph(*Lp, B));
     ZL_CUDA(cudaDeviceSynchronize());
     ZL_CUDA(cudaEventRecord(L0.ev0, L0.stream));
@@ -1052,6 +1064,7 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
     std::lock_guard<std::mutex> g(L.mu);
     const int n = L.resident_n[set];
     if (n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident set not uploaded");
+    L.same_size = L.resident_same[set];
     const int B = graph_batch_for(n);
     if (!L.ops.count(B)) ZL_TRY(build_ops(L, B));
     ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)set * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
@@ -1100,6 +1113,7 @@ int32_t Engine::profile_stalls(int set, uint64_t* out, int cap_ops, int32_t* n_o
     std::lock_guard<std::mutex> g(L.mu);
     const int n = L.resident_n[set];
     if (n == 0) ZL_FAIL(ZL_INVALID_ARGUMENT, "resident set not uploaded");
+    L.same_size = L.resident_same[set];
     const int B = graph_batch_for(n);
     if (!L.ops.count(B)) ZL_TRY(build_ops(L, B));
     std::vector<Op> ops;

@@ -78,6 +78,8 @@ struct Lane {
     std::map<int, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int resident_n[4] = {0, 0, 0, 0};
+    bool resident_same[4] = {false, false, false, false};
+    bool same_size = false;                     // the batch being launched: every frame already has the model's size (fast preprocess kernel)
 };
 
 class Engine {

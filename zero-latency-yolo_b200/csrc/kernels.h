@@ -37,7 +37,7 @@ enum PreLayout : int32_t {
     PRE_S2D16_F16 = 5
 };
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
-                          int32_t mw, int32_t mh, int32_t layout, void* out, int32_t letterbox = 0);
+                          int32_t mw, int32_t mh, int32_t layout, void* out, int32_t letterbox = 0, int32_t same_size = 0);   // same_size: every frame is mw x mh (host-checked)
 // ZL_PRE_LETTERBOX: the kept boxes of a batch mapped back from the letterboxed model frame to the request frame.
 int32_t launch_letterbox_unmap(cudaStream_t st, int32_t n, int32_t maxn, const uint32_t* header, DevDet* dets, const FrameDesc* descs,
                                int32_t mw, int32_t mh, uint32_t cap);

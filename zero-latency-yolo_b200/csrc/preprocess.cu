@@ -159,6 +159,72 @@ preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __re
     o[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// Fast path of the space-to-depth variant for frames that already have the model's size (the reference's default client
+// sends 416x416 to a 416x416 model; the throughput configs send 640x640): no resampling, so a thread takes FOUR 2x2 blocks
+// of one block row = 24 contiguous bytes from each of two frame rows (three 8-byte loads per row instead of 24 single-byte
+// loads) and turns bytes into 16-bit values through a 256-entry table of the correctly rounded value/255.0f (built with
+// __fdiv_rn, so the result is bit-identical to the general kernel's).  One thread = 128 contiguous output bytes.
+template <bool F16>
+__global__ void __launch_bounds__(256)
+preprocess_s2d_same_size_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs, int mw, int mh, uint4* __restrict__ out)
+{
+    __shared__ uint16_t lut[256];
+    {
+        const float q = __fdiv_rn((float)threadIdx.x, 255.0f);
+        lut[threadIdx.x] = pack1_16(q, F16);
+    }
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int W2 = mw >> 1, H2 = mh >> 1, WQ = W2 >> 2;                // WQ groups of four blocks per block row
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= WQ * H2) return;
+    const FrameDesc d = descs[f];
+    const int Y = item / WQ, XQ = item - Y * WQ;
+    const uint8_t* __restrict__ img = staging + d.offset;
+    uint32_t b[2][6];                                                   // two rows x 24 bytes
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const uint2* rp = reinterpret_cast<const uint2*>(img + ((size_t)(2 * Y + dy) * mw + (size_t)XQ * 8) * 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const uint2 t = __ldg(rp + k); b[dy][2 * k] = t.x; b[dy][2 * k + 1] = t.y; }
+    }
+    auto byte_at = [&](int dy, int i) -> uint32_t { return (b[dy][i >> 2] >> ((i & 3) * 8)) & 0xffu; };
+    // A thread owns 128 contiguous output bytes; stored directly, a warp-wide 16-byte store would touch 32 different
+    // 128-byte lines.  The eight 16-byte chunks go through shared memory (XOR-swizzled: conflict-free both ways) so that
+    // every store instruction of a warp writes 512 contiguous bytes.
+    __shared__ uint4 tr[8][32 * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint4* tw = tr[warp];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                                       // block j of the four: pixels 2j, 2j+1 of both rows
+        uint32_t v[12];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int px = (2 * j + dx) * 3;                         // BGR in the frame, RGB out (channel c reads byte 2 - c)
+                v[(dy * 2 + dx) * 3 + 0] = lut[byte_at(dy, px + 2)];
+                v[(dy * 2 + dx) * 3 + 1] = lut[byte_at(dy, px + 1)];
+                v[(dy * 2 + dx) * 3 + 2] = lut[byte_at(dy, px + 0)];
+            }
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = v[2 * i] | (v[2 * i + 1] << 16);
+        w[6] = 0u; w[7] = 0u;
+        tw[lane * 8 + ((2 * j) ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+        tw[lane * 8 + ((2 * j + 1) ^ (lane & 7))] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    __syncwarp();
+    // items of a warp are consecutive (the grid is sized so that whole warps are in range or out), so its 4 KB are contiguous
+    const int item0 = item - lane;
+    uint4* o = out + ((size_t)f * H2 * W2 + (size_t)item0 * 4) * 2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = k * 32 + lane, t = c >> 3, j = c & 7;              // chunk c of the warp belongs to thread t, its j-th chunk
+        o[c] = tw[t * 8 + (j ^ (t & 7))];
+    }
+}
+
 // The kept boxes of a letterboxed batch, mapped back to the request frame: the filter normalised model-pixel boxes by the
 // frame's width / height like the reference does; undo that, remove the padding and the gain, normalise again.
 __global__ void letterbox_unmap_kernel(int n, int maxn, const uint32_t* __restrict__ header, DevDet* __restrict__ dets,
@@ -192,11 +258,18 @@ int32_t launch_letterbox_unmap(cudaStream_t st, int32_t n, int32_t maxn, const u
 }
 
 int32_t launch_preprocess(cudaStream_t st, const uint8_t* staging, const FrameDesc* descs, int32_t n,
-                          int32_t mw, int32_t mh, int32_t layout, void* out, int32_t letterbox)
+                          int32_t mw, int32_t mh, int32_t layout, void* out, int32_t letterbox, int32_t same_size)
 {
     if (n <= 0) return ZL_OK;
     if (layout == PRE_S2D16_BF16 || layout == PRE_S2D16_F16) {
         if ((mw & 1) || (mh & 1)) ZL_FAIL(ZL_INVALID_ARGUMENT, "s2d preprocess needs even model dims");
+        if (same_size && !letterbox && (mw % 8) == 0 && ((mw / 8) * (mh / 2)) % 32 == 0) {      // every frame of the batch already has the model's size
+            dim3 gs(ceil_div((mw / 8) * (mh / 2), 256), n);
+            if (layout == PRE_S2D16_F16) preprocess_s2d_same_size_kernel<true><<<gs, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out);
+            else preprocess_s2d_same_size_kernel<false><<<gs, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out);
+            ZL_CUDA(cudaGetLastError());
+            return ZL_OK;
+        }
         dim3 g(ceil_div((mw / 2) * (mh / 2), 256), n);
         if (layout == PRE_S2D16_F16) preprocess_s2d_kernel<true><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out, letterbox);
         else preprocess_s2d_kernel<false><<<g, 256, 0, st>>>(staging, descs, mw, mh, (uint4*)out, letterbox);
