@@ -69,7 +69,7 @@ struct HaloParams {
     int32_t ypitch, rpitch, y_f32, y_vec, r_vec, f16, act, silu_tanh;
     int32_t kc, cchunks, stages, sub, y_tma, nsplit, nt, ostage;
     int32_t tiles_x, tiles_y, num_tiles;
-    int32_t epi_variant, esets;                      // epilogue_role specialisation (0..5 fast, 6 generic); warp sets (1 or 2)
+    int32_t epi_variant, esets, direct_store;                      // epilogue_role specialisation (0..5 fast, 6 generic); warp sets (1 or 2)
     int32_t wstream, nacc, nacc_log2, acc_cols;      // weights streamed with the patches (1) or resident (0); accumulator ring
     uint32_t wtile_bytes, wchunk_bytes, wchunk_alloc, patch_bytes, patch_alloc, subpatch_alloc, chunk_stride, stage_stride, tmem_cols;
     int32_t cps, nst;                                // channel chunks per pipeline stage; stages per tile (= cchunks / cps)
@@ -181,6 +181,7 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
     int j0 = 0, k0 = c2;
     while (k0 >= nchunk) { k0 -= nchunk; ++j0; }
     const int res_jstride = kTH * p.W * p.rpitch;            // residual elements between sub-tiles (fits 32 bits: one image row block)
+    const int y_jstride = kTH * p.W * p.ypitch;              // output elements between sub-tiles
     // tile walk: this set takes tiles tile0 + set*step, then every 2*step-th; (n, ty, tx) advance by a fixed decomposition
     TileWalk tw_;
     walk_init(tw_, c.tile0 + set * c.tile_step, p.esets * c.tile_step, p.tiles_x, p.tiles_y);
@@ -193,6 +194,7 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
         const int oy_base = ty * p.sub * kTH + th;           // this thread's row in sub-tile 0
         // residual pixel of sub-tile 0 (64-bit once per tile; per item only 32-bit offsets are added)
         const __nv_bfloat16* res_px = has_res ? res_g + (((size_t)n * p.H + oy_base) * p.W + ox) * p.rpitch : nullptr;
+        char* y_px = reinterpret_cast<char*>(c.y_g) + (((size_t)n * p.H + oy_base) * p.W + ox) * p.ypitch * (y_f32 ? 4 : 2);   // direct-store variant
         // residual of this warp's FIRST item: issued before the accumulator wait, so its latency hides under the MMAs
         uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
         bool r_have = false;
@@ -282,7 +284,34 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
                             if (c0 + i < cout_l) a[i] += unpack1_16(rp[i], f16);
                     }
                 }
-                if (FAST || p.y_tma) {
+                if (FAST && p.direct_store) {
+                    // ---- 256-bit global stores straight from registers (st.global.v8.b32, sm_100): one full 32-byte sector
+                    //      per thread (two for fp32), no staging tile, no proxy fence, no bulk-store instruction — the TMA unit
+                    //      and ~12 % of the tile's shared-memory traffic are left to the patches and the MMAs
+                    if (in_px) {
+                        if (y_f32) {
+                            float* yp = reinterpret_cast<float*>(y_px) + jj * y_jstride + c0;
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp), "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])),
+                                         "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])), "r"(__float_as_uint(a[4])), "r"(__float_as_uint(a[5])),
+                                         "r"(__float_as_uint(a[6])), "r"(__float_as_uint(a[7])) : "memory");
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp + 8), "r"(__float_as_uint(a[8])), "r"(__float_as_uint(a[9])),
+                                         "r"(__float_as_uint(a[10])), "r"(__float_as_uint(a[11])), "r"(__float_as_uint(a[12])), "r"(__float_as_uint(a[13])),
+                                         "r"(__float_as_uint(a[14])), "r"(__float_as_uint(a[15])) : "memory");
+                        } else {
+                            uint32_t w[8];
+                            if (f16) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) { const __half2 hh = __floats2half2_rn(a[2 * i], a[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&hh); }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) { const __nv_bfloat162 hh = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&hh); }
+                            }
+                            uint16_t* yp = reinterpret_cast<uint16_t*>(y_px) + jj * y_jstride + c0;
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                                         "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+                        }
+                    }
+                } else if (FAST || p.y_tma) {
                     // ---- stage [32 px][16 ch] in smem, one TMA store per warp (image borders and ragged channel counts are
                     //      clipped by the hardware against the tensor map's extents)
                     const uint32_t sbuf = stage_out + (nstore & 1u) * (uint32_t)p.ostage;
@@ -951,6 +980,11 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.cps = o.cps; p.nst = o.nst;
     p.wstream = o.wstream; p.nacc = o.nacc; p.acc_cols = o.acc_cols;
     p.esets = (o.num_tiles * o.nsplit > grid_for(o, num_sms)) ? 2 : 1;      // more than one tile per CTA: two alternating sets
+    // 256-bit global stores instead of staged bulk stores: measured (profiles/README_r02.md) a few us faster on the 1x1 layers
+    // with 16-bit outputs, slower on fp32 outputs and on layer 0 -> default 1 = those layers only; 0 = never; 2 = wherever possible
+    static const int direct_env = [] { const char* e = getenv("ZL_EPI_DIRECT"); return e ? atoi(e) : 1; }();
+    const bool direct_ok = (o.ypitch * (o.y_f32 ? 4 : 2)) % 32 == 0 && (reinterpret_cast<uintptr_t>(o.y) & 31) == 0;
+    p.direct_store = (direct_ok && (direct_env == 2 || (direct_env == 1 && o.mode == 1 && !o.y_f32))) ? 1 : 0;
     p.epi_variant = 6;
     if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC")) {
         const int fmt = o.f16 ? 3 : 0;
