@@ -83,7 +83,7 @@ typedef struct zl_config {
     int32_t max_frame_w, max_frame_h; /* largest request frame accepted (staging size) */
     int32_t preprocess_mode;    /* ZL_PRE_* */
     int32_t queue_depth;        /* bound of the async queue; full queue -> ZL_INFERENCE_ERROR */
-    int32_t num_lanes;          /* concurrent pipelines (streams + buffers) for the async path, 1..4 */
+    int32_t num_lanes;          /* concurrent pipelines (streams + buffers) for the async path, 1..8 */
     int32_t use_graph;          /* 1 = capture each batch size in a CUDA graph */
     int32_t batch_window_us;    /* async path: wait this long to coalesce a batch (0 = take what is queued) */
     int32_t emit_wire;          /* 1 = also emit every frame's result in the reference's wire layout on the device (zl_*_wire entry points) */

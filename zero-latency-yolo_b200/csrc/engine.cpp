@@ -75,7 +75,7 @@ int32_t Engine::init()
     if (cfg.max_frame_w <= 0) cfg.max_frame_w = cfg.model_w;
     if (cfg.max_frame_h <= 0) cfg.max_frame_h = cfg.model_h;
     if (cfg.num_lanes < 1) cfg.num_lanes = 1;
-    if (cfg.num_lanes > 4) cfg.num_lanes = 4;
+    if (cfg.num_lanes > 8) cfg.num_lanes = 8;
     if (cfg.queue_depth < 1) cfg.queue_depth = 8;     // constants::INFERENCE_QUEUE_SIZE (src/common/constants.h)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
