@@ -6,12 +6,12 @@ OUT=../lib
 mkdir -p "$OUT" .obj
 NVCC=${NVCC:-nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xcompiler -Wall)
-SRCS=(conv_tc.cu conv_halo.cu conv_simt.cu preprocess.cu pool_upsample.cu postprocess.cu engine.cpp weights.cpp capi.cpp)
+SRCS=(conv_tc.cu conv_halo.cu head_fused.cu conv_simt.cu preprocess.cu pool_upsample.cu postprocess.cu engine.cpp weights.cpp capi.cpp)
 TEST_SRCS=(umma_probe.cu test_hooks.cpp)     # unit-test / measurement hooks: libzl_b200_test.so only
 pids=()
 for s in "${SRCS[@]}" "${TEST_SRCS[@]}"; do
   o=.obj/${s%.*}.o
-  if [[ ! -f $o || $s -nt $o || kernels.h -nt $o || common.h -nt $o || tc_ptx.cuh -nt $o || half16.cuh -nt $o || engine.h -nt $o || weights.h -nt $o || ../../include/zl_b200.h -nt $o || ../../include/zl_b200_test.h -nt $o ]]; then
+  if [[ ! -f $o || $s -nt $o || kernels.h -nt $o || common.h -nt $o || tc_ptx.cuh -nt $o || head_math.cuh -nt $o || half16.cuh -nt $o || engine.h -nt $o || weights.h -nt $o || ../../include/zl_b200.h -nt $o || ../../include/zl_b200_test.h -nt $o ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$s" -o "$o" &
     pids+=($!)
   fi

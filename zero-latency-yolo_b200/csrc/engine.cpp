@@ -558,6 +558,7 @@ int32_t Engine::build_ops(Lane& L, int B)
         else conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(0, md.cb), nullptr);
         conv(b + ".1.conv", buf("HBC1_" + s).slice(0, md.cb), buf("HB2_" + s), nullptr);
         conv(b + ".2", buf("HB2_" + s), buf("BOX_" + s), nullptr);
+        if (rc == ZL_OK) ops.back().path = 3;
     }
     for (int l = 0; l < 3; ++l) {
         const std::string s = std::to_string(l), b = "model.22.cv3." + s;
@@ -566,12 +567,32 @@ int32_t Engine::build_ops(Lane& L, int B)
         conv(b + ".1.conv", buf("HBC1_" + s).slice(md.cb, md.cc), buf("HC2_" + s), nullptr);
         View cls = buf("CLS_" + s); cls.c = md.nc;
         conv(b + ".2", buf("HC2_" + s), cls, nullptr);
+        if (rc == ZL_OK) ops.back().path = 3;
     }
     if (rc != ZL_OK) return rc;
+    if (bf16) {
+        // the last 1x1 convs of both branches + Detect tail + decode/threshold as one kernel (head_fused.cu)
+        const ConvWeights* wb[3] = {nullptr, nullptr, nullptr};
+        const ConvWeights* wc[3] = {nullptr, nullptr, nullptr};
+        View xb[3], xc[3];
+        for (int l = 0; l < 3; ++l) {
+            const std::string s = std::to_string(l);
+            auto ib = conv_by_name.find("model.22.cv2." + s + ".2"), ic = conv_by_name.find("model.22.cv3." + s + ".2");
+            if (ib != conv_by_name.end()) wb[l] = ib->second;
+            if (ic != conv_by_name.end()) wc[l] = ic->second;
+            xb[l] = buf("HB2_" + s); xc[l] = buf("HC2_" + s);
+        }
+        if (head_fused_supported(wb, wc, xb, xc, md.nc)) {
+            Op op; op.kind = Op::HEAD_FUSED; op.name = "head.2+decode+filter"; op.path = 4;
+            ZL_TRY(head_fused_prepare(wb, wc, xb, xc, L.levels, md.nc, num_anchors, num_sms, &op.hf));
+            op.flops = op.hf.flops; op.bytes = op.hf.bytes;
+            ops.push_back(op);
+        }
+    }
     const double rawb = (double)B * (4 + md.nc) * num_anchors * 4;
-    { Op op; op.kind = Op::DECODE; op.name = "dfl_decode"; op.bytes = (double)B * num_anchors * (64 + md.nc) * 4 + rawb; ops.push_back(op); }
-    { Op op; op.kind = Op::FILTER; op.name = "filter"; op.bytes = rawb; ops.push_back(op); }
-    { Op op; op.kind = Op::DECODE_FILTER; op.name = "decode+filter"; op.bytes = (double)B * num_anchors * md.nc * 4; ops.push_back(op); }
+    { Op op; op.kind = Op::DECODE; op.name = "dfl_decode"; op.path = 1; op.bytes = (double)B * num_anchors * (64 + md.nc) * 4 + rawb; ops.push_back(op); }
+    { Op op; op.kind = Op::FILTER; op.name = "filter"; op.path = 1; op.bytes = rawb; ops.push_back(op); }
+    { Op op; op.kind = Op::DECODE_FILTER; op.name = "decode+filter"; op.path = 2; op.bytes = (double)B * num_anchors * md.nc * 4; ops.push_back(op); }
     { Op op; op.kind = Op::NMS; op.name = "nms"; op.bytes = 0; ops.push_back(op); }
     L.ops[B] = std::move(ops);
     return ZL_OK;
@@ -598,9 +619,34 @@ int32_t Engine::launch_op(Lane& L, int B, const Op& op)
         case Op::FILTER: return launch_filter(st, L.raw, B, md.nc, num_anchors, L.d_descs, nullptr, cfg.conf_threshold, d_class_weights, L.pb);
         case Op::DECODE_FILTER:
             return launch_decode_filter(st, L.levels, B, md.nc, num_anchors, L.d_descs, cfg.conf_threshold, d_class_weights, L.pb, !bf16);
+        case Op::HEAD_FUSED: return head_fused_launch(st, op.hf, L.d_descs, cfg.conf_threshold, d_class_weights, L.pb);
         case Op::NMS: return launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb);
     }
     return ZL_OK;
+}
+
+// Which ops of the list a pass runs (Op::path).
+static bool head_is_fused(const std::vector<Op>& ops)
+{
+    for (const Op& op : ops) if (op.kind == Op::HEAD_FUSED) return true;
+    return false;
+}
+static bool op_selected(const Op& op, bool want_raw, bool fused)
+{
+    switch (op.path) {
+        case 1: return want_raw;
+        case 2: return !want_raw && !fused;
+        case 3: return want_raw || !fused;
+        case 4: return !want_raw && fused;
+        default: return true;
+    }
+}
+static std::vector<Op> hot_ops(const std::vector<Op>& all)
+{
+    const bool fused = head_is_fused(all);
+    std::vector<Op> ops;
+    for (const Op& op : all) if (op_selected(op, false, fused)) ops.push_back(op);
+    return ops;
 }
 
 // want_raw: materialise the raw head tensor (zl_forward_raw) with the two-kernel D1, F1 path; otherwise the fused
@@ -612,8 +658,9 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
     if (it == L.ops.end()) { ZL_TRY(build_ops(L, B)); it = L.ops.find(B); }
     ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st));
     ZL_CUDA(cudaMemsetAsync(L.pb.header, 0, sizeof(uint32_t) * 4, st));
+    const bool fused = head_is_fused(it->second);
     for (const Op& op : it->second) {
-        if (want_raw ? op.kind == Op::DECODE_FILTER : (op.kind == Op::DECODE || op.kind == Op::FILTER)) continue;
+        if (!op_selected(op, want_raw, fused)) continue;
         ZL_TRY(launch_op(L, B, op));
     }
     if (cfg.preprocess_mode == ZL_PRE_LETTERBOX)      // non-parity mode: boxes back from the letterboxed model frame to the request frame
@@ -1051,7 +1098,7 @@ int32_t Engine::run_resident(int n_sets, int steps, float* total_ms, int64_t* la
     float ms = 0;
     ZL_CUDA(cudaEventElapsedTime(&ms, L0.ev0, L0.ev1));
     if (total_ms) *total_ms = ms;
-    if (launches) *launches = (int64_t)steps * ((int64_t)L0.ops[B].size() - 2);     // DECODE + FILTER ops are the raw-mode alternates
+    if (launches) *launches = (int64_t)steps * (int64_t)hot_ops(L0.ops[B]).size();     // the ops of the hot path (raw-mode alternates excluded)
     if (total_dets) *total_dets = ((const uint32_t*)L0.h_result)[0];
     return ZL_OK;
 }
@@ -1070,8 +1117,7 @@ int32_t Engine::profile(int set, int iters, zl_op_profile* out, int cap, int32_t
     ZL_CUDA(cudaMemcpyAsync(L.d_descs, L.d_res_descs + (size_t)set * cfg.max_batch, sizeof(FrameDesc) * B, cudaMemcpyDeviceToDevice, L.stream));
     ZL_TRY(run_ops(L, B, false));                         // warm
     ZL_CUDA(cudaStreamSynchronize(L.stream));
-    std::vector<Op> ops;
-    for (const Op& op : L.ops[B]) if (op.kind != Op::DECODE && op.kind != Op::FILTER) ops.push_back(op);
+    std::vector<Op> ops = hot_ops(L.ops[B]);
     std::vector<cudaEvent_t> ev(ops.size() + 1);
     for (auto& e : ev) cudaEventCreate(&e);
     std::vector<double> acc(ops.size(), 0.0);
@@ -1116,8 +1162,7 @@ int32_t Engine::profile_stalls(int set, uint64_t* out, int cap_ops, int32_t* n_o
     L.same_size = L.resident_same[set];
     const int B = graph_batch_for(n);
     if (!L.ops.count(B)) ZL_TRY(build_ops(L, B));
-    std::vector<Op> ops;
-    for (const Op& op : L.ops[B]) if (op.kind != Op::DECODE && op.kind != Op::FILTER) ops.push_back(op);
+    std::vector<Op> ops = hot_ops(L.ops[B]);
     if ((int)ops.size() > cap_ops) ZL_FAIL(ZL_INSUFFICIENT_RESOURCES, "stall buffer too small");
     unsigned long long* d = nullptr;
     const size_t bytes = ops.size() * kHaloStatSlots * sizeof(unsigned long long);

@@ -30,12 +30,16 @@ struct ModelDef {
 };
 
 struct Op {
-    enum Kind : int32_t { PRE = 0, CONV_TC = 1, CONV_SIMT = 2, CONV0 = 3, POOL = 4, UPSAMPLE = 5, DECODE = 6, FILTER = 7, NMS = 8, CONV_HALO = 9, PRE_CONV0 = 10, DECODE_FILTER = 11 };
+    enum Kind : int32_t { PRE = 0, CONV_TC = 1, CONV_SIMT = 2, CONV0 = 3, POOL = 4, UPSAMPLE = 5, DECODE = 6, FILTER = 7, NMS = 8, CONV_HALO = 9, PRE_CONV0 = 10, DECODE_FILTER = 11, HEAD_FUSED = 12 };
     int32_t kind = PRE;
     std::string name;
     const ConvWeights* w = nullptr;
     ConvTcOp tc;
     ConvHaloOp halo;
+    HeadFusedOp hf;
+    // which passes run this op: 0 all; 1 raw-head passes only (zl_forward_raw); 2 hot path when the head is NOT fused;
+    // 3 raw passes and the unfused hot path (the last 1x1 convs of the head); 4 hot path with the fused head kernel
+    int32_t path = 0;
     View x, y, res, p1, p2, p3;
     bool has_res = false;
     double flops = 0, bytes = 0;

@@ -147,6 +147,19 @@ int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, 
 int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb);
 int32_t nms_configure();   // one-time cudaFuncSetAttribute calls
 
+// model.22.cv2.l.2 + model.22.cv3.l.2 (the two last 1x1 convs of every level) + D1 + F1 in one persistent tcgen05 kernel
+// (head_fused.cu): the fp32 logits stay in TMEM, only the candidates are written.  Same candidates, bit for bit, as the
+// conv kernels followed by launch_decode_filter.  ZL_FUSE_HEAD=0 turns it off (A/B).
+struct HeadFusedOp {
+    alignas(64) unsigned char blob[2560];   // tensor maps + kernel parameters (head_fused.cu: HeadFusedImpl)
+    int32_t grid, smem_bytes;
+    double flops, bytes;
+};
+bool head_fused_supported(const ConvWeights* const wb[3], const ConvWeights* const wc[3], const View xb[3], const View xc[3], int nc);
+int32_t head_fused_prepare(const ConvWeights* const wb[3], const ConvWeights* const wc[3], const View xb[3], const View xc[3],
+                           const HeadLevel lvl[3], int nc, int A, int num_sms, HeadFusedOp* op);
+int32_t head_fused_launch(cudaStream_t st, const HeadFusedOp& op, const FrameDesc* descs, float conf_thr, const float* class_weights, const PostBuffers& pb);
+
 // Result wire layout on the device: per frame {frame_id u32, timestamp u64, count u16} + count x 40-byte
 // Detection, packed back to back in batch order (src/common/protocol.h:541-567, src/common/types.h:20-26).
 struct WireMeta { uint32_t frame_id; uint32_t pad; uint64_t timestamp; };     // meta[n] per frame; meta[maxn].timestamp = Detection::timestamp of the batch
@@ -154,6 +167,8 @@ constexpr int kWireHeader = 14, kWireDet = 40;
 int32_t launch_wire_pack(cudaStream_t st, int32_t n, const PostBuffers& pb, const WireMeta* meta, uint8_t* wire, uint32_t wire_cap, uint32_t* wire_off);
 
 // ---------------------------------------------------------------- TMA helper
+// 3-D map {cin, cout_pad, taps} with strides {ktot*2, cin*2} bytes and box {kc, nt, taps}: lands as [taps][nt][kc] (conv_halo.cu)
+int32_t make_tmap_w3d(CUtensorMap* map, const void* w, int cin, int cout_pad, int taps, int ktot, int kc, int nt, bool f16);
 int32_t make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int32_t swizzle_bytes, bool f16);
 

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "head_math.cuh"
 #include "kernels.h"
 
 namespace zl {
@@ -33,44 +34,24 @@ constexpr int kDflThreads = 256;   // 8 warps, 4 anchors each
 template <bool PRECISE>
 __device__ __forceinline__ float dfl_side(const float* __restrict__ bins)
 {
-    using T = typename std::conditional<PRECISE, double, float>::type;
     float z[16];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(bins) + q);
         z[4 * q] = v.x; z[4 * q + 1] = v.y; z[4 * q + 2] = v.z; z[4 * q + 3] = v.w;
     }
-    float m = z[0];
-#pragma unroll
-    for (int i = 1; i < 16; ++i) m = fmaxf(m, z[i]);
-    T se = (T)0, sw = (T)0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const T e = PRECISE ? (T)exp((double)z[i] - (double)m) : (T)__expf(z[i] - m);
-        se += e;
-        sw += e * (T)i;
-    }
-    return PRECISE ? (float)(sw / se) : __fdividef((float)sw, (float)se);
+    return dfl_expect<PRECISE>(z);
 }
 
 // All four lanes of the anchor's quad call this with the same (lv, pix, x, y); every lane returns the box.
 template <bool PRECISE>
 __device__ __forceinline__ float4 dfl_box4(const HeadLevel& lv, size_t pix, int x, int y, int side, unsigned quad_mask)
 {
-    using T = typename std::conditional<PRECISE, double, float>::type;
     const float d = dfl_side<PRECISE>(lv.box + pix * 64 + side * 16);
     const int lane = threadIdx.x & 31, q0 = lane & ~3;
     const float dl = __shfl_sync(quad_mask, d, q0 + 0), dt = __shfl_sync(quad_mask, d, q0 + 1);
     const float dr = __shfl_sync(quad_mask, d, q0 + 2), db = __shfl_sync(quad_mask, d, q0 + 3);
-    const T ax = (T)x + (T)0.5, ay = (T)y + (T)0.5, s = (T)lv.stride;
-    const T x1 = ax - (T)dl, y1 = ay - (T)dt, x2 = ax + (T)dr, y2 = ay + (T)db;
-    return make_float4((float)((x1 + x2) * (T)0.5 * s), (float)((y1 + y2) * (T)0.5 * s), (float)((x2 - x1) * s), (float)((y2 - y1) * s));
-}
-
-template <bool PRECISE>
-__device__ __forceinline__ float cls_score(float z)
-{
-    return PRECISE ? (float)(1.0 / (1.0 + exp(-(double)z))) : __fdividef(1.0f, 1.0f + __expf(-z));
+    return dfl_box<PRECISE>(dl, dt, dr, db, x, y, lv.stride);
 }
 
 // PRECISE = fp64 softmax / sigmoid / box arithmetic (exact mode); otherwise fp32 (bf16 mode).
@@ -124,16 +105,7 @@ dfl_decode_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2, in
 }
 
 // ============================================================= F1: filter
-// key = class[12] | (~confidence bits)[32] | anchor[20]: ascending key order ==
-// (class asc, confidence desc, anchor asc).  Confidence is > 0 here, so its
-// IEEE bit pattern is monotone.
-__device__ __forceinline__ uint64_t make_key(int cls, float conf, int anchor) {
-    return ((uint64_t)(uint32_t)cls << 52) | ((uint64_t)(~__float_as_uint(conf)) << kKeyAnchorBits) | (uint64_t)(uint32_t)anchor;
-}
-__device__ __forceinline__ int key_class(uint64_t k) { return (int)(k >> 52); }
-__device__ __forceinline__ float key_conf(uint64_t k) { return __uint_as_float(~(uint32_t)(k >> kKeyAnchorBits)); }
-__device__ __forceinline__ int key_anchor(uint64_t k) { return (int)(k & ((1u << kKeyAnchorBits) - 1)); }
-
+// candidate sort key: head_math.cuh (make_key / key_class / key_conf / key_anchor)
 __global__ void __launch_bounds__(256)
 filter_kernel(const float* __restrict__ raw, int nc, int A, const FrameDesc* __restrict__ descs,
               const int32_t* __restrict__ img_wh, float conf_thr, const float* __restrict__ class_weights,
