@@ -22,6 +22,10 @@ ZL_API int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_
 
 /* Measurement hook: cycles for `count` tcgen05.mma (M=128) of width N with the given swizzle / group stride /
  * accumulator rotation; sizes the conv tiles (DESIGN.md "UMMA probe"). */
+/* SPPF max-pools (5/9/13 windows, -inf padding) of x [n,h,w,c] into the concat buffer [n,h,w,4c] = x | p1 | p2 | p3, as fp32.
+ * dtype: 0 fp32, 1 bf16, 2 fp16 (x is rounded to the format first). */
+ZL_API int32_t zl_test_sppf_pool(int32_t device, int32_t dtype, const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* cat);
+
 ZL_API int32_t zl_probe_umma(int32_t device, int32_t N, int32_t swz, int32_t sbo_a, int32_t nacc, int32_t count,
                              int32_t shift_rows, int32_t ksteps, int32_t grid, int64_t* issue_cycles, int64_t* total_cycles);
 

@@ -256,6 +256,29 @@ def _check_post(eng, raw, img_w, img_h, conf, iou):
         assert len(got[f]) == len(ref), f"frame {f}: kept {len(got[f])} vs oracle {len(ref)}"
         assert np.array_equal(got[f].view(np.uint8), ref.view(np.uint8)), f"frame {f}: detections differ bitwise"
 
+@pytest.mark.parametrize("dtype", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(3, 20, 20, 32), (2, 13, 13, 16), (1, 7, 5, 48), (2, 40, 40, 128)])
+def test_sppf_pools_are_exact(built_lib, dtype, shape):
+    """SPPF = three chained 5x5/s1/p2 max-pools == windows 5 / 9 / 13 of the input with -inf padding.
+    max() is exact in every format, so the kernel (packed 16-bit or fp32) must equal numpy on the rounded input bit for bit."""
+    import torch
+    import zlb200
+    rng = np.random.default_rng(hash((dtype,) + shape) % (1 << 31))
+    x = rng.standard_normal(shape).astype(np.float32) * 3
+    x[rng.random(shape) < 0.05] = 0.0
+    cat = zlb200.test_sppf_pool(x, dtype)
+    c = shape[3]
+    xq = cat[..., :c]                                             # the input as the kernel saw it (rounded to the format)
+    t = torch.from_numpy(xq).permute(0, 3, 1, 2)
+    if dtype != "fp32":
+        assert np.array_equal(xq, (torch.from_numpy(x).to(torch.float16 if dtype == "fp16" else torch.bfloat16).float().numpy()))
+    for i in range(3):
+        t = torch.nn.functional.max_pool2d(t, 5, 1, 2)
+        want = t.permute(0, 2, 3, 1).numpy()
+        got = cat[..., (i + 1) * c:(i + 2) * c]
+        assert np.array_equal(got, want), f"pool {i + 1} differs: {np.abs(got - want).max()}"
+
+
 
 def test_post_small_random(eng):
     _check_post(eng, synth.stress_head(4, 4, 3549, seed=1, img=416), 416, 416, 0.25, 0.45)

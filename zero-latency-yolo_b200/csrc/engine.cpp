@@ -1173,7 +1173,9 @@ int32_t Engine::profile_stalls(int set, uint64_t* out, int cap_ops, int32_t* n_o
     cudaMemsetAsync(L.pb.header, 0, 16, L.stream);
     int32_t rc = ZL_OK;
     for (size_t i = 0; i < ops.size() && rc == ZL_OK; ++i)
-        rc = ops[i].kind == Op::CONV_HALO ? conv_halo_launch(L.stream, ops[i].halo, num_sms, d + i * kHaloStatSlots) : launch_op(L, B, ops[i]);
+        rc = ops[i].kind == Op::CONV_HALO ? conv_halo_launch(L.stream, ops[i].halo, num_sms, d + i * kHaloStatSlots)
+             : ops[i].kind == Op::HEAD_FUSED ? head_fused_launch(L.stream, ops[i].hf, L.d_descs, cfg.conf_threshold, d_class_weights, L.pb, d + i * kHaloStatSlots)
+                                             : launch_op(L, B, ops[i]);
     cudaError_t ce = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, L.stream);
     cudaError_t cs = cudaStreamSynchronize(L.stream);
     cudaFree(d);

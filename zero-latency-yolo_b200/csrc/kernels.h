@@ -158,7 +158,8 @@ struct HeadFusedOp {
 bool head_fused_supported(const ConvWeights* const wb[3], const ConvWeights* const wc[3], const View xb[3], const View xc[3], int nc);
 int32_t head_fused_prepare(const ConvWeights* const wb[3], const ConvWeights* const wc[3], const View xb[3], const View xc[3],
                            const HeadLevel lvl[3], int nc, int A, int num_sms, HeadFusedOp* op);
-int32_t head_fused_launch(cudaStream_t st, const HeadFusedOp& op, const FrameDesc* descs, float conf_thr, const float* class_weights, const PostBuffers& pb);
+int32_t head_fused_launch(cudaStream_t st, const HeadFusedOp& op, const FrameDesc* descs, float conf_thr, const float* class_weights, const PostBuffers& pb,
+                          unsigned long long* stats = nullptr);     // stats: the instrumented instantiation (same slots as conv_halo_launch; 12-14 = scan pass 1 / pass 2 / box + emit)
 
 // Result wire layout on the device: per frame {frame_id u32, timestamp u64, count u16} + count x 40-byte
 // Detection, packed back to back in batch order (src/common/protocol.h:541-567, src/common/types.h:20-26).

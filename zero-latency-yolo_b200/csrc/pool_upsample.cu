@@ -145,6 +145,65 @@ sppf_pool_smem_kernel(const T* __restrict__ a, T* __restrict__ p1, T* __restrict
     }
 }
 
+// 16-bit variant of the kernel above: max() is exact in any format, so the planes stay PACKED (one uint4 = 8 channels of
+// one pixel) and every step is a 128-bit shared-memory access plus four packed max instructions — a fifth of the
+// instructions of the fp32-staged version (round-2 profile: 50 us for 6.5 MB in, 19.7 MB out; this form: HBM-bound).
+template <bool F16>
+__device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b)
+{
+    if (F16) { const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b)); return *reinterpret_cast<const uint32_t*>(&r); }
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <bool F16>
+__device__ __forceinline__ uint4 vmax16(const uint4 a, const uint4 b)
+{
+    return make_uint4(max2_16<F16>(a.x, b.x), max2_16<F16>(a.y, b.y), max2_16<F16>(a.z, b.z), max2_16<F16>(a.w, b.w));
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(256)
+sppf_pool16_kernel(const uint16_t* __restrict__ a, uint16_t* __restrict__ p1, uint16_t* __restrict__ p2, uint16_t* __restrict__ p3,
+                   int H, int W, int apitch, int p1pitch, int p2pitch, int p3pitch)
+{
+    extern __shared__ uint4 pool16_sm[];
+    const int npix = H * W, nv = npix * 2;                     // 16 channels per CTA = two vectors per pixel
+    uint4* A = pool16_sm;
+    uint4* B = pool16_sm + nv;
+    const int n = blockIdx.y, cg = blockIdx.x * 16, tid = threadIdx.x;
+    for (int idx = tid; idx < nv; idx += 256)
+        A[idx] = __ldg(reinterpret_cast<const uint4*>(a + ((size_t)n * npix + (idx >> 1)) * apitch + cg + (idx & 1) * 8));
+    __syncthreads();
+    uint16_t* outs[3] = {p1, p2, p3};
+    const int pitches[3] = {p1pitch, p2pitch, p3pitch};
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int idx = tid; idx < nv; idx += 256) {            // row max: B = max over x-2..x+2 of A
+            const int pix = idx >> 1, x = pix % W;
+            uint4 m = A[idx];
+            if (x >= 2) m = vmax16<F16>(m, A[idx - 4]);
+            if (x >= 1) m = vmax16<F16>(m, A[idx - 2]);
+            if (x + 1 < W) m = vmax16<F16>(m, A[idx + 2]);
+            if (x + 2 < W) m = vmax16<F16>(m, A[idx + 4]);
+            B[idx] = m;
+        }
+        __syncthreads();
+        uint16_t* o = outs[pass];
+        const int op = pitches[pass];
+        for (int idx = tid; idx < nv; idx += 256) {            // column max: A = max over y-2..y+2 of B, written out as it is produced
+            const int pix = idx >> 1, y = pix / W;
+            uint4 m = B[idx];
+            if (y >= 2) m = vmax16<F16>(m, B[idx - 4 * W]);
+            if (y >= 1) m = vmax16<F16>(m, B[idx - 2 * W]);
+            if (y + 1 < H) m = vmax16<F16>(m, B[idx + 2 * W]);
+            if (y + 2 < H) m = vmax16<F16>(m, B[idx + 4 * W]);
+            A[idx] = m;
+            *reinterpret_cast<uint4*>(o + ((size_t)n * npix + pix) * op + cg + (idx & 1) * 8) = m;
+        }
+        __syncthreads();
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xpitch, int ypitch)
@@ -177,6 +236,26 @@ int32_t launch_sppf_pool(cudaStream_t st, const View& a, const View& p1, const V
     const int vn = a.dtype == DT_F32 ? 4 : 8;
     if (a.c % vn || !aligned16(a) || !aligned16(p1) || !aligned16(p2) || !aligned16(p3))
         ZL_FAIL(ZL_INVALID_ARGUMENT, "sppf_pool: views must be 16-B aligned");
+    const size_t smem16 = (size_t)a.h * a.w * 2 * sizeof(uint4) * 2;
+    if (a.dtype != DT_F32 && (a.c % 16) == 0 && smem16 <= 200 * 1024) {
+        static thread_local int last_dev16 = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != last_dev16) {
+            ZL_CUDA(cudaFuncSetAttribute(sppf_pool16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            ZL_CUDA(cudaFuncSetAttribute(sppf_pool16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            last_dev16 = dev;
+        }
+        dim3 g(a.c / 16, a.n);
+        if (a.dtype == DT_F16)
+            sppf_pool16_kernel<true><<<g, 256, smem16, st>>>((const uint16_t*)a.ptr, (uint16_t*)p1.ptr, (uint16_t*)p2.ptr, (uint16_t*)p3.ptr, a.h, a.w,
+                                                              a.pitch, p1.pitch, p2.pitch, p3.pitch);
+        else
+            sppf_pool16_kernel<false><<<g, 256, smem16, st>>>((const uint16_t*)a.ptr, (uint16_t*)p1.ptr, (uint16_t*)p2.ptr, (uint16_t*)p3.ptr, a.h, a.w,
+                                                               a.pitch, p1.pitch, p2.pitch, p3.pitch);
+        ZL_CUDA(cudaGetLastError());
+        return ZL_OK;
+    }
     const size_t smem = (size_t)a.h * a.w * 16 * sizeof(float) * 2;
     if ((a.c % 16) == 0 && smem <= 200 * 1024) {
         static thread_local int last_dev = -1;

@@ -119,4 +119,41 @@ int32_t zl_test_conv(int32_t device, int32_t impl, const float* x, int32_t n, in
     ZL_GUARD_END
 }
 
+// SPPF pools (pool_upsample.cu) on a 16-bit or fp32 NHWC map: x [n,h,w,c] -> p1 | p2 | p3 written into ONE concat buffer
+// [n,h,w,4c] next to a copy of x (the layout the engine uses), returned as fp32.  dtype: 0 fp32, 1 bf16, 2 fp16.
+int32_t zl_test_sppf_pool(int32_t device, int32_t dtype, const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* cat)
+{
+    ZL_GUARD_BEGIN
+    using namespace zl;
+    if (!x || !cat || dtype < 0 || dtype > 2) { set_error("bad argument"); return ZL_INVALID_ARGUMENT; }
+    ZL_CUDA(cudaSetDevice(device));
+    const size_t npix = (size_t)n * h * w, nel = npix * 4 * c;
+    const int es = dtype == 0 ? 4 : 2;
+    std::vector<uint8_t> host(nel * es, 0);
+    for (size_t p = 0; p < npix; ++p)
+        for (int k = 0; k < c; ++k) {
+            const float v = x[p * c + k];
+            const size_t o = p * 4 * c + k;
+            if (dtype == 0) std::memcpy(&host[o * 4], &v, 4);
+            else { const uint16_t q = dtype == 2 ? f2h_host(v) : f2bf_host(v); std::memcpy(&host[o * 2], &q, 2); }
+        }
+    void* d = nullptr;
+    ZL_CUDA(cudaMalloc(&d, nel * es));
+    cudaMemcpy(d, host.data(), nel * es, cudaMemcpyHostToDevice);
+    const int dt = dtype == 0 ? DT_F32 : (dtype == 2 ? DT_F16 : DT_BF16);
+    View cv{d, n, h, w, 4 * c, 4 * c, dt};
+    int32_t rc = launch_sppf_pool(nullptr, cv.slice(0, c), cv.slice(c, c), cv.slice(2 * c, c), cv.slice(3 * c, c));
+    if (rc == ZL_OK && cudaDeviceSynchronize() != cudaSuccess) { set_error(std::string("sppf_pool: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; }
+    if (rc == ZL_OK) {
+        cudaMemcpy(host.data(), d, nel * es, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < nel; ++i) {
+            if (dtype == 0) std::memcpy(&cat[i], &host[i * 4], 4);
+            else { uint16_t q; std::memcpy(&q, &host[i * 2], 2); cat[i] = dtype == 2 ? h2f_host(q) : bf2f_host(q); }
+        }
+    }
+    cudaFree(d);
+    return rc;
+    ZL_GUARD_END
+}
+
 }  // extern "C"

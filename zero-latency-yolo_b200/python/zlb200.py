@@ -61,7 +61,7 @@ EXPORTS = [
     "zl_engine_run_resident", "zl_engine_profile", "zl_engine_profile_stalls", "zl_bench_e2e", "zl_bench_h2d", "zl_bench_latency", "zl_bench_preprocess", "zl_bench_decode_nms",
     "zl_model_probe", "zl_host_alloc", "zl_host_free", "zl_last_error", "zl_version", "zl_device_count",
 ]
-TEST_EXPORTS = ["zl_test_conv", "zl_probe_umma", "zl_probe_tma"]     # libzl_b200_test.so only
+TEST_EXPORTS = ["zl_test_conv", "zl_test_sppf_pool", "zl_probe_umma", "zl_probe_tma"]     # libzl_b200_test.so only
 
 
 class ZlError(RuntimeError):
@@ -138,6 +138,7 @@ def testlib():
         L = C.CDLL(TEST_LIB_PATH)
         vp, i32, u32 = C.c_void_p, C.c_int32, C.c_uint32
         L.zl_test_conv.restype, L.zl_test_conv.argtypes = i32, [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.zl_test_sppf_pool.restype, L.zl_test_sppf_pool.argtypes = i32, [i32, i32, vp, i32, i32, i32, i32, vp]
         L.zl_probe_umma.restype, L.zl_probe_umma.argtypes = i32, [i32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.zl_probe_tma.restype, L.zl_probe_tma.argtypes = i32, [i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, u32, vp, u32, C.POINTER(i32)]
         L.zl_last_error.restype, L.zl_last_error.argtypes = C.c_char_p, []
@@ -383,6 +384,15 @@ def test_conv(x_nhwc, w_ohwi, bias, stride=1, act=True, res=None, impl=0, device
     _check_t(testlib().zl_test_conv(device, impl, _ptr(x), n, h, wd, cin, _ptr(w), _ptr(b), cout, k, stride, flags,
                               _ptr(r) if r is not None else None, _ptr(y)))
     return y
+
+
+def test_sppf_pool(x_nhwc, dtype="fp16", device=0):
+    """SPPF pools of x [n,h,w,c] through the engine's kernel: returns the concat buffer [n,h,w,4c] = x | p1 | p2 | p3 (fp32)."""
+    x = np.ascontiguousarray(x_nhwc, np.float32)
+    n, h, w, c = x.shape
+    cat = np.zeros((n, h, w, 4 * c), np.float32)
+    _check_t(testlib().zl_test_sppf_pool(device, {"fp32": 0, "bf16": 1, "fp16": 2}[dtype], _ptr(x), n, h, w, c, _ptr(cat)))
+    return cat
 
 
 def probe_umma(N, swz=128, sbo=None, nacc=1, count=512, shift_rows=0, ksteps=4, grid=1, device=0):
