@@ -15,9 +15,10 @@ if __name__ == "__main__":
     scale = sys.argv[1] if len(sys.argv) > 1 else "n"
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     hw = int(sys.argv[3]) if len(sys.argv) > 3 else 640
-    t = yolov8_ref.synthetic_model(scale, 80, 0)
-    e = zlb200.Engine(hw, hw, 80, scale, precision=zlb200.FP16, max_batch=batch)
-    e.load_weights_blob(zlw.dumps(t, scale, 80))
+    nc = int(sys.argv[4]) if len(sys.argv) > 4 else 80
+    t = yolov8_ref.synthetic_model(scale, nc, 0)
+    e = zlb200.Engine(hw, hw, nc, scale, precision=zlb200.FP16, max_batch=batch)
+    e.load_weights_blob(zlw.dumps(t, scale, nc))
     e.upload_resident(0, list(synth.frames_structured(batch, hw, hw)))
     prof = e.profile(0, 5)
     st = e.profile_stalls(0)
