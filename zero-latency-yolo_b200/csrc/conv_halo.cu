@@ -1,22 +1,22 @@
-// conv_halo.cu — persistent 3x3 / stride-1 convolution on tcgen05 with halo reuse (sm_100a only).
+// conv_halo.cu — the persistent tcgen05 convolution kernel behind every 16-bit conv layer (sm_100a only).
 //
 // Same reference nodes as conv_tc.cu (Conv+BN+SiLU inside Ort::Session::Run,
-// src/inference/onnx_engine.cpp:577-585), but for the layers that dominate HBM
-// traffic — 3x3 stride-1 convs on the high-resolution maps — the nine filter
-// taps are NOT gathered nine times.  Per output tile of 8 (w) x 16 (h) pixels:
-//   * ONE 4-D TMA load per channel chunk brings the (8+2) x (16+2) input patch
-//     into shared memory (OOB zero fill == conv padding, image borders, ragged
-//     tiles), written in the 32/64/128-byte swizzle the tensor core expects;
-//   * the A operand of tap (r,s) is the SAME patch read through a UMMA
-//     descriptor whose start address is shifted by (r*10+s) pixels and whose
-//     8-row groups (one tile row = 8 pixels) are strided by the patch row pitch
-//     (SBO = 10 pixels).  The swizzle XOR is a function of the absolute smem
-//     address, so a shifted view stays consistent with what TMA wrote;
-//   * all 9 x Cin/16 MMAs of the tile accumulate into one of two TMEM buffers
-//     while the four epilogue warps drain the other one.
-// The CTA is persistent (grid = #SMs) and keeps the whole weight tensor
-// (9 x Cout x Cin 16-bit values) resident in shared memory, so per tile only the
-// patch (1.4x the tile's input) is read and the output written once.
+// src/inference/onnx_engine.cpp:577-585).  MODE 9 = 3x3 stride 1, MODE 2 = 3x3 stride 2, MODE 1 = 1x1, MODE 4 = layer 0 as a
+// 2x2 conv over the space-to-depth image (Geo<MODE> below).  The nine filter taps are NOT gathered nine times.  Per output
+// tile of 8 (w) x 16*sub (h) pixels:
+//   * ONE 4-D TMA load per channel chunk brings the (8+2) x (16*sub+2) input patch into shared memory (OOB zero fill ==
+//     conv padding, image borders, ragged tiles), written in the 32/64/128-byte swizzle the tensor core expects;
+//   * the A operand of tap (r,s) is the SAME patch read through a UMMA descriptor whose start address is shifted by
+//     (r*10+s) pixels and whose 8-row groups (one tile row = 8 pixels) are strided by the patch row pitch (SBO = 10 pixels).
+//     The swizzle XOR is a function of the absolute smem address, so a shifted view stays consistent with what TMA wrote;
+//   * all taps x Cin/16 MMAs of the tile accumulate into one slot of a ring of up to 8 TMEM accumulators while sixteen
+//     epilogue warps (two sets of eight on alternate tiles) drain earlier ones: +bias, SiLU, +residual, 16-bit / fp32 NHWC
+//     through swizzled staging tiles and bulk tensor stores (or 256-bit global stores on the 1x1 layers).
+// The CTA is persistent (grid = #SMs, 640 threads: 3 TMA producer warps, 1 MMA warp, 16 epilogue warps).  Weights are
+// either RESIDENT in shared memory for the whole launch (9 x Cout x Cin 16-bit values, or an N-split slice of them) or
+// STREAMED with the patches (each stage carries its channel chunk's [taps][nt][kc] weights), whichever persist_plan prices
+// cheaper; per tile only the patch (1.4x the tile's input) is read and the output written once.
+// Measured behaviour and the reasons for this shape: DESIGN.md 4.1, profiles/README_r02.md.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
