@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(tmp_path, fuse):
-    out = str(tmp_path / f"dets_fuse{fuse}.npz")
-    env = dict(os.environ, ZL_FUSE_HEAD=str(fuse))
+def _run(tmp_path, fuse, branches=8):
+    out = str(tmp_path / f"dets_fuse{fuse}_br{branches}.npz")
+    env = dict(os.environ, ZL_FUSE_HEAD=str(fuse), ZL_HEAD_BRANCHES=str(branches))
     subprocess.check_call([sys.executable, os.path.join(HERE, "headfused_child.py"), out], env=env, timeout=900)
     return np.load(out)
 
@@ -37,3 +37,15 @@ def test_fused_head_gives_the_unfused_chain_s_detections_bit_for_bit(built_lib, 
             assert a.shape == b.shape and np.array_equal(a, b), f"{name} frame {i}: fused and unfused detections differ"
             total += a.size // 40
     assert total > 50, f"the cases must produce detections to compare (got {total})"
+
+
+def test_head_branches_on_side_streams_do_not_change_results(built_lib, tmp_path):
+    """Batches of up to 8 frames run each level's Detect head on side streams next to the rest of the neck (a CUDA graph with
+    forks when captured).  Same kernels, same inputs: the detections must be byte-identical to the single-stream order."""
+    sys.path.insert(0, HERE)
+    import headfused_child
+    forked, serial = _run(tmp_path, 1, 8), _run(tmp_path, 1, 0)
+    for case in headfused_child.CASES:
+        name, n = case[0], case[4]
+        for i in range(n):
+            assert np.array_equal(forked[f"{name}/{i}"], serial[f"{name}/{i}"]), f"{name} frame {i}: side-stream head differs"

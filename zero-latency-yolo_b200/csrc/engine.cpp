@@ -318,6 +318,11 @@ int32_t Engine::alloc_lane(Lane& L)
     ZL_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
     ZL_CUDA(cudaEventCreate(&L.ev0));
     ZL_CUDA(cudaEventCreate(&L.ev1));
+    for (int i = 0; i < 6; ++i) {
+        ZL_CUDA(cudaStreamCreateWithFlags(&L.side[i], cudaStreamNonBlocking));
+        ZL_CUDA(cudaEventCreateWithFlags(&L.ev_dep[i], cudaEventDisableTiming));
+        ZL_CUDA(cudaEventCreateWithFlags(&L.ev_join[i], cudaEventDisableTiming));
+    }
     const int MB = cfg.max_batch, H = cfg.model_h, W = cfg.model_w, nc = md.nc, A = num_anchors;
     const int adt = cfg.precision == ZL_PRECISION_BF16 ? DT_BF16 : (cfg.precision == ZL_PRECISION_FP16 ? DT_F16 : DT_F32);
     const size_t es = adt == DT_F32 ? 4 : 2;
@@ -438,6 +443,12 @@ void Engine::free_lane(Lane& L)
     L.d_wire = nullptr; L.d_wire_off = nullptr; L.d_wmeta = nullptr; L.h_wire = nullptr; L.h_wire_off = nullptr; L.h_wmeta = nullptr;
     if (L.ev0) cudaEventDestroy(L.ev0);
     if (L.ev1) cudaEventDestroy(L.ev1);
+    for (int i = 0; i < 6; ++i) {
+        if (L.side[i]) cudaStreamDestroy(L.side[i]);
+        if (L.ev_dep[i]) cudaEventDestroy(L.ev_dep[i]);
+        if (L.ev_join[i]) cudaEventDestroy(L.ev_join[i]);
+        L.side[i] = nullptr; L.ev_dep[i] = nullptr; L.ev_join[i] = nullptr;
+    }
     if (L.stream) cudaStreamDestroy(L.stream);
     L.arena = nullptr; L.staging = nullptr; L.h_descs = nullptr; L.h_result = nullptr; L.h_frames = nullptr;
 }
@@ -546,28 +557,35 @@ int32_t Engine::build_ops(Lane& L, int B)
     { Op up; up.kind = Op::UPSAMPLE; up.name = "model.13.upsample"; up.x = h12; up.y = buf("CAT14").slice(0, c[3]);
       up.bytes = (double)up.y.pixels() * c[3] * up.y.esize() * 1.25; ops.push_back(up); }
     c2f(15, buf("CAT14"), "CAT15", "T15", buf("O3"), md.nh, false);
+    if (rc == ZL_OK) ops.back().record_ev = 0;                       // O3 ready: level 0's head may start
     conv("model.16.conv", buf("O3"), buf("CAT17").slice(0, c[2]), nullptr);
     c2f(18, buf("CAT17"), "CAT18", "T18", buf("O4"), md.nh, false);
+    if (rc == ZL_OK) ops.back().record_ev = 1;
     conv("model.19.conv", buf("O4"), buf("CAT20").slice(0, c[3]), nullptr);
     c2f(21, buf("CAT20"), "CAT21", "T21", buf("O5"), md.nh, false);
+    if (rc == ZL_OK) ops.back().record_ev = 2;
     const char* outs[3] = {"O3", "O4", "O5"};
     for (int l = 0; l < 3; ++l) {
         const std::string s = std::to_string(l), b = "model.22.cv2." + s;
         const bool fused = bf16 && fuse_stems && conv_by_name.count("model.22.stem." + s) != 0;
         if (fused) conv("model.22.stem." + s, buf(outs[l]), buf("HBC1_" + s), nullptr);
         else conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(0, md.cb), nullptr);
+        // head branches (fused stems only): stem + box branch on side stream 2l, class branch on 2l+1 after the stem
+        if (rc == ZL_OK && fused) { Op& o = ops.back(); o.side = 1 + 2 * l; o.wait_ev = l; o.record_ev = 3 + l; }
         conv(b + ".1.conv", buf("HBC1_" + s).slice(0, md.cb), buf("HB2_" + s), nullptr);
+        if (rc == ZL_OK && fused) ops.back().side = 1 + 2 * l;
         conv(b + ".2", buf("HB2_" + s), buf("BOX_" + s), nullptr);
-        if (rc == ZL_OK) ops.back().path = 3;
+        if (rc == ZL_OK) { ops.back().path = 3; if (fused) ops.back().side = 1 + 2 * l; }
     }
     for (int l = 0; l < 3; ++l) {
         const std::string s = std::to_string(l), b = "model.22.cv3." + s;
         const bool fused = bf16 && fuse_stems && conv_by_name.count("model.22.stem." + s) != 0;
         if (!fused) conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(md.cb, md.cc), nullptr);
         conv(b + ".1.conv", buf("HBC1_" + s).slice(md.cb, md.cc), buf("HC2_" + s), nullptr);
+        if (rc == ZL_OK && fused) { Op& o = ops.back(); o.side = 2 + 2 * l; o.wait_ev = 3 + l; }
         View cls = buf("CLS_" + s); cls.c = md.nc;
         conv(b + ".2", buf("HC2_" + s), cls, nullptr);
-        if (rc == ZL_OK) ops.back().path = 3;
+        if (rc == ZL_OK) { ops.back().path = 3; if (fused) ops.back().side = 2 + 2 * l; }
     }
     if (rc != ZL_OK) return rc;
     if (bf16) {
@@ -583,25 +601,25 @@ int32_t Engine::build_ops(Lane& L, int B)
             xb[l] = buf("HB2_" + s); xc[l] = buf("HC2_" + s);
         }
         if (head_fused_supported(wb, wc, xb, xc, md.nc)) {
-            Op op; op.kind = Op::HEAD_FUSED; op.name = "head.2+decode+filter"; op.path = 4;
+            Op op; op.kind = Op::HEAD_FUSED; op.name = "head.2+decode+filter"; op.path = 4; op.join = 1;
             ZL_TRY(head_fused_prepare(wb, wc, xb, xc, L.levels, md.nc, num_anchors, num_sms, &op.hf));
             op.flops = op.hf.flops; op.bytes = op.hf.bytes;
             ops.push_back(op);
         }
     }
     const double rawb = (double)B * (4 + md.nc) * num_anchors * 4;
-    { Op op; op.kind = Op::DECODE; op.name = "dfl_decode"; op.path = 1; op.bytes = (double)B * num_anchors * (64 + md.nc) * 4 + rawb; ops.push_back(op); }
+    { Op op; op.kind = Op::DECODE; op.name = "dfl_decode"; op.path = 1; op.join = 1; op.bytes = (double)B * num_anchors * (64 + md.nc) * 4 + rawb; ops.push_back(op); }
     { Op op; op.kind = Op::FILTER; op.name = "filter"; op.path = 1; op.bytes = rawb; ops.push_back(op); }
-    { Op op; op.kind = Op::DECODE_FILTER; op.name = "decode+filter"; op.path = 2; op.bytes = (double)B * num_anchors * md.nc * 4; ops.push_back(op); }
+    { Op op; op.kind = Op::DECODE_FILTER; op.name = "decode+filter"; op.path = 2; op.join = 1; op.bytes = (double)B * num_anchors * md.nc * 4; ops.push_back(op); }
     { Op op; op.kind = Op::NMS; op.name = "nms"; op.bytes = 0; ops.push_back(op); }
     L.ops[B] = std::move(ops);
     return ZL_OK;
 }
 
 // ------------------------------------------------------------------ execution
-int32_t Engine::launch_op(Lane& L, int B, const Op& op)
+int32_t Engine::launch_op(Lane& L, int B, const Op& op, cudaStream_t on)
 {
-    cudaStream_t st = L.stream;
+    cudaStream_t st = on ? on : L.stream;
     const bool bf16 = cfg.precision != ZL_PRECISION_FP32;   // any 16-bit tensor-core mode
     const bool f16 = cfg.precision == ZL_PRECISION_FP16;
     switch (op.kind) {
@@ -659,10 +677,26 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
     ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st));
     ZL_CUDA(cudaMemsetAsync(L.pb.header, 0, sizeof(uint32_t) * 4, st));
     const bool fused = head_is_fused(it->second);
+    // Small batches (the latency path): a level's Detect head — stem, box branch, class branch — runs on side streams as soon
+    // as the level's map exists, next to the rest of the neck, instead of queueing behind it: at b=1 every kernel is a few
+    // CTAs, so the branches really overlap (7 kernels leave the critical path).  Captured, this becomes a graph with forks.
+    static const int branch_max_batch = [] { const char* e = getenv("ZL_HEAD_BRANCHES"); return e ? atoi(e) : 8; }();
+    const bool branches = B <= branch_max_batch;
+    bool dirty[6] = {false, false, false, false, false, false};
     for (const Op& op : it->second) {
         if (!op_selected(op, want_raw, fused)) continue;
-        ZL_TRY(launch_op(L, B, op));
+        cudaStream_t s = (branches && op.side > 0) ? L.side[op.side - 1] : st;
+        if (branches && op.join) {
+            for (int k = 0; k < 6; ++k)
+                if (dirty[k]) { ZL_CUDA(cudaEventRecord(L.ev_join[k], L.side[k])); ZL_CUDA(cudaStreamWaitEvent(st, L.ev_join[k], 0)); dirty[k] = false; }
+        }
+        if (branches && op.side > 0 && op.wait_ev >= 0) ZL_CUDA(cudaStreamWaitEvent(s, L.ev_dep[op.wait_ev], 0));
+        ZL_TRY(launch_op(L, B, op, s));
+        if (branches && op.side > 0) dirty[op.side - 1] = true;
+        if (branches && op.record_ev >= 0) ZL_CUDA(cudaEventRecord(L.ev_dep[op.record_ev], s));
     }
+    for (int k = 0; k < 6; ++k)      // nothing may be left un-joined (a list without a join op)
+        if (dirty[k]) { ZL_CUDA(cudaEventRecord(L.ev_join[k], L.side[k])); ZL_CUDA(cudaStreamWaitEvent(st, L.ev_join[k], 0)); }
     if (cfg.preprocess_mode == ZL_PRE_LETTERBOX)      // non-parity mode: boxes back from the letterboxed model frame to the request frame
         ZL_TRY(launch_letterbox_unmap(st, B, L.pb.maxn, L.pb.header, L.pb.dets, L.d_descs, cfg.model_w, cfg.model_h, L.pb.cap));
     if (cfg.emit_wire) ZL_TRY(launch_wire_pack(st, B, L.pb, L.d_wmeta, L.d_wire, (uint32_t)std::min<size_t>(L.wire_cap, 0xffffffffu), L.d_wire_off));

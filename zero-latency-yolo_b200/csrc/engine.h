@@ -40,6 +40,9 @@ struct Op {
     // which passes run this op: 0 all; 1 raw-head passes only (zl_forward_raw); 2 hot path when the head is NOT fused;
     // 3 raw passes and the unfused hot path (the last 1x1 convs of the head); 4 hot path with the fused head kernel
     int32_t path = 0;
+    // head branches (small batches: the Detect head of a level runs on side streams next to the rest of the neck):
+    // side = 0 main stream, 1..6 side stream; wait_ev / record_ev index Lane::ev_dep (-1 none); join = wait for every side stream first
+    int32_t side = 0, wait_ev = -1, record_ev = -1, join = 0;
     View x, y, res, p1, p2, p3;
     bool has_res = false;
     double flops = 0, bytes = 0;
@@ -81,6 +84,9 @@ struct Lane {
     std::map<int, std::vector<Op>> ops;
     std::map<int, cudaGraphExec_t> graphs;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // head branches: level l -> side[2l] (stem, box branch), side[2l+1] (class branch)
+    cudaEvent_t ev_dep[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // 0..2: level l's input map is ready (main stream); 3..5: level l's stem is done
+    cudaEvent_t ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int resident_n[4] = {0, 0, 0, 0};
     bool resident_same[4] = {false, false, false, false};
     bool same_size = false;                     // the batch being launched: every frame already has the model's size (fast preprocess kernel)
@@ -142,7 +148,7 @@ private:
     void free_lane(Lane& L);
     int32_t build_ops(Lane& L, int B);
     int32_t run_ops(Lane& L, int B, bool with_d2h, bool want_raw = false);
-    int32_t launch_op(Lane& L, int B, const Op& op);
+    int32_t launch_op(Lane& L, int B, const Op& op, cudaStream_t on = nullptr);
     int32_t ensure_graph(Lane& L, int B);
     int32_t launch_batch(Lane& L, int B, bool want_raw = false);   // graph if enabled, else direct
     int graph_batch_for(int n) const;
