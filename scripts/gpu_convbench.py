@@ -10,10 +10,13 @@ from oracle import synth, yolov8_ref, zlw  # noqa: E402
 
 if __name__ == "__main__":
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    t = yolov8_ref.synthetic_model("n", 80, 0)
-    e = zlb200.Engine(640, 640, 80, "n", precision=zlb200.FP16, max_batch=64)
-    e.load_weights_blob(zlw.dumps(t, "n", 80))
-    e.upload_resident(0, list(synth.frames_structured(64, 640, 640)))
+    scale = sys.argv[2] if len(sys.argv) > 2 else "n"
+    batch = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+    t = yolov8_ref.synthetic_model(scale, 80, 0)
+    e = zlb200.Engine(640, 640, 80, scale, precision=zlb200.FP16, max_batch=batch)
+    e.load_weights_blob(zlw.dumps(t, scale, 80))
+    frames = list(synth.frames_structured(min(batch, 64), 640, 640))
+    e.upload_resident(0, [frames[i % len(frames)] for i in range(batch)])
     prof = e.profile(0, iters)
     print(sum(p["ms"] for p in prof))
     e.close()

@@ -187,6 +187,16 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
     walk_init(tw_, c.tile0 + set * c.tile_step, p.esets * c.tile_step, p.tiles_x, p.tiles_y);
     // the residual (and, transitively, everything this kernel overwrites) belongs to earlier kernels of the stream
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    // The residual of this warp's first item of the NEXT tile is prefetched into L1 one tile ahead (no registers held: the
+    // kernel is at its 96-register cap, and a register prefetch spilled and doubled the time of the residual layers): on
+    // the narrow residual layers a warp has one item per tile and no earlier point inside the tile to ask from.
+    TileWalk twn = tw_;                                      // the walk, one tile ahead
+    auto prefetch_first = [&](const TileWalk& t) {
+        if (!(res_fast && c2 < items)) return;
+        const int oxq = t.tx * kTW + tw, oyq = t.ty * p.sub * kTH + th + j0 * kTH;
+        if (oyq < p.H && oxq < p.W)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(res_g + (((size_t)t.n * p.H + oyq) * p.W + oxq) * p.rpitch + (k0 << 4)));
+    };
     for (int tile = c.tile0 + set * c.tile_step, tl = set; tile < p.num_tiles; tile += p.esets * c.tile_step, tl += p.esets, walk_next(tw_, p.tiles_x, p.tiles_y)) {
         const uint32_t acc = (uint32_t)tl & (uint32_t)(p.nacc - 1), aph = ((uint32_t)tl >> p.nacc_log2) & 1u;
         const int n = tw_.n, ty = tw_.ty, tx = tw_.tx;
@@ -195,18 +205,21 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
         // residual pixel of sub-tile 0 (64-bit once per tile; per item only 32-bit offsets are added)
         const __nv_bfloat16* res_px = has_res ? res_g + (((size_t)n * p.H + oy_base) * p.W + ox) * p.rpitch : nullptr;
         char* y_px = reinterpret_cast<char*>(c.y_g) + (((size_t)n * p.H + oy_base) * p.W + ox) * p.ypitch * (y_f32 ? 4 : 2);   // direct-store variant
-        // residual of this warp's FIRST item: issued before the accumulator wait, so its latency hides under the MMAs
-        uint4 r0 = make_uint4(0u, 0u, 0u, 0u), r1 = r0;
-        bool r_have = false;
+        // residual of this warp's FIRST item of the tile: requested before the accumulator wait, so its latency hides under the
+        // MMAs (and it was prefetched into L1 one tile ago); the residuals of the following items are requested one item ahead
+        uint4 rn0 = make_uint4(0u, 0u, 0u, 0u), rn1 = rn0;
+        bool rn_have = false;
         if (res_fast && c2 < items) {
             const int oy = oy_base + j0 * kTH;
             if (oy < p.H && ox < p.W && (FAST || (k0 << 4) + 16 <= cout_l)) {
                 const uint4* rp = reinterpret_cast<const uint4*>(res_px + j0 * res_jstride + (k0 << 4));
-                r0 = __ldg(rp);
-                r1 = __ldg(rp + 1);
-                r_have = true;
+                rn0 = __ldg(rp);
+                rn1 = __ldg(rp + 1);
+                rn_have = true;
             }
         }
+        walk_next(twn, p.tiles_x, p.tiles_y);
+        if (tile + p.esets * c.tile_step < p.num_tiles) prefetch_first(twn);
         {
             ZL_ST_BEGIN(t0);
             mbar_wait(c.bar_tfull + 8u * acc, aph, 5);
@@ -215,42 +228,51 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
         tc_fence_after();
         ZL_ST_BEGIN(t_epi);
         const uint32_t taddr = c.tmem_base + ((q * 32u) << 16) + acc * (uint32_t)p.acc_cols;
-        int j = j0, k = k0;                                  // (sub-tile, chunk) of the pair's first item
-        for (int item = c2; item < items; item += 2 * wq) {
-            // the pair: item and item + wq
-            int jb = j, kb = k + wq;
-            while (kb >= nchunk) { kb -= nchunk; ++jb; }
-            const bool have_b = item + wq < items;
-            uint32_t v[2][16];
-            tmem_ld16(taddr + (uint32_t)(j * p.nt + (k << 4)), v[0]);
-            if (have_b) tmem_ld16(taddr + (uint32_t)(jb * p.nt + (kb << 4)), v[1]);
+        // One item (32 px x 16 ch) per iteration, ROLLED: the body is ~300 instructions and has to stay inside the ~6 KB L0
+        // instruction cache of the scheduler (round-2 ncu: with two items unrolled per iteration stall_no_instruction was
+        // 2-4 per issue on the epilogue-bound layers).  The next item's accumulator columns (tcgen05.ld) and residual are
+        // requested before the current item is processed, so both latencies stay hidden as in the unrolled form.
+        int j = j0, k = k0;                                  // (sub-tile, chunk) of the current item
+        uint32_t vn[16];
+        if (c2 < items) tmem_ld16(taddr + (uint32_t)(j * p.nt + (k << 4)), vn);
+#pragma unroll 1
+        for (int item = c2; item < items; item += wq) {
+            uint32_t vc[16];
             {
                 ZL_ST_BEGIN(t0);
                 tmem_ld_wait();
                 ZL_ST_END(t0, st_c);
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1 && !have_b) break;
-                const int jj = h == 0 ? j : jb, c0 = (h == 0 ? k : kb) << 4;
+            for (int i = 0; i < 16; ++i) vc[i] = vn[i];
+            const uint4 r0 = rn0, r1 = rn1;
+            const bool r_have = rn_have;
+            int jn = j, kn = k + wq;                          // the next item of this warp in this tile
+            while (kn >= nchunk) { kn -= nchunk; ++jn; }
+            rn_have = false;
+            if (item + wq < items) {
+                tmem_ld16(taddr + (uint32_t)(jn * p.nt + (kn << 4)), vn);
+                if (res_fast) {
+                    const int oyn = oy_base + jn * kTH;
+                    if (oyn < p.H && ox < p.W && (FAST || (kn << 4) + 16 <= cout_l)) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res_px + jn * res_jstride + (kn << 4));
+                        rn0 = __ldg(rp);
+                        rn1 = __ldg(rp + 1);
+                        rn_have = true;
+                    }
+                }
+            }
+            {
+                const int jj = j, c0 = k << 4;
                 const int oy = oy_base + jj * kTH;
                 const bool in_px = oy < p.H && ox < p.W;
                 const bool in_img = in_px && c0 < cout_l;
-                if (h == 1 || item != c2) {                   // only the tile's first item was prefetched
-                    r_have = false;
-                    if (res_fast && in_px && (FAST || (in_img && c0 + 16 <= cout_l))) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res_px + jj * res_jstride + c0);
-                        r0 = __ldg(rp);
-                        r1 = __ldg(rp + 1);
-                        r_have = true;
-                    }
-                }
                 float a[16];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
-                    a[4 * i + 0] = __uint_as_float(v[h][4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(v[h][4 * i + 1]) + b4.y;
-                    a[4 * i + 2] = __uint_as_float(v[h][4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(v[h][4 * i + 3]) + b4.w;
+                    a[4 * i + 0] = __uint_as_float(vc[4 * i + 0]) + b4.x; a[4 * i + 1] = __uint_as_float(vc[4 * i + 1]) + b4.y;
+                    a[4 * i + 2] = __uint_as_float(vc[4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(vc[4 * i + 3]) + b4.w;
                 }
                 if (act) {
                     if (p.silu_tanh) {
@@ -381,9 +403,7 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
                     }
                 }
             }
-            // next pair: item + 2 * wq
-            k += 2 * wq;
-            while (k >= nchunk) { k -= nchunk; ++j; }
+            j = jn; k = kn;
         }
         // this warp is done reading the accumulator: hand it back to the MMA warp
         {
