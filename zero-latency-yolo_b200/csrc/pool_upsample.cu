@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(256)
 sppf_pool_smem_kernel(const T* __restrict__ a, T* __restrict__ p1, T* __restrict__ p2, T* __restrict__ p3,
                       int H, int W, int apitch, int p1pitch, int p2pitch, int p3pitch)
 {
+    // the next kernel of the stream (a tcgen05 conv launched with programmatic stream serialization) may start its prologue
+    // now; it still waits for this grid to complete (griddepcontrol.wait) before it touches this kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     constexpr int VN = Vec<T>::N, CG = 16, VPP = CG / VN;      // vectors per pixel handled by this CTA
     extern __shared__ float pool_sm[];
     float* A = pool_sm;
@@ -166,6 +169,9 @@ __global__ void __launch_bounds__(256)
 sppf_pool16_kernel(const uint16_t* __restrict__ a, uint16_t* __restrict__ p1, uint16_t* __restrict__ p2, uint16_t* __restrict__ p3,
                    int H, int W, int apitch, int p1pitch, int p2pitch, int p3pitch)
 {
+    // the next kernel of the stream (a tcgen05 conv launched with programmatic stream serialization) may start its prologue
+    // now; it still waits for this grid to complete (griddepcontrol.wait) before it touches this kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ uint4 pool16_sm[];
     const int npix = H * W, nv = npix * 2;                     // 16 channels per CTA = two vectors per pixel
     uint4* A = pool16_sm;
@@ -208,6 +214,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int xpitch, int ypitch)
 {
+    // the next kernel of the stream (a tcgen05 conv launched with programmatic stream serialization) may start its prologue
+    // now; it still waits for this grid to complete (griddepcontrol.wait) before it touches this kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // one thread copies one source vector to its four destination pixels: 32-bit index math, one load, four stores
     constexpr int VN = Vec<T>::N;
     const int cv = C / VN;

@@ -122,6 +122,9 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 preprocess_s2d_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs, int mw, int mh, uint4* __restrict__ out, int letterbox)
 {
+    // the next kernel of the stream (a tcgen05 conv launched with programmatic stream serialization) may start its prologue
+    // now; it still waits for this grid to complete (griddepcontrol.wait) before it touches this kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int f = blockIdx.y;
     const int W2 = mw >> 1, H2 = mh >> 1;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,6 +171,9 @@ template <bool F16>
 __global__ void __launch_bounds__(256)
 preprocess_s2d_same_size_kernel(const uint8_t* __restrict__ staging, const FrameDesc* __restrict__ descs, int mw, int mh, uint4* __restrict__ out)
 {
+    // the next kernel of the stream (a tcgen05 conv launched with programmatic stream serialization) may start its prologue
+    // now; it still waits for this grid to complete (griddepcontrol.wait) before it touches this kernel's output
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ uint16_t lut[256];
     {
         const float q = __fdiv_rn((float)threadIdx.x, 255.0f);
