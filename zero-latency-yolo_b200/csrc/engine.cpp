@@ -387,8 +387,11 @@ int32_t Engine::alloc_lane(Lane& L)
     L.pb.box_by_anchor = (float4*)p; p += box_b;
     L.pb.sorted_box = (float4*)p; p += box_b;
     L.pb.cand_count = (uint32_t*)p; p += cnt_b;
-    L.pb.header = (uint32_t*)p; p += hdr_b;
-    L.pb.dets = (DevDet*)p; p += det_b;
+    // result block: header {total, pad[3], cnt[MB], off[MB]} immediately followed by the records, so that the header and the
+    // inline window of records leave in ONE device-to-host copy (one graph node less on the latency path)
+    L.pb.header = (uint32_t*)p;
+    L.pb.dets = (DevDet*)(p + (size_t)(4 + 2 * MB) * 4);
+    p += hdr_b + det_b;
     L.pb.maxn = MB;
     L.pb.cap = det_cap;
     L.d_descs = (FrameDesc*)p; p += desc_b;
@@ -701,10 +704,9 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
         ZL_TRY(launch_letterbox_unmap(st, B, L.pb.maxn, L.pb.header, L.pb.dets, L.d_descs, cfg.model_w, cfg.model_h, L.pb.cap));
     if (cfg.emit_wire) ZL_TRY(launch_wire_pack(st, B, L.pb, L.d_wmeta, L.d_wire, (uint32_t)std::min<size_t>(L.wire_cap, 0xffffffffu), L.d_wire_off));
     if (with_d2h) {
-        // header (total, cnt[], off[]) and the first inline_dets records in two fixed-size copies
+        // header (total, cnt[], off[]) and the first inline_dets records in one fixed-size copy
         const size_t hdr = (size_t)(4 + 2 * L.pb.maxn) * 4;
-        ZL_CUDA(cudaMemcpyAsync(L.h_result, L.pb.header, hdr, cudaMemcpyDeviceToHost, st));
-        ZL_CUDA(cudaMemcpyAsync(L.h_result + hdr, L.pb.dets, (size_t)inline_dets(B) * sizeof(DevDet), cudaMemcpyDeviceToHost, st));
+        ZL_CUDA(cudaMemcpyAsync(L.h_result, L.pb.header, hdr + (size_t)inline_dets(B) * sizeof(DevDet), cudaMemcpyDeviceToHost, st));   // dets follow the header (alloc_lane)
         if (cfg.emit_wire) {           // the wire blocks: offsets and the inline window, fixed sizes (graph-capturable)
             ZL_CUDA(cudaMemcpyAsync(L.h_wire_off, L.d_wire_off, sizeof(uint32_t) * (B + 1), cudaMemcpyDeviceToHost, st));
             ZL_CUDA(cudaMemcpyAsync(L.h_wire, L.d_wire, wire_inline_bytes(B), cudaMemcpyDeviceToHost, st));

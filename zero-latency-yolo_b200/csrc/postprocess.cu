@@ -328,6 +328,8 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     __shared__ int s_large[2 * kMaxLargeSeg];
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // launched with programmatic stream serialization behind the decode kernel: everything above ran under its tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int n = (int)min(cand_count[f], (uint32_t)A);
     uint32_t* h_total = header;
     uint32_t* h_cnt = header + 4;
@@ -755,9 +757,15 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != last_dev) { ZL_TRY(nms_configure()); last_dev = dev; }
-    nms_kernel<<<n, kNmsThreads, smem, st>>>(A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, pb.box_by_anchor, pb.sorted_box, pb.cand_count,
-                                            pb.header, pb.dets, pb.maxn, pb.cap);
-    ZL_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n); cfg.blockDim = dim3(kNmsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    ZL_CUDA(cudaLaunchKernelEx(&cfg, nms_kernel, A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, (const float4*)pb.box_by_anchor, pb.sorted_box,
+                               (const uint32_t*)pb.cand_count, pb.header, pb.dets, pb.maxn, pb.cap));
     static const char* dbg = getenv("ZL_NMS_DEBUG");
     if (dbg) {
         long long h[8] = {0};
