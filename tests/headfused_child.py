@@ -19,6 +19,10 @@ CASES = [
     ("n4_416_b7", "n", 4, 416, 7, "bf16", 0.25, False),
     ("s80_fp16", "s", 80, 640, 2, "fp16", 0.25, False),
     ("n3_odd", "n", 3, 416, 3, "fp16", 0.25, False),
+    # class counts that take the rolled scan loops (neither 16 nor 80 padded classes): 2, 7 and 12 chunks of 16
+    ("n20_loop", "n", 20, 320, 2, "fp16", 0.25, False),
+    ("n100_loop", "n", 100, 320, 2, "bf16", 0.25, False),
+    ("n192_max", "n", 192, 320, 2, "fp16", 0.2, False),
 ]
 
 

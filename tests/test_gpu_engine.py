@@ -214,6 +214,20 @@ def test_fp16_mode_other_scales(built_lib, scale):
     e.close(); e2.close()
 
 
+def test_fp16_mode_with_100_classes(built_lib):
+    """nc >= 100 makes the Detect class branch 100 channels wide (ultralytics: max(ch0, min(nc, 100))), which is not a
+    multiple of 16: the 16-bit engine widens it with zero channels on the device.  Same contract as every other config."""
+    import zlb200
+    from conftest import synthetic_model
+    tensors, blob = synthetic_model("n", 100)
+    frames = list(synth.frames_structured(2, 320, 320, seed=41))
+    e = zlb200.Engine(320, 320, 100, "n", precision=zlb200.FP16, max_batch=2)
+    e.load_weights_blob(blob)
+    e.warmup(1)
+    _check_16bit(e, tensors, "n", 100, frames, 320, 320, "fp16", strict=True)
+    e.close()
+
+
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
 def test_16bit_results_do_not_depend_on_batch(built_lib, model_n80, prec):
     """Frames never share state: a frame's detections are bit-identical whether it runs alone, in a batch of 3

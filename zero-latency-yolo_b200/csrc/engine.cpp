@@ -61,6 +61,10 @@ int32_t Engine::build_model_def()
     md.nh = rep(3, depth[cfg.scale]);
     md.cb = std::max(16, std::max(md.c[2] / 4, 64));
     md.cc = std::max(md.c[2], std::min(md.nc, 100));
+    // 16-bit modes: the tensor-core kernels take channel counts in multiples of 16 (UMMA K step, 16-byte rows), and cc = 100
+    // for every model with >= 100 classes.  The class branch is widened with ZERO channels on the device: zero filter rows
+    // and bias give SiLU(0) = 0, zero filter columns in the consumer add exact zeros — the results do not change.
+    md.ccd = cfg.precision != ZL_PRECISION_FP32 ? round_up(md.cc, 16) : md.cc;
     return ZL_OK;
 }
 
@@ -164,9 +168,9 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
     const std::map<std::string, HostTensor>& host_w = pm.tensors;
 
     // the conv list of YOLOv8, names as ultralytics exports them
-    struct Spec { std::string name; int cin, cout, k, s, act; };
+    struct Spec { std::string name; int cin, cout, k, s, act, cin_dev, cout_dev; };     // *_dev: widths on the device (>= the file's: zero padding)
     std::vector<Spec> specs;
-    auto conv = [&](const std::string& n, int ci, int co, int k, int s, int act = 1) { specs.push_back({n, ci, co, k, s, act}); };
+    auto conv = [&](const std::string& n, int ci, int co, int k, int s, int act = 1) { specs.push_back({n, ci, co, k, s, act, ci, co}); };
     auto c2f = [&](int idx, int ci, int co, int n) {
         const int c = co / 2;
         const std::string b = "model." + std::to_string(idx);
@@ -204,8 +208,11 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
     for (int l = 0; l < 3; ++l) {
         const std::string b = "model.22.cv3." + std::to_string(l);
         conv(b + ".0.conv", c[2 + l], md.cc, 3, 1);
+        specs.back().cout_dev = md.ccd;
         conv(b + ".1.conv", md.cc, md.cc, 3, 1);
+        specs.back().cin_dev = md.ccd; specs.back().cout_dev = md.ccd;
         conv(b + ".2", md.cc, md.nc, 1, 1, 0);
+        specs.back().cin_dev = md.ccd;
     }
 
     // validate every tensor BEFORE the first device allocation: a bad or partially written file costs nothing
@@ -232,9 +239,9 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
             bi->second.data.size() != (size_t)s.cout)
             ZL_FAIL(ZL_MODEL_LOAD_FAILED, "shape mismatch for " + s.name);
         std::unique_ptr<ConvWeights> cw(new ConvWeights());
-        cw->name = s.name; cw->cin = s.cin; cw->cout = s.cout; cw->k = s.k; cw->stride = s.s; cw->act = s.act;
-        cw->cout_pad = round_up(s.cout, 16);
-        cw->ktot = s.k * s.k * s.cin;
+        cw->name = s.name; cw->cin = s.cin_dev; cw->cout = s.cout_dev; cw->k = s.k; cw->stride = s.s; cw->act = s.act;
+        cw->cout_pad = round_up(s.cout_dev, 16);
+        cw->ktot = s.k * s.k * s.cin_dev;
         std::vector<float> bias(cw->cout_pad, 0.f);
         std::copy(bi->second.data.begin(), bi->second.data.end(), bias.begin());
         ZL_CUDA(cudaMalloc(&cw->bias, bias.size() * 4));
@@ -246,7 +253,7 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
                 for (int ci = 0; ci < s.cin; ++ci)
                     for (int r = 0; r < s.k; ++r)
                         for (int q = 0; q < s.k; ++q)
-                            ws[((size_t)(r * s.k + q) * s.cin + ci) * cw->cout_pad + o] = W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q];
+                            ws[((size_t)(r * s.k + q) * s.cin_dev + ci) * cw->cout_pad + o] = W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q];
             ZL_CUDA(cudaMalloc(&cw->w_simt, ws.size() * 4));
             ZL_CUDA(cudaMemcpy(cw->w_simt, ws.data(), ws.size() * 4, cudaMemcpyHostToDevice));
         }
@@ -273,7 +280,7 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
                 for (int ci = 0; ci < s.cin; ++ci)
                     for (int r = 0; r < s.k; ++r)
                         for (int q = 0; q < s.k; ++q)
-                            wt[(size_t)o * cw->ktot + (size_t)(r * s.k + q) * s.cin + ci] = f16 ? f2h(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]) : f2bf(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]);
+                            wt[(size_t)o * cw->ktot + (size_t)(r * s.k + q) * s.cin_dev + ci] = f16 ? f2h(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]) : f2bf(W.data[(((size_t)o * s.cin + ci) * s.k + r) * s.k + q]);
             ZL_CUDA(cudaMalloc(&cw->w_tc, wt.size() * 2));
             ZL_CUDA(cudaMemcpy(cw->w_tc, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         }
@@ -281,7 +288,7 @@ int32_t Engine::prepare_weights(const void* blob, size_t len)
         new_convs.push_back(std::move(cw));
     }
     // fused Detect stems (16-bit modes): rows of cv2.l.0 followed by rows of cv3.l.0, one [cb + cc][9 * cin] tensor
-    if (bf16 && md.cb + md.cc <= 256) {
+    if (bf16 && md.cb + md.ccd <= 256) {
         for (int l = 0; l < 3; ++l) {
             const std::string sl = std::to_string(l);
             const ConvWeights* a = new_by_name["model.22.cv2." + sl + ".0.conv"];
@@ -357,8 +364,8 @@ int32_t Engine::alloc_lane(Lane& L)
         const std::string s = std::to_string(l);
         // HBC1 = [ cv2.l.0 output (cb) | cv3.l.0 output (cc) ]: the two Detect stems read the same map, so in the 16-bit modes
         // they run as ONE conv of width cb + cc (one wide MMA costs far less than two narrow ones: umma_probe)
-        add("HBC1_" + s, hh, ww, md.cb + md.cc, adt); add("HB2_" + s, hh, ww, md.cb, adt); add("BOX_" + s, hh, ww, 64, DT_F32);
-        add("HC2_" + s, hh, ww, md.cc, adt); add("CLS_" + s, hh, ww, ncp, DT_F32);
+        add("HBC1_" + s, hh, ww, md.cb + md.ccd, adt); add("HB2_" + s, hh, ww, md.cb, adt); add("BOX_" + s, hh, ww, 64, DT_F32);
+        add("HC2_" + s, hh, ww, md.ccd, adt); add("CLS_" + s, hh, ww, ncp, DT_F32);
     }
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t total = 0;
@@ -583,8 +590,8 @@ int32_t Engine::build_ops(Lane& L, int B)
     for (int l = 0; l < 3; ++l) {
         const std::string s = std::to_string(l), b = "model.22.cv3." + s;
         const bool fused = bf16 && fuse_stems && conv_by_name.count("model.22.stem." + s) != 0;
-        if (!fused) conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(md.cb, md.cc), nullptr);
-        conv(b + ".1.conv", buf("HBC1_" + s).slice(md.cb, md.cc), buf("HC2_" + s), nullptr);
+        if (!fused) conv(b + ".0.conv", buf(outs[l]), buf("HBC1_" + s).slice(md.cb, md.ccd), nullptr);
+        conv(b + ".1.conv", buf("HBC1_" + s).slice(md.cb, md.ccd), buf("HC2_" + s), nullptr);
         if (rc == ZL_OK && fused) { Op& o = ops.back(); o.side = 2 + 2 * l; o.wait_ev = 3 + l; }
         View cls = buf("CLS_" + s); cls.c = md.nc;
         conv(b + ".2", buf("HC2_" + s), cls, nullptr);

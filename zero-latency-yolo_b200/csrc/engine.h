@@ -26,7 +26,8 @@ struct ModelDef {
     int c[5] = {0, 0, 0, 0, 0};       // widths of the five stages
     int n[4] = {1, 2, 2, 1};          // backbone C2f repeats
     int nh = 1;                       // head C2f repeats
-    int cb = 64, cc = 64;             // Detect box / class branch widths
+    int cb = 64, cc = 64;             // Detect box / class branch widths (as in the model file)
+    int ccd = 64;                     // class branch width ON THE DEVICE: cc, padded to a multiple of 16 in the 16-bit modes (zero channels)
 };
 
 struct Op {
