@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libzl_b200.so")
+LIB_PATH = os.environ.get("ZL_B200_LIB") or os.path.join(_PKG, "lib", "libzl_b200.so")     # override: A/B runs against another build
 TEST_LIB_PATH = os.path.join(_PKG, "lib", "libzl_b200_test.so")     # engine objects + unit-test / measurement hooks (include/zl_b200_test.h)
 
 OK, INVALID_ARGUMENT, NOT_INITIALIZED = 0, 2, 3
