@@ -10,9 +10,10 @@ from oracle import synth, yolov8_ref, zlw  # noqa: E402
 
 if __name__ == "__main__":
     batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    t = yolov8_ref.synthetic_model("n", 80, 0)
-    e = zlb200.Engine(640, 640, 80, "n", precision=zlb200.FP16, max_batch=batch, use_graph=0)
-    e.load_weights_blob(zlw.dumps(t, "n", 80))
+    scale = sys.argv[2] if len(sys.argv) > 2 else "n"
+    t = yolov8_ref.synthetic_model(scale, 80, 0)
+    e = zlb200.Engine(640, 640, 80, scale, precision=zlb200.FP16, max_batch=batch, use_graph=0)
+    e.load_weights_blob(zlw.dumps(t, scale, 80))
     frames = list(synth.frames_structured(batch, 640, 640))
     e.upload_resident(0, frames)
     ms, launches, dets = e.run_resident(1, 2)

@@ -1000,11 +1000,16 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.cps = o.cps; p.nst = o.nst;
     p.wstream = o.wstream; p.nacc = o.nacc; p.acc_cols = o.acc_cols;
     p.esets = (o.num_tiles * o.nsplit > grid_for(o, num_sms)) ? 2 : 1;      // more than one tile per CTA: two alternating sets
-    // 256-bit global stores instead of staged bulk stores: measured (profiles/README_r02.md) a few us faster on the 1x1 layers
-    // with 16-bit outputs, slower on fp32 outputs and on layer 0 -> default 1 = those layers only; 0 = never; 2 = wherever possible
-    static const int direct_env = [] { const char* e = getenv("ZL_EPI_DIRECT"); return e ? atoi(e) : 1; }();
+    // 256-bit global stores instead of staged bulk stores.  Measured (profiles/README_r02.md): a few us faster on the 1x1 layers
+    // with 16-bit outputs, slower on fp32 outputs and on layer 0; and bulk stores of 32-byte rows into a concat slice that starts
+    // INSIDE a 128-byte line are 1.3x slower than the same stores into an aligned slice (YOLOv8m, c = 96: 509 vs 386 us), which
+    // direct stores are not.  Default 3 = 16-bit outputs of 1x1 layers and of slices off a 128-byte boundary; 1 = 1x1 layers
+    // only; 2 = wherever aligned to 32 bytes; 0 = never.
+    static const int direct_env = [] { const char* e = getenv("ZL_EPI_DIRECT"); return e ? atoi(e) : 3; }();
     const bool direct_ok = (o.ypitch * (o.y_f32 ? 4 : 2)) % 32 == 0 && (reinterpret_cast<uintptr_t>(o.y) & 31) == 0;
-    p.direct_store = (direct_ok && (direct_env == 2 || (direct_env == 1 && o.mode == 1 && !o.y_f32))) ? 1 : 0;
+    const bool slice_off_line = (reinterpret_cast<uintptr_t>(o.y) & 127) != 0;     // output slice starts inside a 128-byte line
+    p.direct_store = (direct_ok && (direct_env == 2 || (direct_env == 1 && o.mode == 1 && !o.y_f32) ||
+                                    (direct_env == 3 && !o.y_f32 && (o.mode == 1 || slice_off_line)))) ? 1 : 0;
     p.epi_variant = 6;
     if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC")) {
         const int fmt = o.f16 ? 3 : 0;
