@@ -317,6 +317,27 @@ def test_post_threshold_edges(eng):
         _check_post(eng, raw, 640, 480, 0.5, iou)
 
 
+@pytest.mark.parametrize("frames,nc,conf", [(20, 80, 0.05), (40, 80, 0.05), (24, 1, 0.3), (36, 3, 0.2), (9, 2, 0.01)])
+def test_post_frames_split_over_cluster(eng, frames, nc, conf):
+    """N1 with a frame's classes dealt to the 2 / 4 / 8 CTAs of a thread-block cluster (launch_nms picks the cluster size
+    from the batch: 8 up to 16 frames, 4 up to 32, 2 up to 72).  Few classes leave ranks without any candidate; one class
+    puts the whole frame on one rank.  Bit-exact against the oracle like every other N1 case."""
+    raw = synth.stress_head(frames, nc, 8400 if nc > 3 else 2100, seed=900 + frames)
+    got = eng.decode_nms(raw, 640, 640, conf, 0.45)
+    ref, counts = oracle_c.postprocess_batch(raw, 640, 640, conf, 0.45)
+    assert [len(g) for g in got] == list(counts)
+    assert np.array_equal(np.concatenate(got).view(np.uint8), ref.view(np.uint8))
+
+
+def test_post_split_with_dominant_class(eng):
+    """One class holds most candidates (the shape of the bench frames: an 800-candidate class next to many small ones)."""
+    raw = synth.stress_head(5, 80, 8400, seed=77)
+    raw[:, 4 + 17, ::3] = np.maximum(raw[:, 4 + 17, ::3], 0.6)         # class 17 wins a third of the anchors
+    _check_post(eng, raw, 640, 640, 0.3, 0.45)
+    raw = synth.stress_head_adversarial(20, 80, 8400, seed=78)
+    _check_post(eng, raw, 640, 640, 0.3, 0.5)
+
+
 def test_post_full_cfg5_batch128(eng):
     # BASELINE.json config 5 at full size: A=8400, nc=80, conf 0.01, batch 128
     raw = synth.stress_head(128, 80, 8400, seed=42)

@@ -15,6 +15,8 @@
 #include <cfloat>
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include <cstdio>
 #include <cstdlib>
 
@@ -274,6 +276,7 @@ decode_filter_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2,
 // ============================================================= N1: NMS
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxLargeSeg = 512;
+constexpr int kNmsSplitMin = 256;     // frames with fewer candidates are not split over a cluster's CTAs
 constexpr int kWholeCtaSeg = 512;     // class segments larger than this are swept by all 1024 threads, one segment at a time     // queue slots for class segments with more than 32 candidates
 
 // calculateIoU (onnx_engine.cpp:881-909) with IEEE single ops in the reference's order.
@@ -293,9 +296,10 @@ __device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
 
 // Phase timestamps of the slowest-looking CTA (debug aid, ZL_NMS_DEBUG=1 prints them): written by thread 0 of the CTA
 // whose frame index is g_nms_dbg_frame.
-__device__ long long g_nms_dbg[8];
-__device__ int g_nms_dbg_frame = 0;
-#define ZL_NMS_STAMP(k) do { if (tid == 0 && f == g_nms_dbg_frame) g_nms_dbg[k] = clock64(); } while (0)
+__device__ long long g_nms_dbg[8][10];      // [cluster rank][0..5 phase stamps, 6 entry, 7 candidates of the rank, 8/9 globaltimer at entry / exit]
+__device__ int g_nms_dbg_frame = -1;
+__device__ __forceinline__ long long nms_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define ZL_NMS_STAMP(k) do { if (tid == 0 && f == g_nms_dbg_frame) g_nms_dbg[rank][k] = clock64(); } while (0)
 
 // `calculateIoU(a, b) > thr` (onnx_engine.cpp:871,881-909), decided EXACTLY but usually without the IEEE division: boxes that
 // do not overlap have IoU 0 (never > thr for thr >= 0); otherwise a reciprocal estimate of inter/union settles every case
@@ -315,7 +319,12 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
     return __fdiv_rn(inter, uni) > thr;
 }
 
-// One CTA per frame.  Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | scan scratch.
+// One CTA per frame, or — launched as thread-block CLUSTERS of S CTAs (launch_nms) — S CTAs per frame, each owning a
+// contiguous range of classes.  Classes never interact in applyNMS (onnx_engine.cpp:856-875 compares class ids before any
+// IoU), so the ranks sort, sweep and compact their own candidates independently; they only exchange their kept counts
+// (distributed shared memory) so that the frame's detections land contiguously in (class asc, confidence desc) order.
+// The class ranges are cut where the running candidate count crosses multiples of n/S: balanced up to one class.
+// Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | sorted boxes (the class histogram of the split lives there first).
 __global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
            float4* __restrict__ sorted_box, const uint32_t* __restrict__ cand_count, uint32_t* __restrict__ header,
@@ -323,32 +332,88 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
 {
     extern __shared__ __align__(16) uint8_t nms_smem[];
     __shared__ uint32_t s_warp_tot[32];
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_base, s_mine, s_lower;
+    __shared__ uint32_t s_xkept[8], s_xbase;                  // written by the other ranks of the cluster
     __shared__ int s_nlarge, s_qhead, s_gq[8], s_nk[8], s_kidx[8][32];
     __shared__ int s_large[2 * kMaxLargeSeg];
-    const int f = blockIdx.x;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int S = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int f = blockIdx.x / S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0 && f == g_nms_dbg_frame) { g_nms_dbg[rank][6] = clock64(); g_nms_dbg[rank][8] = nms_gtime(); }
     // launched with programmatic stream serialization behind the decode kernel: everything above ran under its tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int n = (int)min(cand_count[f], (uint32_t)A);
+    const int n_all = (int)min(cand_count[f], (uint32_t)A);
     uint32_t* h_total = header;
     uint32_t* h_cnt = header + 4;
     uint32_t* h_off = header + 4 + maxn;
-    if (n == 0) {
-        if (tid == 0) { h_cnt[f] = 0; h_off[f] = 0; }
+    // few candidates: the split (histogram + two cluster barriers) costs more than it saves; rank 0 does the frame alone.
+    // n_all is the same in every rank, so the whole cluster takes the same branch (no rank waits on a barrier alone).
+    const bool split = S > 1 && n_all > kNmsSplitMin;
+    if (n_all == 0 || (!split && rank != 0)) {
+        if (tid == 0 && rank == 0) { h_cnt[f] = 0; h_off[f] = 0; }
         return;
+    }
+    uint64_t* gkeys = keys_g + (size_t)f * key_pitch;
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(nms_smem);
+    volatile uint32_t* removed = reinterpret_cast<volatile uint32_t*>(nms_smem + (size_t)key_cap_smem * 8);
+    int n = n_all;
+    if (split) {
+        // every rank must be running before anyone writes into its shared memory: arrive now, wait right before the exchange
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        // launch_nms only forms clusters when every frame's keys fit the smem sort buffer (key_cap_smem >= pow2(A))
+        uint32_t* hist = reinterpret_cast<uint32_t*>(nms_smem + (size_t)key_cap_smem * 8 + (size_t)(((((A + 31) >> 5) * 4) + 15) & ~15));
+        for (int i = tid; i < kMaxClasses; i += kNmsThreads) hist[i] = 0u;
+        if (tid == 0) { s_mine = 0u; s_lower = 0u; }
+        __syncthreads();
+        for (int i = tid; i < n_all; i += kNmsThreads) atomicAdd(&hist[key_class(gkeys[i])], 1u);
+        __syncthreads();
+        // exclusive prefix over the class bins, in place (thread t owns bins 4t .. 4t+3)
+        static_assert(kMaxClasses == 4 * kNmsThreads, "one uint4 of class bins per thread");
+        const uint4 hc = reinterpret_cast<const uint4*>(hist)[tid];
+        const uint32_t mine4 = hc.x + hc.y + hc.z + hc.w;
+        uint32_t x = mine4;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) s_warp_tot[warp] = x;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp_tot[w];
+        const uint32_t e0 = woff + x - mine4;
+        reinterpret_cast<uint4*>(hist)[tid] = make_uint4(e0, e0 + hc.x, e0 + hc.x + hc.y, e0 + hc.x + hc.y + hc.z);
+        __syncthreads();
+        // this rank's candidates -> smem, any order (the sort follows)
+        for (int i0 = 0; i0 < n_all; i0 += kNmsThreads) {
+            const int i = i0 + tid;
+            uint64_t k = 0;
+            bool mine = false, lower = false;
+            if (i < n_all) {
+                k = gkeys[i];
+                const int r = min(S - 1, (int)((hist[key_class(k)] * (uint32_t)S) / (uint32_t)n_all));   // owner of the class: where its first candidate falls
+                mine = r == rank;
+                lower = r < rank;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, mine), ball = __ballot_sync(0xffffffffu, lower);
+            uint32_t wbase = 0;
+            if (lane == 0 && ball != 0u) atomicAdd(&s_lower, (uint32_t)__popc(ball));      // candidates of the ranks below: this rank's slot in the global box scratch
+            if (lane == 0 && bal != 0u) wbase = atomicAdd(&s_mine, (uint32_t)__popc(bal));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (mine) skeys[wbase + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = k;
+        }
+        __syncthreads();
+        n = (int)s_mine;
     }
     int P = 1;
     while (P < n) P <<= 1;
-    uint64_t* gkeys = keys_g + (size_t)f * key_pitch;
     // keys live in smem when they fit, else they are sorted in place in global memory
     // (each frame's slice holds key_pitch = pow2 >= A slots, so the +inf padding is real)
     const bool in_smem = P <= key_cap_smem;
-    uint64_t* skeys = reinterpret_cast<uint64_t*>(nms_smem);
-    volatile uint32_t* removed = reinterpret_cast<volatile uint32_t*>(nms_smem + (size_t)key_cap_smem * 8);
     const int nwords = (n + 31) >> 5;
 
-    if (in_smem) {
+    if (split) {
+        for (int i = n + tid; i < P; i += kNmsThreads) skeys[i] = ~0ull;
+    } else if (in_smem) {
         for (int i = tid; i < P; i += kNmsThreads) skeys[i] = i < n ? gkeys[i] : ~0ull;
     } else {
         for (int i = n + tid; i < P; i += kNmsThreads) gkeys[i] = ~0ull;
@@ -411,7 +476,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     // dependent box reads, so its latency is the box read latency), else the global scratch
     float4* sb = (n <= box_cap_smem)
                      ? reinterpret_cast<float4*>(nms_smem + (size_t)key_cap_smem * 8 + (size_t)(((((A + 31) >> 5) * 4) + 15) & ~15))
-                     : sorted_box + (size_t)f * A;
+                     : sorted_box + (size_t)f * A + (split ? s_lower : 0u);
     for (int i = tid; i < n; i += kNmsThreads) sb[i] = box_by_anchor[(size_t)f * A + key_anchor(K[i])];
     __syncthreads();
 
@@ -602,12 +667,34 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
         kept_total += tot;
         __syncthreads();
     }
-    if (tid == 0) {
-        s_base = atomicAdd(h_total, kept_total);
-        h_cnt[f] = kept_total;
-        h_off[f] = s_base;
+    if (!split) {
+        if (tid == 0) {
+            s_base = atomicAdd(h_total, kept_total);
+            h_cnt[f] = kept_total;
+            h_off[f] = s_base;
+        }
+        __syncthreads();
+    } else {
+        // every rank tells every rank how many it kept; rank 0 reserves the frame's slice and tells everyone where it starts
+        asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+        if (tid < S) *cl.map_shared_rank(&s_xkept[rank], tid) = kept_total;
+        cl.sync();
+        if (rank == 0 && tid == 0) {
+            uint32_t total = 0;
+            for (int r = 0; r < S; ++r) total += s_xkept[r];
+            const uint32_t b = atomicAdd(h_total, total);
+            h_cnt[f] = total;
+            h_off[f] = b;
+            for (int r = 0; r < S; ++r) *cl.map_shared_rank(&s_xbase, r) = b;
+        }
+        cl.sync();                                            // no remote access after this barrier: ranks may exit independently
+        if (tid == 0) {
+            uint32_t b = s_xbase;
+            for (int r = 0; r < rank; ++r) b += s_xkept[r];
+            s_base = b;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const uint32_t base = s_base;
     uint32_t running = 0;
     for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
@@ -632,6 +719,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
         __syncthreads();
     }
     ZL_NMS_STAMP(5);
+    if (tid == 0 && f == g_nms_dbg_frame) { g_nms_dbg[rank][7] = n; g_nms_dbg[rank][9] = nms_gtime(); }
 }
 
 int g_nms_smem_keys = 0;   // key capacity (elements) of the smem sort buffer
@@ -741,39 +829,67 @@ int32_t nms_configure()
     return ZL_OK;
 }
 
+// CTAs per frame (cluster size) for a batch of n frames: as many as keep every cluster resident at once.  One CTA owns
+// an SM (200 KB of shared memory), a cluster lives inside one GPC (16+ usable SMs on B200).  ZL_NMS_SPLIT=1/2/4/8 overrides.
+static int nms_split_for(int n, bool keys_fit_smem)
+{
+    if (!keys_fit_smem) return 1;                  // global-memory sort works in place on the frame's key slice: one CTA only
+    static const int forced = [] { const char* e = getenv("ZL_NMS_SPLIT"); return e ? atoi(e) : 0; }();
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+    return n <= 16 ? 8 : (n <= 32 ? 4 : (n <= 72 ? 2 : 1));
+}
+
 int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb)
 {
     // smem plan: keys (only as many as can ever be needed) + removed bitmask (A bits)
     int key_cap = 1;
     while (key_cap < A) key_cap <<= 1;
     if (key_cap > 16384) key_cap = 0;              // too many to sort in smem -> sort in global memory
+    const int split = nms_split_for(n, key_cap != 0);
     const size_t mask_bytes = ((size_t)ceil_div(A, 32) * 4 + 15) & ~(size_t)15;
     size_t smem = (size_t)key_cap * 8 + mask_bytes;
     if (smem > 200 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "nms: anchor count too large for the suppression bitmask");
     int box_cap = (int)((200 * 1024 - smem) / 16);
     if (box_cap > A) box_cap = A;
-    smem += (size_t)box_cap * 16;
+    size_t tail = (size_t)box_cap * 16;
+    if (split > 1 && tail < (size_t)kMaxClasses * 4) tail = (size_t)kMaxClasses * 4;      // the class histogram of the split
+    smem += tail;
     static thread_local int last_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != last_dev) { ZL_TRY(nms_configure()); last_dev = dev; }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n); cfg.blockDim = dim3(kNmsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(n * split); cfg.blockDim = dim3(kNmsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     static const bool use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
-    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+    if (use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (split > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)split; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
     ZL_CUDA(cudaLaunchKernelEx(&cfg, nms_kernel, A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, (const float4*)pb.box_by_anchor, pb.sorted_box,
                                (const uint32_t*)pb.cand_count, pb.header, pb.dets, pb.maxn, pb.cap));
     static const char* dbg = getenv("ZL_NMS_DEBUG");
     if (dbg) {
-        long long h[8] = {0};
+        // debug aid: phase stamps of frame <ZL_NMS_DEBUG> of the PREVIOUS launch on this stream (the frame index is armed below)
+        long long h[8][10];
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(h, g_nms_dbg, sizeof(h));
-        fprintf(stderr, "nms frame %d phases (cycles): sort %lld gather %lld small-seg %lld large-seg %lld compact %lld\n", atoi(dbg), h[1] - h[0], h[2] - h[1], h[3] - h[2],
-                h[4] - h[3], h[5] - h[4]);
         const int fr = atoi(dbg);
+        int cur = -1;
+        cudaMemcpyFromSymbol(&cur, g_nms_dbg_frame, sizeof(int));
+        if (cur == fr)
+            for (int r = 0; r < split; ++r)
+                fprintf(stderr, "nms frame %d rank %d/%d: cand %lld | cycles: load/split %lld sort %lld gather %lld small-seg %lld large-seg %lld compact+exchange %lld | wall %lld ns, start +%lld ns\n",
+                        fr, r, split, h[r][7], h[r][0] - h[r][6], h[r][1] - h[r][0], h[r][2] - h[r][1], h[r][3] - h[r][2], h[r][4] - h[r][3], h[r][5] - h[r][4],
+                        h[r][9] - h[r][8], h[r][8] - h[0][8]);
         cudaMemcpyToSymbol(g_nms_dbg_frame, &fr, sizeof(int));
     }
     return ZL_OK;
