@@ -336,6 +336,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     __shared__ uint32_t s_xkept[8], s_xbase;                  // written by the other ranks of the cluster
     __shared__ int s_nlarge, s_qhead, s_gq[8], s_nk[8], s_kidx[8][32];
     __shared__ int s_large[2 * kMaxLargeSeg];
+    __shared__ uint32_t s_col[2 + 2 * 8][32];                  // suppression-matrix columns: two buffers for the CTA team, two per group
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
     const int S = (int)cl.num_blocks(), rank = (int)cl.block_rank();
@@ -527,33 +528,55 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
         const int nlarge = min(s_nlarge, kMaxLargeSeg);
         const bool overflow = s_nlarge > kMaxLargeSeg;                      // more large segments than queue slots: handled below
         const int grp = warp >> 2, gtid = tid & 127;                        // 8 groups of 128 threads
-        // Very large segments (one class holding hundreds of candidates) first, one at a time, with the WHOLE CTA sweeping:
+        // Blocked greedy sweep with bitmask suppression, exact.  A segment is walked in blocks of 32 candidates.  By the time a
+        // block is reached every candidate in it has been tested against the kept boxes of ALL earlier blocks, so
+        //  (a) the block resolves internally from its 32 x 32 suppression matrix: column t = the ballot of "box t suppresses
+        //      box i" over the lanes i > t.  The matrix does not depend on what earlier blocks removed, so the team computes
+        //      the NEXT block's columns (one or eight per warp) next to the current block's sweep; the resolving warp then
+        //      follows the reference's serial chain over the kept boxes with one shuffle + two bit operations per link
+        //      (it cost a shuffled box + an IoU, ~150 cycles, per link when the tests were made inside the chain);
+        //  (b) all threads of the team test the later candidates against the block's kept boxes in parallel.
+        // Very large segments (one class holding hundreds of candidates) first, one at a time, with the WHOLE CTA as the team:
         // a 128-thread group would leave the other seven idle behind it.
+        auto block_columns = [&](int b0, int e0, int t_first, int t_count, uint32_t* col) {
+            const int i = b0 + lane;
+            const bool valid = i < e0;
+            const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = t_first; t < t_first + t_count; ++t) {
+                bool sup = false;
+                if (b0 + t < e0) {                                           // warp-uniform
+                    const float4 bt = sb[b0 + t];
+                    sup = valid && t < lane && iou_gt(bt, bi, iou_thr);      // strict '>' (onnx_engine.cpp:871)
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0) col[t] = bal;
+            }
+        };
+        auto block_resolve = [&](int b0, int e0, const uint32_t* col, int* kidx, int* nk_out) {      // one warp
+            const int i = b0 + lane;
+            const bool valid = i < e0;
+            const bool alive = valid && (((removed[i >> 5] >> (i & 31)) & 1u) == 0u);
+            uint32_t cur = __ballot_sync(0xffffffffu, alive);                // alive, not yet decided
+            const uint32_t mycol = col[lane];
+            uint32_t kept = 0u;
+            while (cur != 0u) {
+                const int t = __ffs(cur) - 1;                                // next candidate in sorted order that is not removed
+                kept |= 1u << t;
+                cur &= ~(1u << t);
+                cur &= ~__shfl_sync(0xffffffffu, mycol, t);                  // everything box t suppresses
+            }
+            if (alive && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
+            if ((kept >> lane) & 1u) kidx[__popc(kept & ((1u << lane) - 1u))] = i;
+            if (lane == 0) *nk_out = __popc(kept);
+        };
         for (int q = 0; q < nlarge; ++q) {
             const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
             if (e0 - s0 <= kWholeCtaSeg) continue;
-            for (int b0 = s0; b0 < e0; b0 += 32) {
-                if (warp == 0) {
-                    const int i = b0 + lane;
-                    const bool valid = i < e0;
-                    const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const bool alive = valid && (((removed[i >> 5] >> (i & 31)) & 1u) == 0u);
-                    uint32_t cur = __ballot_sync(0xffffffffu, alive);
-                    uint32_t kept = 0u;
-                    while (cur != 0u) {
-                        const int t = __ffs(cur) - 1;
-                        kept |= 1u << t;
-                        cur &= ~(1u << t);
-                        float4 bt;
-                        bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
-                        bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
-                        const bool sup = ((cur >> lane) & 1u) && iou_gt(bt, bi, iou_thr);
-                        cur &= ~__ballot_sync(0xffffffffu, sup);
-                    }
-                    if (alive && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
-                    if ((kept >> lane) & 1u) s_kidx[0][__popc(kept & ((1u << lane) - 1u))] = i;
-                    if (lane == 0) s_nk[0] = __popc(kept);
-                }
+            block_columns(s0, e0, warp, 1, s_col[0]);                        // 32 warps: one column each
+            __syncthreads();
+            int buf = 0;
+            for (int b0 = s0; b0 < e0; b0 += 32, buf ^= 1) {
+                if (warp == 0) block_resolve(b0, e0, s_col[buf], s_kidx[0], &s_nk[0]);
                 __syncthreads();
                 const int nk = s_nk[0];
                 if (nk > 0) {
@@ -565,6 +588,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
                         }
                     }
                 }
+                if (b0 + 32 < e0) block_columns(b0 + 32, e0, warp, 1, s_col[buf ^ 1]);
                 __syncthreads();
             }
         }
@@ -579,34 +603,13 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
             if (q >= nlarge) break;
             const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
             if (e0 - s0 > kWholeCtaSeg) continue;                          // done above by the whole CTA
-            // Blocked greedy sweep, exact: the segment is walked in blocks of 32 candidates.  By the time a block is reached
-            // every candidate in it has been tested against the kept boxes of ALL earlier blocks, so (a) the group's first
-            // warp resolves the block internally with boxes in registers (one shuffle + one IoU per link, like phase 1) and
-            // (b) all 128 threads then test the later candidates against the block's kept boxes in parallel.  The serial
-            // chain costs ~100 cycles per kept box instead of two named barriers (~800 cycles): the round-2 profile had this
-            // loop at 220 us on frames with a 800-candidate class.
-            for (int b0 = s0; b0 < e0; b0 += 32) {
-                if ((gtid >> 5) == 0) {
-                    const int i = b0 + lane;
-                    const bool valid = i < e0;
-                    const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const bool alive = valid && (((removed[i >> 5] >> (i & 31)) & 1u) == 0u);
-                    uint32_t cur = __ballot_sync(0xffffffffu, alive);            // alive, not yet decided
-                    uint32_t kept = 0u;
-                    while (cur != 0u) {
-                        const int t = __ffs(cur) - 1;
-                        kept |= 1u << t;
-                        cur &= ~(1u << t);
-                        float4 bt;
-                        bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
-                        bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
-                        const bool sup = ((cur >> lane) & 1u) && iou_gt(bt, bi, iou_thr);     // strict '>' (onnx_engine.cpp:871)
-                        cur &= ~__ballot_sync(0xffffffffu, sup);
-                    }
-                    if (alive && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
-                    if ((kept >> lane) & 1u) s_kidx[grp][__popc(kept & ((1u << lane) - 1u))] = i;
-                    if (lane == 0) s_nk[grp] = __popc(kept);
-                }
+            const int gw = gtid >> 5;                                      // warp of the group: eight columns each
+            uint32_t* gcol = s_col[2 + 2 * grp];                           // this group's two column buffers
+            block_columns(s0, e0, gw * 8, 8, gcol);
+            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            int buf = 0;
+            for (int b0 = s0; b0 < e0; b0 += 32, buf ^= 1) {
+                if (gw == 0) block_resolve(b0, e0, gcol + 32 * buf, s_kidx[grp], &s_nk[grp]);
                 asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
                 const int nk = s_nk[grp];
                 if (nk > 0) {
@@ -618,7 +621,8 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
                         }
                     }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");       // flags and s_kidx settled before the next block
+                if (b0 + 32 < e0) block_columns(b0 + 32, e0, gw * 8, 8, gcol + 32 * (buf ^ 1));
+                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");       // flags, s_kidx and the next columns settled before the next block
             }
         }
         if (overflow) {
@@ -863,7 +867,12 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
     cudaLaunchAttribute attr[2];
     int na = 0;
     static const bool use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
-    if (use_pdl) {
+    // Measured on B200 (driver 580, CUDA 12.9): a CLUSTER launch that is also a programmatic dependent of the fused head
+    // kernel (which fires its launch trigger at its top) started before the head kernel's candidates were visible —
+    // griddepcontrol.wait did not hold it (missing detections in every engine-path test).  Cluster launches therefore keep
+    // plain stream order; ZL_NMS_CLUSTER_PDL=1 re-enables the combination for experiments.
+    static const bool cluster_pdl = [] { const char* e = getenv("ZL_NMS_CLUSTER_PDL"); return e && e[0] == '1'; }();
+    if (use_pdl && (split == 1 || cluster_pdl)) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
