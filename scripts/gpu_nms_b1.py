@@ -12,7 +12,7 @@ if __name__ == "__main__":
     t = yolov8_ref.synthetic_model("n", 4, 0)
     e = zlb200.Engine(416, 416, 4, "n", precision=zlb200.FP16, max_batch=1, use_graph=0)
     e.load_weights_blob(zlw.dumps(t, "n", 4))
-    frames = list(synth.frames_structured(4, 416, 416, seed=11))
+    frames = [synth.frames_structured(1, 416, 416)[0]] * 4       # the frame bench.py / gpu_latency.py time
     for f in frames:
         d = e.infer([f])
         print("dets", len(d[0]), flush=True)

@@ -1033,7 +1033,7 @@ int32_t Engine::decode_nms(const float* raw, int n, int nc, int A, const int32_t
         cudaEventRecord(ev[0], st);
         rc = launch_filter(st, d_raw, n, nc, A, nullptr, d_wh, conf, nullptr, pb);
         cudaEventRecord(ev[1], st);
-        if (rc == ZL_OK) rc = launch_nms(st, n, A, iou, pb);
+        if (rc == ZL_OK) rc = launch_nms(st, n, A, iou, pb, true);
         cudaEventRecord(ev[2], st);
         if (cudaStreamSynchronize(st) != cudaSuccess) { set_error(std::string("decode_nms: ") + cudaGetErrorString(cudaGetLastError())); rc = ZL_INFERENCE_ERROR; break; }
         float a = 0, b = 0;

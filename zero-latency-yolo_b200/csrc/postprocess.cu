@@ -423,39 +423,65 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     __syncthreads();
 
     ZL_NMS_STAMP(0);
-    // ---- bitonic sort, ascending.  Comparator strides >= 32 go through memory with a block barrier per step; the five
-    // innermost strides (16..1) of every merge stay inside aligned 32-key groups, so a warp runs them in registers with
-    // shuffles (no memory traffic, no barrier): 21 block barriers instead of 66 for 2048 keys.
+    // ---- bitonic sort, ascending.  The five innermost strides (16..1) of every merge stay inside aligned 32-key groups, so
+    // a warp runs them in registers with shuffles (no memory traffic, no barrier), and the first five merges (k = 2..32)
+    // are one register pass.  Strides >= 32 go through memory: every thread owns whole comparator PAIRS (no idle half), and
+    // two strides (j, j/2) are taken per barrier on quads {i, i|j/2, i|j, i|j|j/2} while both are >= 32:
+    // 16 block barriers + 8 register passes for 4096 keys (it was 28 + 12, with half of the warps idle in each step).
     if (n > 1) {
         uint64_t* kk = in_smem ? skeys : gkeys;
-        for (int k = 2; k <= P; k <<= 1) {
-            int j = k >> 1;
-            for (; j >= 32; j >>= 1) {
-                for (int i = tid; i < P; i += kNmsThreads) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const uint64_t a = kk[i], b = kk[ixj];
+        auto cmpx = [](uint64_t& a, uint64_t& b, bool up) { if ((a > b) == up) { const uint64_t t = a; a = b; b = t; } };
+        auto warp_steps = [&](uint64_t x, int i, int k, int jfirst) {
+            const bool up = (i & k) == 0;
+            for (int jj = jfirst; jj >= 1; jj >>= 1) {
+                const uint64_t y = __shfl_xor_sync(0xffffffffu, x, jj);
+                const bool lower = (lane & jj) == 0;                          // this lane keeps the smaller key of the pair when ascending
+                const bool take_min = lower == up;
+                x = take_min ? (x < y ? x : y) : (x > y ? x : y);
+            }
+            return x;
+        };
+        if (P >= 32) {
+            for (int base = warp * 32; base < P; base += kNmsThreads) {      // each warp owns whole 32-key groups
+                const int i = base + lane;
+                uint64_t x = kk[i];
+                for (int k = 2; k <= 32; k <<= 1) x = warp_steps(x, i, k, k >> 1);
+                kk[i] = x;
+            }
+            __syncthreads();
+            for (int k = 64; k <= P; k <<= 1) {
+                int j = k >> 1;
+                while (j >= 64) {
+                    const int h = j >> 1, lowm = h - 1;
+                    for (int q = tid; q < (P >> 2); q += kNmsThreads) {
+                        const int i = (q & lowm) | ((q & ~lowm) << 2);          // bits h and j clear
                         const bool up = (i & k) == 0;
-                        if ((a > b) == up) { kk[i] = b; kk[ixj] = a; }
+                        uint64_t x0 = kk[i], x1 = kk[i | h], x2 = kk[i | j], x3 = kk[i | j | h];
+                        cmpx(x0, x2, up); cmpx(x1, x3, up);                     // stride j
+                        cmpx(x0, x1, up); cmpx(x2, x3, up);                     // stride j/2
+                        kk[i] = x0; kk[i | h] = x1; kk[i | j] = x2; kk[i | j | h] = x3;
                     }
+                    __syncthreads();
+                    j >>= 2;
+                }
+                if (j == 32) {
+                    for (int q = tid; q < (P >> 1); q += kNmsThreads) {
+                        const int i = (q & 31) | ((q & ~31) << 1);              // bit 32 clear
+                        const bool up = (i & k) == 0;
+                        uint64_t a = kk[i], b = kk[i | 32];
+                        if ((a > b) == up) { kk[i] = b; kk[i | 32] = a; }
+                    }
+                    __syncthreads();
+                }
+                for (int base = warp * 32; base < P; base += kNmsThreads) {
+                    const int i = base + lane;
+                    kk[i] = warp_steps(kk[i], i, k, 16);
                 }
                 __syncthreads();
             }
-            if (P >= 32) {
-                for (int base = warp * 32; base < P; base += kNmsThreads) {      // each warp owns whole 32-key groups
-                    const int i = base + lane;
-                    uint64_t x = kk[i];
-                    const bool up = (i & k) == 0;
-                    for (int jj = j; jj >= 1; jj >>= 1) {
-                        const uint64_t y = __shfl_xor_sync(0xffffffffu, x, jj);
-                        const bool lower = (lane & jj) == 0;                      // this lane keeps the smaller key of the pair when ascending
-                        const bool take_min = lower == up;
-                        x = take_min ? (x < y ? x : y) : (x > y ? x : y);
-                    }
-                    kk[i] = x;
-                }
-            } else {
-                for (; j >= 1; j >>= 1) {                                         // tiny P (< 32): plain steps
+        } else {
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j >= 1; j >>= 1) {                           // tiny P (< 32): plain steps
                     for (int i = tid; i < P; i += kNmsThreads) {
                         const int ixj = i ^ j;
                         if (ixj > i) {
@@ -467,7 +493,6 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
                     __syncthreads();
                 }
             }
-            __syncthreads();
         }
     }
     const uint64_t* K = in_smem ? skeys : gkeys;
@@ -835,21 +860,22 @@ int32_t nms_configure()
 
 // CTAs per frame (cluster size) for a batch of n frames: as many as keep every cluster resident at once.  One CTA owns
 // an SM (200 KB of shared memory), a cluster lives inside one GPC (16+ usable SMs on B200).  ZL_NMS_SPLIT=1/2/4/8 overrides.
-static int nms_split_for(int n, bool keys_fit_smem)
+static int nms_split_for(int n, bool keys_fit_smem, bool allow_cluster)
 {
     if (!keys_fit_smem) return 1;                  // global-memory sort works in place on the frame's key slice: one CTA only
     static const int forced = [] { const char* e = getenv("ZL_NMS_SPLIT"); return e ? atoi(e) : 0; }();
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+    if (!allow_cluster) return 1;
     return n <= 16 ? 8 : (n <= 32 ? 4 : (n <= 72 ? 2 : 1));
 }
 
-int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb)
+int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb, bool allow_cluster)
 {
     // smem plan: keys (only as many as can ever be needed) + removed bitmask (A bits)
     int key_cap = 1;
     while (key_cap < A) key_cap <<= 1;
     if (key_cap > 16384) key_cap = 0;              // too many to sort in smem -> sort in global memory
-    const int split = nms_split_for(n, key_cap != 0);
+    const int split = nms_split_for(n, key_cap != 0, allow_cluster);
     const size_t mask_bytes = ((size_t)ceil_div(A, 32) * 4 + 15) & ~(size_t)15;
     size_t smem = (size_t)key_cap * 8 + mask_bytes;
     if (smem > 200 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "nms: anchor count too large for the suppression bitmask");
