@@ -345,7 +345,12 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     if (tid == 0 && f == g_nms_dbg_frame) { g_nms_dbg[rank][6] = clock64(); g_nms_dbg[rank][8] = nms_gtime(); }
     // launched with programmatic stream serialization behind the decode kernel: everything above ran under its tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int n_all = (int)min(cand_count[f], (uint32_t)A);
+    // The count is read with a volatile asm load: cand_count is `const __restrict__`, and nvcc hoists such (invariant,
+    // LDG.CONSTANT) loads ABOVE the asm statement of griddepcontrol.wait whatever its memory clobber — seen in the SASS of
+    // this kernel, where the NMS then started on a count the head kernel had not finished writing.
+    uint32_t n_raw;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(n_raw) : "l"(cand_count + f) : "memory");
+    const int n_all = (int)min(n_raw, (uint32_t)A);
     uint32_t* h_total = header;
     uint32_t* h_cnt = header + 4;
     uint32_t* h_off = header + 4 + maxn;
