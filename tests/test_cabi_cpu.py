@@ -77,3 +77,34 @@ def test_null_handle_is_an_error_not_a_crash(built_lib):
     assert built_lib.zl_engine_queue_size(None) == 0
     assert built_lib.zl_engine_destroy(None) == 0
     assert b"zl_b200" in built_lib.zl_version()
+
+
+def test_no_load_is_hoisted_above_the_programmatic_launch_wait(built_lib):
+    """Kernels launched as programmatic dependents (PDL) start while their predecessor still runs and must not read its
+    output before `griddepcontrol.wait` (SASS: ACQBULK).  nvcc treats loads through `const __restrict__` pointers / `__ldg`
+    as invariant (LDG.E.CONSTANT) and moves them across asm statements whatever their memory clobber: round 2 lost
+    detections to exactly that in nms_kernel (the candidate count was loaded above the wait).  This test reads the SASS of
+    the product library: in every kernel that waits, no invariant global load may precede the first ACQBULK."""
+    import shutil
+    import subprocess
+    import zlb200
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", zlb200.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    kernels, name, before_wait, waited, bad = 0, None, 0, False, {}
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name, before_wait, waited = line.split("Function :")[1].strip(), 0, False
+            continue
+        if name is None or waited:
+            continue
+        if "ACQBULK" in line:
+            waited = True
+            kernels += 1
+            if before_wait:
+                bad[name] = before_wait
+        elif "LDG" in line and ".CONSTANT" in line:
+            before_wait += 1
+    assert kernels >= 5, f"expected the tcgen05 conv, head and NMS kernels to contain the wait, found {kernels}"
+    assert not bad, f"invariant loads above griddepcontrol.wait: {bad}"

@@ -275,7 +275,14 @@ decode_filter_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2,
 
 // ============================================================= N1: NMS
 constexpr int kNmsThreads = 1024;
+#ifndef ZL_NMS_MINBLOCKS
+#define ZL_NMS_MINBLOCKS 1
+#endif
 constexpr int kMaxLargeSeg = 512;
+#ifndef ZL_NMS_W
+#define ZL_NMS_W 4
+#endif
+constexpr int kSweepW = ZL_NMS_W;     // IoU tests in flight per candidate in the block sweeps
 constexpr int kNmsSplitMin = 256;     // frames with fewer candidates are not split over a cluster's CTAs
 constexpr int kWholeCtaSeg = 512;     // class segments larger than this are swept by all 1024 threads, one segment at a time     // queue slots for class segments with more than 32 candidates
 
@@ -298,8 +305,16 @@ __device__ __forceinline__ float iou_ref(const float4 a, const float4 b) {
 // whose frame index is g_nms_dbg_frame.
 __device__ long long g_nms_dbg[8][10];      // [cluster rank][0..5 phase stamps, 6 entry, 7 candidates of the rank, 8/9 globaltimer at entry / exit]
 __device__ int g_nms_dbg_frame = -1;
+__device__ long long g_nms_dbg2[64];        // fine stamps inside the large-segment phase (group 0 of rank 0, in program order)
 __device__ __forceinline__ long long nms_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#ifndef ZL_NMS_STAMPS
+#define ZL_NMS_STAMPS 1
+#endif
+#if ZL_NMS_STAMPS
 #define ZL_NMS_STAMP(k) do { if (tid == 0 && f == g_nms_dbg_frame) g_nms_dbg[rank][k] = clock64(); } while (0)
+#else
+#define ZL_NMS_STAMP(k) do { } while (0)
+#endif
 
 // `calculateIoU(a, b) > thr` (onnx_engine.cpp:871,881-909), decided EXACTLY but usually without the IEEE division: boxes that
 // do not overlap have IoU 0 (never > thr for thr >= 0); otherwise a reciprocal estimate of inter/union settles every case
@@ -319,13 +334,62 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
     return __fdiv_rn(inter, uni) > thr;
 }
 
+// The same decision for SEVERAL independent pairs at once.  One test is a chain of ~40 dependent instructions (~350
+// cycles of latency on the round-2 stamps: a sweep against 13 kept boxes cost 4500 cycles), so the bulk sweeps call the
+// branch-free form below four or eight times in a row — the compiler interleaves the chains — and only the pairs it could
+// not settle (quotient within 1e-5 of the threshold, degenerate unions) go through the exact, out-of-line form.
+struct BoxC { float x0, x1, y0, y1, area; };
+__device__ __forceinline__ BoxC box_corners(const float4 b) {
+    const float hw = __fmul_rn(b.z, 0.5f), hh = __fmul_rn(b.w, 0.5f);
+    BoxC c;
+    c.x0 = __fsub_rn(b.x, hw); c.x1 = __fadd_rn(b.x, hw); c.y0 = __fsub_rn(b.y, hh); c.y1 = __fadd_rn(b.y, hh);
+    c.area = __fmul_rn(b.z, b.w);
+    return c;
+}
+__device__ __forceinline__ bool iou_gt_fast(const BoxC& a, const BoxC& b, float thr, bool& undecided) {
+    const float xo = fmaxf(0.0f, __fsub_rn(fminf(a.x1, b.x1), fmaxf(a.x0, b.x0)));
+    const float yo = fmaxf(0.0f, __fsub_rn(fminf(a.y1, b.y1), fmaxf(a.y0, b.y0)));
+    const float inter = __fmul_rn(xo, yo);
+    const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(uni));      // 1 ulp: far inside the 1e-5 guard band
+    const float q = inter * r;
+    const bool zero = !(inter > 0.0f) && thr >= 0.0f;            // IoU is 0: not > thr
+    const bool degenerate = !(uni > 1e-30f);                     // union guard of the reference / reciprocal out of range: exact form decides
+    const bool gt = q > thr + 1e-5f, lt = q < thr - 1e-5f;
+    undecided = !zero && (degenerate || !(gt || lt));
+    return !zero && gt;
+}
+__device__ __noinline__ bool iou_gt_exact(const float4 a, const float4 b, float thr) { return iou_ref(a, b) > thr; }
+
+// The reference's greedy chain over <= 32 candidates in sorted order (applyNMS, onnx_engine.cpp:856-875), given for every
+// candidate i (= lane) the mask `row` of EARLIER candidates whose IoU with it exceeds the threshold and the mask `und` of the
+// candidates still alive.  "i is kept iff it is alive and no kept t < i suppresses it" has one solution; instead of walking
+// the kept boxes one by one (a dependent shuffle + two bit operations per link, ~130 cycles) the warp settles, per round,
+// every candidate whose earlier suppressors are all settled: removed if one of them is kept, kept if none is left
+// undecided.  The first undecided candidate always settles, so the loop ends; real segments take 2-4 rounds.
+__device__ __forceinline__ uint32_t resolve_rows(uint32_t und, uint32_t row, int lane) {
+    uint32_t kept = 0u;
+    while (und != 0u) {
+        const bool me = (und >> lane) & 1u;
+        const bool rem = me && (row & kept) != 0u;
+        const bool kp = me && !rem && (row & und) == 0u;
+        const unsigned kb = __ballot_sync(0xffffffffu, kp), rb = __ballot_sync(0xffffffffu, rem);
+        kept |= kb;
+        und &= ~(kb | rb);
+    }
+    return kept;
+}
 // One CTA per frame, or — launched as thread-block CLUSTERS of S CTAs (launch_nms) — S CTAs per frame, each owning a
 // contiguous range of classes.  Classes never interact in applyNMS (onnx_engine.cpp:856-875 compares class ids before any
 // IoU), so the ranks sort, sweep and compact their own candidates independently; they only exchange their kept counts
 // (distributed shared memory) so that the frame's detections land contiguously in (class asc, confidence desc) order.
 // The class ranges are cut where the running candidate count crosses multiples of n/S: balanced up to one class.
 // Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | sorted boxes (the class histogram of the split lives there first).
-__global__ void __launch_bounds__(kNmsThreads)
+// CL = false is the instantiation of the engine's step: no cluster special registers at all (with them in the kernel the
+// graph-captured b=1 path measured 9 us slower although the kernel itself was not).
+template <bool CL>
+__global__ void __launch_bounds__(kNmsThreads, ZL_NMS_MINBLOCKS)
 nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
            float4* __restrict__ sorted_box, const uint32_t* __restrict__ cand_count, uint32_t* __restrict__ header,
            DevDet* __restrict__ dets, int maxn, uint32_t cap)
@@ -334,15 +398,26 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     __shared__ uint32_t s_warp_tot[32];
     __shared__ uint32_t s_base, s_mine, s_lower;
     __shared__ uint32_t s_xkept[8], s_xbase;                  // written by the other ranks of the cluster
-    __shared__ int s_nlarge, s_qhead, s_gq[8], s_nk[8], s_kidx[8][32];
+    __shared__ int s_nlarge, s_qhead, s_gq[8], s_nk[8];
+    __shared__ float4 s_kbox[8][32];                           // kept boxes of the block a team is sweeping with
     __shared__ int s_large[2 * kMaxLargeSeg];
-    __shared__ uint32_t s_col[2 + 2 * 8][32];                  // suppression-matrix columns: two buffers for the CTA team, two per group
+    __shared__ uint32_t s_col[2 * 8][32];                      // suppression-matrix columns: two buffers per team
     namespace cg = cooperative_groups;
-    cg::cluster_group cl = cg::this_cluster();
-    const int S = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    int S = 1, rank = 0;
+    if constexpr (CL) { S = (int)cg::this_cluster().num_blocks(); rank = (int)cg::this_cluster().block_rank(); }
     const int f = blockIdx.x / S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if ZL_NMS_STAMPS
+    const bool dbg_on = f == g_nms_dbg_frame && rank == 0;
+    int dbg_i = 0;
+    bool dbg_seg = false;                                    // this thread leads the group that drew the first queued segment
+#define ZL_NMS_FINE(tag) do { if (dbg_seg && dbg_i < 31) { g_nms_dbg2[2 * dbg_i] = (tag); g_nms_dbg2[2 * dbg_i + 1] = clock64(); ++dbg_i; } } while (0)
+#define ZL_NMS_FINE_ARM(cond) dbg_seg = dbg_on && (cond)
     if (tid == 0 && f == g_nms_dbg_frame) { g_nms_dbg[rank][6] = clock64(); g_nms_dbg[rank][8] = nms_gtime(); }
+#else
+#define ZL_NMS_FINE(tag) do { } while (0)
+#define ZL_NMS_FINE_ARM(cond) do { } while (0)
+#endif
     // launched with programmatic stream serialization behind the decode kernel: everything above ran under its tail
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // The count is read with a volatile asm load: cand_count is `const __restrict__`, and nvcc hoists such (invariant,
@@ -356,7 +431,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     uint32_t* h_off = header + 4 + maxn;
     // few candidates: the split (histogram + two cluster barriers) costs more than it saves; rank 0 does the frame alone.
     // n_all is the same in every rank, so the whole cluster takes the same branch (no rank waits on a barrier alone).
-    const bool split = S > 1 && n_all > kNmsSplitMin;
+    const bool split = CL && S > 1 && n_all > kNmsSplitMin;
     if (n_all == 0 || (!split && rank != 0)) {
         if (tid == 0 && rank == 0) { h_cnt[f] = 0; h_off[f] = 0; }
         return;
@@ -367,7 +442,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     int n = n_all;
     if (split) {
         // every rank must be running before anyone writes into its shared memory: arrive now, wait right before the exchange
-        asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        if constexpr (CL) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
         // launch_nms only forms clusters when every frame's keys fit the smem sort buffer (key_cap_smem >= pow2(A))
         uint32_t* hist = reinterpret_cast<uint32_t*>(nms_smem + (size_t)key_cap_smem * 8 + (size_t)(((((A + 31) >> 5) * 4) + 15) & ~15));
         for (int i = tid; i < kMaxClasses; i += kNmsThreads) hist[i] = 0u;
@@ -521,138 +596,191 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     if (n > 1) {
         if (tid == 0) { s_nlarge = 0; s_qhead = 0; }
         __syncthreads();
-        for (int head = warp; head < n; head += kNmsThreads / 32) {
-            const bool is_head = head == 0 || key_class(K[head]) != key_class(K[head - 1]);
-            if (!is_head) continue;
-            const int cls = key_class(K[head]);
-            int lo = head + 1, hi = n;                       // segment end: first index with a larger class
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (key_class(K[mid]) > cls) hi = mid; else lo = mid + 1;
+        for (int base = warp * 32; base < n; base += kNmsThreads) {      // a warp looks at 32 sorted positions at once
+            const int pos = base + lane;
+            const int cls = pos < n ? key_class(K[pos]) : -1;
+            int prev = __shfl_up_sync(0xffffffffu, cls, 1);
+            if (lane == 0) prev = pos > 0 && pos < n ? key_class(K[pos - 1]) : -2;
+            unsigned heads = __ballot_sync(0xffffffffu, pos < n && cls != prev);
+            while (heads != 0u) {
+                const int hl = __ffs(heads) - 1;
+                heads &= heads - 1u;
+                const int head = base + hl;
+                const int hcls = __shfl_sync(0xffffffffu, cls, hl);
+                // the next 32 positions: where the class changes is the end of a small segment
+                const int pp = head + 1 + lane;
+                const unsigned db = __ballot_sync(0xffffffffu, pp >= n || key_class(K[pp]) != hcls);
+                if (db == 0u) {                                  // more than 32 candidates: find the end, queue for phase 2
+                    int lo = head + 33, hi = n;                  // first index with a larger class
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (key_class(K[mid]) > hcls) hi = mid; else lo = mid + 1;
+                    }
+                    if (lane == 0) { const int q = atomicAdd(&s_nlarge, 1); if (q < kMaxLargeSeg) { s_large[2 * q] = head; s_large[2 * q + 1] = lo; } }
+                    continue;
+                }
+                const int m = __ffs(db);                         // candidates head .. head + m - 1
+                if (m == 1) continue;
+                // each candidate's row of the suppression matrix, eight independent tests in flight, then the chain in rounds
+                const int i = head + lane;
+                const bool valid = lane < m;
+                const float4 bi = sb[min(i, n - 1)];
+                const BoxC ci = box_corners(bi);
+                uint32_t row = 0u;
+                for (int t0 = 0; t0 < m - 1; t0 += 8) {
+                    bool r[8], u[8], any_u = false;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        r[k] = iou_gt_fast(box_corners(sb[min(head + t0 + k, n - 1)]), ci, iou_thr, u[k]);
+                        any_u |= u[k];
+                    }
+                    if (any_u) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (u[k]) r[k] = iou_gt_exact(sb[min(head + t0 + k, n - 1)], bi, iou_thr);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (r[k] && t0 + k < lane) row |= 1u << (t0 + k);       // strict '>' (onnx_engine.cpp:871); t < i only
+                }
+                const uint32_t all = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
+                const uint32_t kept = resolve_rows(all, valid ? (row & all) : 0u, lane);
+                if (valid && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
             }
-            const int end = lo, m = end - head;
-            if (m == 1) continue;
-            if (m > 32) {
-                if (lane == 0) { const int q = atomicAdd(&s_nlarge, 1); if (q < kMaxLargeSeg) { s_large[2 * q] = head; s_large[2 * q + 1] = end; } }
-                continue;
-            }
-            const int i = head + lane;
-            const bool valid = lane < m;
-            const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t cur = m == 32 ? 0xffffffffu : ((1u << m) - 1u);      // alive, not yet decided
-            uint32_t kept = 0u;
-            while (cur != 0u) {
-                const int t = __ffs(cur) - 1;                              // next candidate in sorted order that is not removed
-                kept |= 1u << t;
-                cur &= ~(1u << t);
-                float4 bt;
-                bt.x = __shfl_sync(0xffffffffu, bi.x, t); bt.y = __shfl_sync(0xffffffffu, bi.y, t);
-                bt.z = __shfl_sync(0xffffffffu, bi.z, t); bt.w = __shfl_sync(0xffffffffu, bi.w, t);
-                const bool sup = ((cur >> lane) & 1u) && iou_gt(bt, bi, iou_thr);     // strict '>' (onnx_engine.cpp:871)
-                cur &= ~__ballot_sync(0xffffffffu, sup);
-            }
-            if (valid && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
         }
         __syncthreads();
         ZL_NMS_STAMP(3);
         const int nlarge = min(s_nlarge, kMaxLargeSeg);
         const bool overflow = s_nlarge > kMaxLargeSeg;                      // more large segments than queue slots: handled below
-        const int grp = warp >> 2, gtid = tid & 127;                        // 8 groups of 128 threads
-        // Blocked greedy sweep with bitmask suppression, exact.  A segment is walked in blocks of 32 candidates.  By the time a
-        // block is reached every candidate in it has been tested against the kept boxes of ALL earlier blocks, so
+        // Blocked greedy sweep with bitmask suppression, exact.  A segment is walked in blocks of 32 candidates by a TEAM of
+        // 128 ... 1024 threads.  By the time a block is reached every candidate in it has been tested against the kept boxes
+        // of ALL earlier blocks, so
         //  (a) the block resolves internally from its 32 x 32 suppression matrix: column t = the ballot of "box t suppresses
-        //      box i" over the lanes i > t.  The matrix does not depend on what earlier blocks removed, so the team computes
-        //      the NEXT block's columns (one or eight per warp) next to the current block's sweep; the resolving warp then
-        //      follows the reference's serial chain over the kept boxes with one shuffle + two bit operations per link
-        //      (it cost a shuffled box + an IoU, ~150 cycles, per link when the tests were made inside the chain);
+        //      box i" over the lanes i > t.  The matrix does not depend on what earlier blocks removed: while the team's first
+        //      warp resolves block b (the chain over its kept boxes), its other warps already compute the columns of block b + 1;
         //  (b) all threads of the team test the later candidates against the block's kept boxes in parallel.
-        // Very large segments (one class holding hundreds of candidates) first, one at a time, with the WHOLE CTA as the team:
-        // a 128-thread group would leave the other seven idle behind it.
-        auto block_columns = [&](int b0, int e0, int t_first, int t_count, uint32_t* col) {
+        // Every bulk IoU test runs kSweepW independent tests in flight (iou_gt_fast): one test alone is ~350 cycles of latency.
+        // Team size: the whole CTA, one segment at a time, for very large segments (one class holding hundreds of candidates);
+        // for the rest the CTA splits into as few teams as there are segments (1 / 2 / 4 / 8): the b=1 latency frame has four
+        // classes, and 128-thread teams left half of the CTA idle.
+        auto block_columns = [&](int b0, int e0, int t_first, int t_stride, uint32_t* col) {   // columns t_first, t_first + t_stride, ... < 32
             const int i = b0 + lane;
             const bool valid = i < e0;
-            const float4 bi = valid ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t = t_first; t < t_first + t_count; ++t) {
-                bool sup = false;
-                if (b0 + t < e0) {                                           // warp-uniform
-                    const float4 bt = sb[b0 + t];
-                    sup = valid && t < lane && iou_gt(bt, bi, iou_thr);      // strict '>' (onnx_engine.cpp:871)
+            const float4 bi = sb[min(i, e0 - 1)];
+            const BoxC ci = box_corners(bi);
+            for (int tb = t_first; tb < 32; tb += kSweepW * t_stride) {
+                bool r[kSweepW], u[kSweepW], any_u = false;
+#pragma unroll
+                for (int k = 0; k < kSweepW; ++k) {                          // independent chains, interleaved
+                    r[k] = iou_gt_fast(box_corners(sb[min(b0 + tb + k * t_stride, e0 - 1)]), ci, iou_thr, u[k]);
+                    any_u |= u[k];
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                if (lane == 0) col[t] = bal;
+                if (any_u) {
+#pragma unroll
+                    for (int k = 0; k < kSweepW; ++k)
+                        if (u[k]) r[k] = iou_gt_exact(sb[min(b0 + tb + k * t_stride, e0 - 1)], bi, iou_thr);
+                }
+#pragma unroll
+                for (int k = 0; k < kSweepW; ++k) {
+                    const int t = tb + k * t_stride;
+                    if (t < 32) {                                            // warp-uniform
+                        const bool sup = valid && b0 + t < e0 && t < lane && r[k];   // strict '>' (onnx_engine.cpp:871)
+                        const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                        if (lane == 0) col[t] = bal;
+                    }
+                }
             }
         };
-        auto block_resolve = [&](int b0, int e0, const uint32_t* col, int* kidx, int* nk_out) {      // one warp
+        auto block_resolve = [&](int b0, int e0, const uint32_t* col, float4* kbox, int* nk_out) {      // one warp
             const int i = b0 + lane;
             const bool valid = i < e0;
             const bool alive = valid && (((removed[i >> 5] >> (i & 31)) & 1u) == 0u);
             uint32_t cur = __ballot_sync(0xffffffffu, alive);                // alive, not yet decided
             const uint32_t mycol = col[lane];
+            const float4 bi = sb[min(i, e0 - 1)];
             uint32_t kept = 0u;
-            while (cur != 0u) {
-                const int t = __ffs(cur) - 1;                                // next candidate in sorted order that is not removed
-                kept |= 1u << t;
+            while (cur != 0u) {                                              // the reference's chain over the kept boxes: one shuffle per link
+                const int t = __ffs(cur) - 1;                                // (measured: ~130 cycles per link; transposing the columns for
+                kept |= 1u << t;                                             //  resolve_rows costs more than the 8-13 links of a block)
                 cur &= ~(1u << t);
                 cur &= ~__shfl_sync(0xffffffffu, mycol, t);                  // everything box t suppresses
             }
             if (alive && !((kept >> lane) & 1u)) atomicOr(const_cast<uint32_t*>(&removed[i >> 5]), 1u << (i & 31));
-            if ((kept >> lane) & 1u) kidx[__popc(kept & ((1u << lane) - 1u))] = i;
+            if ((kept >> lane) & 1u) kbox[__popc(kept & ((1u << lane) - 1u))] = bi;
             if (lane == 0) *nk_out = __popc(kept);
         };
+        // later candidates of the segment against the block's kept boxes.  When fewer candidates are left than the team has
+        // threads, 2 / 4 / 8 threads share a candidate and split the kept boxes between them (setting a flag twice is harmless).
+        auto block_sweep = [&](int j_first, int e0, int gtid, int T, const float4* kbox, int nk) {
+            const int left = e0 - j_first;
+            int psh = 0;                                                     // log2(threads per candidate)
+            while (psh < 3 && (left << (psh + 1)) <= T && (kSweepW << psh) < nk) ++psh;
+            const int part = gtid & ((1 << psh) - 1);
+            for (int j = j_first + (gtid >> psh); j < e0; j += T >> psh) {
+                if (((removed[j >> 5] >> (j & 31)) & 1u) != 0u) continue;
+                const float4 bj = sb[j];
+                const BoxC cj = box_corners(bj);
+                bool sup = false;
+                for (int t = part * kSweepW; t < nk && !sup; t += kSweepW << psh) {
+                    bool r[kSweepW], u[kSweepW], any_u = false;
+#pragma unroll
+                    for (int k = 0; k < kSweepW; ++k) {                      // past the end: the last kept box again (same answer)
+                        r[k] = iou_gt_fast(box_corners(kbox[min(t + k, nk - 1)]), cj, iou_thr, u[k]);
+                        any_u |= u[k];
+                    }
+                    if (any_u) {
+#pragma unroll
+                        for (int k = 0; k < kSweepW; ++k)
+                            if (u[k]) r[k] = iou_gt_exact(kbox[min(t + k, nk - 1)], bj, iou_thr);
+                    }
+#pragma unroll
+                    for (int k = 0; k < kSweepW; ++k) sup = sup || r[k];
+                }
+                if (sup) atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31));
+            }
+        };
+        // one segment by one team of T threads (team index grp, thread gtid of the team, named barrier grp + 1)
+        auto run_segment = [&](int s0, int e0, int T, int grp, int gtid, bool stamp) {
+            const int TW = T >> 5, gw = gtid >> 5;
+            uint32_t* gcol = s_col[2 * grp];                               // the team's two column buffers
+            ZL_NMS_FINE_ARM(stamp);
+            ZL_NMS_FINE(1000 + (e0 - s0));
+            block_columns(s0, e0, gw, TW, gcol);
+            asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(T) : "memory");
+            ZL_NMS_FINE(1);
+            int buf = 0;
+            for (int b0 = s0; b0 < e0; b0 += 32, buf ^= 1) {
+                if (gw == 0) block_resolve(b0, e0, gcol + 32 * buf, s_kbox[grp], &s_nk[grp]);
+                else if (b0 + 32 < e0) block_columns(b0 + 32, e0, gw - 1, TW - 1, gcol + 32 * (buf ^ 1));
+                ZL_NMS_FINE(2);
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(T) : "memory");
+                const int nk = s_nk[grp];
+                ZL_NMS_FINE(300 + nk);
+                if (nk > 0 && b0 + 32 < e0) block_sweep(b0 + 32, e0, gtid, T, s_kbox[grp], nk);
+                ZL_NMS_FINE(4);
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(T) : "memory");       // flags and kept boxes settled before the next block
+                ZL_NMS_FINE(6);
+            }
+        };
+        int nrest = 0;                                                      // segments the teams of pass 2 share
         for (int q = 0; q < nlarge; ++q) {
             const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
-            if (e0 - s0 <= kWholeCtaSeg) continue;
-            block_columns(s0, e0, warp, 1, s_col[0]);                        // 32 warps: one column each
-            __syncthreads();
-            int buf = 0;
-            for (int b0 = s0; b0 < e0; b0 += 32, buf ^= 1) {
-                if (warp == 0) block_resolve(b0, e0, s_col[buf], s_kidx[0], &s_nk[0]);
-                __syncthreads();
-                const int nk = s_nk[0];
-                if (nk > 0) {
-                    for (int j = b0 + 32 + tid; j < e0; j += kNmsThreads) {
-                        if (((removed[j >> 5] >> (j & 31)) & 1u) != 0u) continue;
-                        const float4 bj = sb[j];
-                        for (int t = 0; t < nk; ++t) {
-                            if (iou_gt(sb[s_kidx[0][t]], bj, iou_thr)) { atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31)); break; }
-                        }
-                    }
-                }
-                if (b0 + 32 < e0) block_columns(b0 + 32, e0, warp, 1, s_col[buf ^ 1]);
-                __syncthreads();
-            }
+            if (e0 - s0 <= kWholeCtaSeg) { ++nrest; continue; }
+            run_segment(s0, e0, kNmsThreads, 0, tid, false);
         }
-        for (;;) {
-            int q = 0;
-            if (gtid == 0) q = atomicAdd(&s_qhead, 1);
-            // broadcast q inside the group through the named barrier + smem
-            if (gtid == 0) s_gq[grp] = q;
-            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-            q = s_gq[grp];
-            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-            if (q >= nlarge) break;
-            const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
-            if (e0 - s0 > kWholeCtaSeg) continue;                          // done above by the whole CTA
-            const int gw = gtid >> 5;                                      // warp of the group: eight columns each
-            uint32_t* gcol = s_col[2 + 2 * grp];                           // this group's two column buffers
-            block_columns(s0, e0, gw * 8, 8, gcol);
-            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-            int buf = 0;
-            for (int b0 = s0; b0 < e0; b0 += 32, buf ^= 1) {
-                if (gw == 0) block_resolve(b0, e0, gcol + 32 * buf, s_kidx[grp], &s_nk[grp]);
-                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-                const int nk = s_nk[grp];
-                if (nk > 0) {
-                    for (int j = b0 + 32 + gtid; j < e0; j += 128) {
-                        if (((removed[j >> 5] >> (j & 31)) & 1u) != 0u) continue;
-                        const float4 bj = sb[j];
-                        for (int t = 0; t < nk; ++t) {
-                            if (iou_gt(sb[s_kidx[grp][t]], bj, iou_thr)) { atomicOr(const_cast<uint32_t*>(&removed[j >> 5]), 1u << (j & 31)); break; }
-                        }
-                    }
-                }
-                if (b0 + 32 < e0) block_columns(b0 + 32, e0, gw * 8, 8, gcol + 32 * (buf ^ 1));
-                asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");       // flags, s_kidx and the next columns settled before the next block
+        if (nrest > 0) {
+            const int T = nrest <= 1 ? 1024 : (nrest <= 2 ? 512 : (nrest <= 4 ? 256 : 128));
+            const int grp = tid / T, gtid = tid - grp * T;
+            for (;;) {
+                // the team's next segment: drawn by its first thread, broadcast through smem + the team's named barrier
+                if (gtid == 0) s_gq[grp] = atomicAdd(&s_qhead, 1);
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(T) : "memory");
+                const int q = s_gq[grp];
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(T) : "memory");
+                if (q >= nlarge) break;
+                const int s0 = s_large[2 * q], e0 = s_large[2 * q + 1];
+                if (e0 - s0 > kWholeCtaSeg) continue;                      // done above by the whole CTA
+                run_segment(s0, e0, T, grp, gtid, gtid == 0 && q == 0);
             }
         }
         if (overflow) {
@@ -708,8 +836,9 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
             h_off[f] = s_base;
         }
         __syncthreads();
-    } else {
+    } else if constexpr (CL) {
         // every rank tells every rank how many it kept; rank 0 reserves the frame's slice and tells everyone where it starts
+        cg::cluster_group cl = cg::this_cluster();
         asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
         if (tid < S) *cl.map_shared_rank(&s_xkept[rank], tid) = kept_total;
         cl.sync();
@@ -753,7 +882,12 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
         __syncthreads();
     }
     ZL_NMS_STAMP(5);
+#if ZL_NMS_STAMPS
     if (tid == 0 && f == g_nms_dbg_frame) { g_nms_dbg[rank][7] = n; g_nms_dbg[rank][9] = nms_gtime(); }
+    if (dbg_i > 0) g_nms_dbg2[62] = dbg_i;
+#endif
+#undef ZL_NMS_FINE
+#undef ZL_NMS_FINE_ARM
 }
 
 int g_nms_smem_keys = 0;   // key capacity (elements) of the smem sort buffer
@@ -858,7 +992,8 @@ int32_t nms_configure()
 {
     // 16384 keys (128 KB) + removed bitmask for up to 2^20 candidates would not fit; the
     // bitmask is sized for kMaxAnchors only when keys spill to global.  Budget: 200 KB.
-    ZL_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ZL_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ZL_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     g_nms_smem_keys = 16384;
     return ZL_OK;
 }
@@ -898,10 +1033,8 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
     cudaLaunchAttribute attr[2];
     int na = 0;
     static const bool use_pdl = [] { const char* e = getenv("ZL_DISABLE_PDL"); return !(e && e[0] == '1'); }();
-    // Measured on B200 (driver 580, CUDA 12.9): a CLUSTER launch that is also a programmatic dependent of the fused head
-    // kernel (which fires its launch trigger at its top) started before the head kernel's candidates were visible —
-    // griddepcontrol.wait did not hold it (missing detections in every engine-path test).  Cluster launches therefore keep
-    // plain stream order; ZL_NMS_CLUSTER_PDL=1 re-enables the combination for experiments.
+    // Cluster launches keep plain stream order (they only serve the stand-alone call, where nothing is gained from an early
+    // start); ZL_NMS_CLUSTER_PDL=1 makes them programmatic dependents as well (results identical: tests/test_gpu_headfused.py).
     static const bool cluster_pdl = [] { const char* e = getenv("ZL_NMS_CLUSTER_PDL"); return e && e[0] == '1'; }();
     if (use_pdl && (split == 1 || cluster_pdl)) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -914,7 +1047,7 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
         ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    ZL_CUDA(cudaLaunchKernelEx(&cfg, nms_kernel, A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, (const float4*)pb.box_by_anchor, pb.sorted_box,
+    ZL_CUDA(cudaLaunchKernelEx(&cfg, split > 1 ? nms_kernel<true> : nms_kernel<false>, A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, (const float4*)pb.box_by_anchor, pb.sorted_box,
                                (const uint32_t*)pb.cand_count, pb.header, pb.dets, pb.maxn, pb.cap));
     static const char* dbg = getenv("ZL_NMS_DEBUG");
     if (dbg) {
@@ -930,6 +1063,13 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
                 fprintf(stderr, "nms frame %d rank %d/%d: cand %lld | cycles: load/split %lld sort %lld gather %lld small-seg %lld large-seg %lld compact+exchange %lld | wall %lld ns, start +%lld ns\n",
                         fr, r, split, h[r][7], h[r][0] - h[r][6], h[r][1] - h[r][0], h[r][2] - h[r][1], h[r][3] - h[r][2], h[r][4] - h[r][3], h[r][5] - h[r][4],
                         h[r][9] - h[r][8], h[r][8] - h[0][8]);
+        if (cur == fr) {
+            long long h2[64];
+            cudaMemcpyFromSymbol(h2, g_nms_dbg2, sizeof(h2));
+            fprintf(stderr, "  large-segment fine stamps (tag:+cycles; 1000+m segment of m, 1 columns, 2 resolve, 300+nk after barrier, 4 sweep, 5 next columns, 6 barrier):");
+            for (int i = 1; i < (int)h2[62] && i < 31; ++i) fprintf(stderr, " %lld:+%lld", h2[2 * i], h2[2 * i + 1] - h2[2 * i - 1]);
+            fprintf(stderr, "\n");
+        }
         cudaMemcpyToSymbol(g_nms_dbg_frame, &fr, sizeof(int));
     }
     return ZL_OK;
