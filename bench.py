@@ -439,6 +439,9 @@ def run_ours(args, rank, local_rank, world):
             cfg5 = {"workload": "head tensor [128, 84, 8400] fp32, conf 0.01, iou 0.45 (SURVEY 8d stress set)", "filter_ms": mf, "nms_ms": mn, "kept": kept,
                     "filter_gbs_vs_2.822MB_per_frame": b / (mf * 1e-3) / 1e9, "filter_hbm_frac": b / (mf * 1e-3) / 1e9 / peaks["hbm"],
                     "decode_plus_nms_frames_per_s": 128 / ((mf + mn) * 1e-3)}
+            # the same call at a small batch: launch_nms deals each frame's classes to a thread-block cluster (4 CTAs at 32 frames)
+            mf32, mn32, kept32 = eng.bench_decode_nms(raw[:32], 0.01, 0.45, iters=5)
+            cfg5["batch32_cluster_of_4"] = {"filter_ms": mf32, "nms_ms": mn32, "kept": kept32}
         except Exception as ex:
             cfg5 = {"error": str(ex)}
 
