@@ -47,7 +47,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 2 ms from a thread
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled back to back from a thread
     (nvidia-smi -lms cannot start fast enough for a region of tens of milliseconds); nvidia-smi as a fallback."""
 
     def __init__(self, gpu_index):
@@ -97,7 +97,7 @@ class ClockSampler:
                             self.reasons.add(name)
                 except Exception:
                     pass
-                time.sleep(0.002)
+                time.sleep(0.0005)        # an NVML query takes 1-30 ms on a loaded box: poll nearly back to back
             return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._stop.is_set():

@@ -145,8 +145,8 @@ int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, 
                              float conf_thr, const float* class_weights, const PostBuffers& pb, bool precise);
 // applyNMS (onnx_engine.cpp:837-878): per-frame key sort + per-class greedy bitmask suppression.
 // allow_cluster: batches of up to 72 frames may deal a frame's classes to the 2 / 4 / 8 CTAs of a thread-block cluster (the
-// stand-alone decode + NMS call: 2-3x shorter at small batches).  The engine's graph-captured step passes false — measured
-// on B200: a cluster node cannot be a programmatic dependent of the head kernel, and with it the b=1 graph lost 70 us.
+// stand-alone decode + NMS call: 2-6x shorter at small batches).  The engine's graph-captured step passes false: measured
+// on B200 the split is neutral there (the step's throughput depends on the NMS's SM-time, not on its span).
 int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb, bool allow_cluster = false);
 int32_t nms_configure();   // one-time cudaFuncSetAttribute calls
 

@@ -386,8 +386,8 @@ __device__ __forceinline__ uint32_t resolve_rows(uint32_t und, uint32_t row, int
 // (distributed shared memory) so that the frame's detections land contiguously in (class asc, confidence desc) order.
 // The class ranges are cut where the running candidate count crosses multiples of n/S: balanced up to one class.
 // Dynamic smem: keys[P] (P = pow2 >= n) | removed bitmask | sorted boxes (the class histogram of the split lives there first).
-// CL = false is the instantiation of the engine's step: no cluster special registers at all (with them in the kernel the
-// graph-captured b=1 path measured 9 us slower although the kernel itself was not).
+// CL = false is the instantiation of the engine's step (one CTA per frame, no cluster code at all); CL = true the one of
+// the stand-alone decode + NMS call at small batches.
 template <bool CL>
 __global__ void __launch_bounds__(kNmsThreads, ZL_NMS_MINBLOCKS)
 nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
