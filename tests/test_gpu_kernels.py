@@ -338,6 +338,15 @@ def test_post_split_with_dominant_class(eng):
     _check_post(eng, raw, 640, 640, 0.3, 0.5)
 
 
+@pytest.mark.parametrize("conf", [0.3, 0.01])
+def test_post_more_anchors_than_the_shared_memory_sort_holds(eng, conf):
+    """A > 16384 anchors per frame (a 1280x1280 input has 33600): the keys are sorted in place in global memory, and at the
+    low threshold (every anchor a candidate) the sorted boxes live in the global scratch as well — the paths no 640x640
+    case reaches."""
+    raw = synth.stress_head(2, 8, 20000, seed=505)
+    _check_post(eng, raw, 640, 640, conf, 0.45)
+
+
 def test_post_full_cfg5_batch128(eng):
     # BASELINE.json config 5 at full size: A=8400, nc=80, conf 0.01, batch 128
     raw = synth.stress_head(128, 80, 8400, seed=42)
