@@ -75,6 +75,7 @@ struct Lane {
     HeadLevel levels[3];
     // pinned host memory
     FrameDesc* h_descs = nullptr;
+    std::vector<FrameDesc> descs_on_device;     // what d_descs holds (empty = unknown): a batch with the same geometry as the last one skips the copy
     uint8_t* h_result = nullptr; size_t h_result_bytes = 0;
     uint8_t* h_frames = nullptr;                // staging for non-pinned sync inputs: [max_batch] slots
     // N3 (cfg.emit_wire): result wire blocks written by the device
