@@ -103,7 +103,7 @@ typedef struct zl_stats {
     double p99_inference_time_ms;
     double avg_preprocessing_time_ms;  /* device time of P1 per batch (profile mode only, else 0) */
     double avg_postprocessing_time_ms;
-    double avg_device_time_ms;         /* device time per batch (CUDA events) */
+    double avg_device_time_ms;         /* device time per batch (CUDA events around a SAMPLE of the batches: every 256th of a lane) */
     int32_t graph_captured;
     int32_t device;
     int32_t precision;

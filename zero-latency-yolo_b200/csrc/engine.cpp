@@ -648,7 +648,7 @@ int32_t Engine::launch_op(Lane& L, int B, const Op& op, cudaStream_t on)
         case Op::DECODE_FILTER:
             return launch_decode_filter(st, L.levels, B, md.nc, num_anchors, L.d_descs, cfg.conf_threshold, d_class_weights, L.pb, !bf16);
         case Op::HEAD_FUSED: return head_fused_launch(st, op.hf, L.d_descs, cfg.conf_threshold, d_class_weights, L.pb);
-        case Op::NMS: return launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb);
+        case Op::NMS: return launch_nms(st, B, num_anchors, cfg.iou_threshold, L.pb, false, L.nms_host_out);
     }
     return ZL_OK;
 }
@@ -684,8 +684,12 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
     cudaStream_t st = L.stream;
     auto it = L.ops.find(B);
     if (it == L.ops.end()) { ZL_TRY(build_ops(L, B)); it = L.ops.find(B); }
-    ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, sizeof(uint32_t) * B, st));
-    ZL_CUDA(cudaMemsetAsync(L.pb.header, 0, sizeof(uint32_t) * 4, st));
+    // candidate counts and the result total in ONE memset: the header sits right behind the counts (alloc_lane), and every
+    // node in front of the first kernel is ~2 us on the b=1 path
+    ZL_CUDA(cudaMemsetAsync(L.pb.cand_count, 0, (size_t)(reinterpret_cast<char*>(L.pb.header) - reinterpret_cast<char*>(L.pb.cand_count)) + sizeof(uint32_t) * 4, st));
+    // b=1, plain results: the NMS CTA writes the result block into the pinned host buffer itself (no copy node at the end)
+    static const bool host_direct = [] { const char* e = getenv("ZL_NMS_HOST_DIRECT"); return !(e && e[0] == '0'); }();
+    L.nms_host_out = (with_d2h && B == 1 && host_direct && !cfg.emit_wire && cfg.preprocess_mode != ZL_PRE_LETTERBOX) ? reinterpret_cast<uint32_t*>(L.h_result) : nullptr;
     const bool fused = head_is_fused(it->second);
     // Small batches (the latency path): a level's Detect head — stem, box branch, class branch — runs on side streams as soon
     // as the level's map exists, next to the rest of the neck, instead of queueing behind it: at b=1 every kernel is a few
@@ -710,7 +714,7 @@ int32_t Engine::run_ops(Lane& L, int B, bool with_d2h, bool want_raw)
     if (cfg.preprocess_mode == ZL_PRE_LETTERBOX)      // non-parity mode: boxes back from the letterboxed model frame to the request frame
         ZL_TRY(launch_letterbox_unmap(st, B, L.pb.maxn, L.pb.header, L.pb.dets, L.d_descs, cfg.model_w, cfg.model_h, L.pb.cap));
     if (cfg.emit_wire) ZL_TRY(launch_wire_pack(st, B, L.pb, L.d_wmeta, L.d_wire, (uint32_t)std::min<size_t>(L.wire_cap, 0xffffffffu), L.d_wire_off));
-    if (with_d2h) {
+    if (with_d2h && !L.nms_host_out) {
         // header (total, cnt[], off[]) and the first inline_dets records in one fixed-size copy
         const size_t hdr = (size_t)(4 + 2 * L.pb.maxn) * 4;
         ZL_CUDA(cudaMemcpyAsync(L.h_result, L.pb.header, hdr + (size_t)inline_dets(B) * sizeof(DevDet), cudaMemcpyDeviceToHost, st));   // dets follow the header (alloc_lane)
@@ -811,13 +815,23 @@ int32_t Engine::run_lane_batch(Lane& L, const uint8_t* const* frames, const int3
         L.h_wmeta[L.pb.maxn] = WireMeta{0u, 0u, wr ? wr->det_ts : 0ull};
         ZL_CUDA(cudaMemcpyAsync(L.d_wmeta, L.h_wmeta, sizeof(WireMeta) * (L.pb.maxn + 1), cudaMemcpyHostToDevice, L.stream));
     }
-    ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
+    // Device time of the step (getStatus: avg_device_time_ms) from a SAMPLE of the batches: the two event records around the
+    // graph launch cost 9 us per call on the b=1 path (measured: p50 0.3546 -> 0.3457 ms without them), so only every
+    // 256th batch of a lane (and its second) is timed.  ZL_TIMING_EVERY=1 times every batch.
+    static const int timing_every = [] { const char* e = getenv("ZL_TIMING_EVERY"); const int v = e ? atoi(e) : 256; return v > 0 ? v : 256; }();
+    const uint64_t kth = L.batches_run++;                 // the lane's first batch (graph capture inside) is never the sample
+    const bool timed = kth == 1 || (kth >= (uint64_t)timing_every && kth % (uint64_t)timing_every == 0);
+    if (timed) ZL_CUDA(cudaEventRecord(L.ev0, L.stream));
     ZL_TRY(launch_batch(L, B, want_raw));
-    ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
+    if (timed) ZL_CUDA(cudaEventRecord(L.ev1, L.stream));
     ZL_CUDA(cudaStreamSynchronize(L.stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, L.ev0, L.ev1);
-    { std::lock_guard<std::mutex> g(smu); dev_ms_sum += ms; dev_ms_n++; st_batches++; }
+    {
+        float ms = 0;
+        if (timed) cudaEventElapsedTime(&ms, L.ev0, L.ev1);
+        std::lock_guard<std::mutex> g(smu);
+        if (timed) { dev_ms_sum += ms; dev_ms_n++; }
+        st_batches++;
+    }
 
     const uint32_t* hdr = (const uint32_t*)L.h_result;
     const uint32_t total = hdr[0];

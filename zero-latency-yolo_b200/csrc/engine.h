@@ -75,6 +75,8 @@ struct Lane {
     HeadLevel levels[3];
     // pinned host memory
     FrameDesc* h_descs = nullptr;
+    uint32_t* nms_host_out = nullptr;            // set by run_ops: the NMS of a one-frame step writes the result block here itself
+    uint64_t batches_run = 0;                   // batches this lane has launched (the device-time statistic samples every 256th)
     std::vector<FrameDesc> descs_on_device;     // what d_descs holds (empty = unknown): a batch with the same geometry as the last one skips the copy
     uint8_t* h_result = nullptr; size_t h_result_bytes = 0;
     uint8_t* h_frames = nullptr;                // staging for non-pinned sync inputs: [max_batch] slots

@@ -147,7 +147,10 @@ int32_t launch_decode_filter(cudaStream_t st, const HeadLevel lv[3], int32_t n, 
 // allow_cluster: batches of up to 72 frames may deal a frame's classes to the 2 / 4 / 8 CTAs of a thread-block cluster (the
 // stand-alone decode + NMS call: 2-6x shorter at small batches).  The engine's graph-captured step passes false: measured
 // on B200 the split is neutral there (the step's throughput depends on the NMS's SM-time, not on its span).
-int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb, bool allow_cluster = false);
+// host_result (one-frame launches only): pinned host copy of the result block {header, records} the CTA writes itself, so
+// that the b=1 step needs no device-to-host copy node.
+int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb, bool allow_cluster = false,
+                   uint32_t* host_result = nullptr);
 int32_t nms_configure();   // one-time cudaFuncSetAttribute calls
 
 // model.22.cv2.l.2 + model.22.cv3.l.2 (the two last 1x1 convs of every level) + D1 + F1 in one persistent tcgen05 kernel

@@ -392,7 +392,7 @@ template <bool CL>
 __global__ void __launch_bounds__(kNmsThreads, ZL_NMS_MINBLOCKS)
 nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
            float4* __restrict__ sorted_box, const uint32_t* __restrict__ cand_count, uint32_t* __restrict__ header,
-           DevDet* __restrict__ dets, int maxn, uint32_t cap)
+           DevDet* __restrict__ dets, int maxn, uint32_t cap, uint32_t* __restrict__ host_hdr)
 {
     extern __shared__ __align__(16) uint8_t nms_smem[];
     __shared__ uint32_t s_warp_tot[32];
@@ -433,7 +433,10 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     // n_all is the same in every rank, so the whole cluster takes the same branch (no rank waits on a barrier alone).
     const bool split = CL && S > 1 && n_all > kNmsSplitMin;
     if (n_all == 0 || (!split && rank != 0)) {
-        if (tid == 0 && rank == 0) { h_cnt[f] = 0; h_off[f] = 0; }
+        if (tid == 0 && rank == 0) {
+            h_cnt[f] = 0; h_off[f] = 0;
+            if (host_hdr) { host_hdr[0] = 0u; host_hdr[4] = 0u; host_hdr[4 + maxn] = 0u; }      // single-frame launch (see below)
+        }
         return;
     }
     uint64_t* gkeys = keys_g + (size_t)f * key_pitch;
@@ -834,6 +837,10 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
             s_base = atomicAdd(h_total, kept_total);
             h_cnt[f] = kept_total;
             h_off[f] = s_base;
+            // host_hdr != nullptr: a ONE-frame launch of the engine's b=1 step.  The CTA writes the result block (header +
+            // records, the layout of the device block) straight into the lane's pinned host buffer: the device-to-host copy
+            // node behind the NMS (~4 us on the latency path) is not needed.
+            if (host_hdr) { host_hdr[0] = s_base + kept_total; host_hdr[4] = kept_total; host_hdr[4 + maxn] = s_base; }
         }
         __syncthreads();
     } else if constexpr (CL) {
@@ -876,6 +883,7 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
                 DevDet d;
                 d.x = b.x; d.y = b.y; d.w = b.z; d.h = b.w; d.conf = key_conf(k); d.cls = key_class(k);
                 dets[slot] = d;
+                if (host_hdr) reinterpret_cast<DevDet*>(host_hdr + 4 + 2 * maxn)[slot] = d;
             }
         }
         running += tot;
@@ -1009,13 +1017,14 @@ static int nms_split_for(int n, bool keys_fit_smem, bool allow_cluster)
     return n <= 16 ? 8 : (n <= 32 ? 4 : (n <= 72 ? 2 : 1));
 }
 
-int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb, bool allow_cluster)
+int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const PostBuffers& pb, bool allow_cluster, uint32_t* host_result)
 {
+    if (host_result && n != 1) ZL_FAIL(ZL_INVALID_ARGUMENT, "nms: the direct host result block is for one-frame launches");
     // smem plan: keys (only as many as can ever be needed) + removed bitmask (A bits)
     int key_cap = 1;
     while (key_cap < A) key_cap <<= 1;
     if (key_cap > 16384) key_cap = 0;              // too many to sort in smem -> sort in global memory
-    const int split = nms_split_for(n, key_cap != 0, allow_cluster);
+    const int split = host_result ? 1 : nms_split_for(n, key_cap != 0, allow_cluster);
     const size_t mask_bytes = ((size_t)ceil_div(A, 32) * 4 + 15) & ~(size_t)15;
     size_t smem = (size_t)key_cap * 8 + mask_bytes;
     if (smem > 200 * 1024) ZL_FAIL(ZL_INVALID_ARGUMENT, "nms: anchor count too large for the suppression bitmask");
@@ -1048,7 +1057,7 @@ int32_t launch_nms(cudaStream_t st, int32_t n, int32_t A, float iou_thr, const P
     }
     cfg.attrs = attr; cfg.numAttrs = na;
     ZL_CUDA(cudaLaunchKernelEx(&cfg, split > 1 ? nms_kernel<true> : nms_kernel<false>, A, iou_thr, key_cap, box_cap, pb.key_pitch, pb.keys, (const float4*)pb.box_by_anchor, pb.sorted_box,
-                               (const uint32_t*)pb.cand_count, pb.header, pb.dets, pb.maxn, pb.cap));
+                               (const uint32_t*)pb.cand_count, pb.header, pb.dets, pb.maxn, pb.cap, host_result));
     static const char* dbg = getenv("ZL_NMS_DEBUG");
     if (dbg) {
         // debug aid: phase stamps of frame <ZL_NMS_DEBUG> of the PREVIOUS launch on this stream (the frame index is armed below)
