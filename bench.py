@@ -72,6 +72,12 @@ class ClockSampler:
             self._nvml = pynvml
             self._h = pynvml.nvmlDeviceGetHandleByIndex(self._phys_index())
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            for _ in range(3):            # the first queries after nvmlInit take tens of ms (a whole timed region): take them here
+                pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+                try:
+                    pynvml.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
             self.src = "nvml"
         except Exception:
             self._nvml = None
