@@ -275,7 +275,7 @@ __device__ __forceinline__ bool epilogue_role(const HaloParams& p, const EpiCtx&
                     a[4 * i + 2] = __uint_as_float(vc[4 * i + 2]) + b4.z; a[4 * i + 3] = __uint_as_float(vc[4 * i + 3]) + b4.w;
                 }
                 if (act) {
-                    if (p.silu_tanh) {
+                    if (FAST || p.silu_tanh) {                   // the fast variants are tanh-only: the two-MUFU form (an A/B switch) takes the generic body
 #pragma unroll
                         for (int i = 0; i < 16; ++i) a[i] = silu_tanh(a[i]);
                     } else {
@@ -1011,7 +1011,7 @@ int32_t conv_halo_launch(cudaStream_t st, const ConvHaloOp& o, int num_sms, unsi
     p.direct_store = (direct_ok && (direct_env == 2 || (direct_env == 1 && o.mode == 1 && !o.y_f32) ||
                                     (direct_env == 3 && !o.y_f32 && (o.mode == 1 || slice_off_line)))) ? 1 : 0;
     p.epi_variant = 6;
-    if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC")) {
+    if (o.y_tma && o.Cout % 16 == 0 && !getenv("ZL_EPI_GENERIC") && (o.silu_tanh || !o.act)) {   // ZL_SILU=exp: generic body (it keeps both SiLU forms; 2 KB of never-run code sat in every fast loop)
         const int fmt = o.f16 ? 3 : 0;
         if (!o.y_f32 && o.act && !o.res) p.epi_variant = fmt + 0;
         else if (!o.y_f32 && o.act && o.res && o.r_vec) p.epi_variant = fmt + 1;
