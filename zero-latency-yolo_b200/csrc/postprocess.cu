@@ -275,9 +275,6 @@ decode_filter_kernel(const HeadLevel l0, const HeadLevel l1, const HeadLevel l2,
 
 // ============================================================= N1: NMS
 constexpr int kNmsThreads = 1024;
-#ifndef ZL_NMS_MINBLOCKS
-#define ZL_NMS_MINBLOCKS 1
-#endif
 constexpr int kMaxLargeSeg = 512;
 #ifndef ZL_NMS_W
 #define ZL_NMS_W 4
@@ -389,7 +386,7 @@ __device__ __forceinline__ uint32_t resolve_rows(uint32_t und, uint32_t row, int
 // CL = false is the instantiation of the engine's step (one CTA per frame, no cluster code at all); CL = true the one of
 // the stand-alone decode + NMS call at small batches.
 template <bool CL>
-__global__ void __launch_bounds__(kNmsThreads, ZL_NMS_MINBLOCKS)
+__global__ void __launch_bounds__(kNmsThreads)
 nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pitch, uint64_t* __restrict__ keys_g, const float4* __restrict__ box_by_anchor,
            float4* __restrict__ sorted_box, const uint32_t* __restrict__ cand_count, uint32_t* __restrict__ header,
            DevDet* __restrict__ dets, int maxn, uint32_t cap, uint32_t* __restrict__ host_hdr)
