@@ -590,9 +590,9 @@ nms_kernel(int A, float iou_thr, int key_cap_smem, int box_cap_smem, int key_pit
     // ---- greedy per-class suppression (applyNMS, onnx_engine.cpp:856-875), exact, in two phases.
     // A class segment is a run of equal class ids in the sorted list.  The reference's loop is a serial chain over the
     // KEPT candidates of a segment; each link tests the still-alive later candidates, which is the parallel part.
-    //  phase 1: segments of <= 32 candidates — one warp each, boxes in registers, links cost one shuffle + one IoU;
-    //  phase 2: larger segments — groups of 4 warps pull segments from a queue; per link the 128 threads sweep the
-    //           remaining candidates and meet on a named barrier.
+    //  phase 1: segments of <= 32 candidates — one warp each: every lane builds its row of the suppression matrix (eight
+    //           independent IoU tests in flight), then the chain is settled in rounds of two ballots (resolve_rows);
+    //  phase 2: larger segments in blocks of 32 by teams of 128 ... 1024 threads (below).
     if (n > 1) {
         if (tid == 0) { s_nlarge = 0; s_qhead = 0; }
         __syncthreads();
